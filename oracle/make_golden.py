@@ -1,0 +1,121 @@
+"""TEST INFRASTRUCTURE — run ONLY in the build container (needs /root/reference):
+
+    python oracle/make_golden.py
+
+1. imports the real reference (via oracle/_refshim.py), loads deterministic synthetic
+   parameters into it (numpy RandomState seeds, oracle.backbone_oracle.synth_params);
+2. checks oracle/backbone_oracle.py and oracle/voxel_oracle.py against it (asserts);
+3. writes the REFERENCE's outputs to tests/golden/*.npz (small: strided subsamples +
+   full-tensor sums for the big configs), so the GPU box — which has no /root/reference —
+   can test both the oracle and the CUDA path against the reference.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import _refshim  # noqa: E402
+
+_refshim.install()
+from oracle import backbone_oracle as bo  # noqa: E402
+from oracle import voxel_oracle as vo  # noqa: E402
+from tests.golden_configs import BACKBONE_CASES, VOXEL_CASES, spec_of, make_voxel_events  # noqa: E402
+
+from models.detection.recurrent_backbone import build_recurrent_backbone  # noqa: E402
+from data.utils.representations import StackedHistogram  # noqa: E402
+
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+
+
+def ref_cfg(spec: bo.BackboneSpec):
+    return _refshim.DictConfig(dict(
+        name='MaxViTRNN', compile=dict(enable=False, args=dict(mode='reduce-overhead')),
+        input_channels=spec.input_channels, enable_masking=spec.enable_masking,
+        partition_split_32=1, embed_dim=spec.embed_dim, dim_multiplier=list(spec.dim_multiplier),
+        num_blocks=list(spec.num_blocks), T_max_chrono_init=[4, 8, 16, 32],
+        stem=dict(patch_size=spec.patch_size),
+        stage=dict(downsample=dict(type='patch', overlap=spec.overlap, norm_affine=True),
+                   attention=dict(use_torch_mha=False, partition_size=tuple(spec.partition_size),
+                                  dim_head=spec.dim_head, attention_bias=True, mlp_activation='gelu',
+                                  mlp_gated=False, mlp_bias=True, mlp_ratio=4, drop_mlp=0, drop_path=0,
+                                  ls_init_value=spec.ls_init_value, norm_eps=spec.norm_eps),
+                   lstm=dict(dws_conv=spec.dws_conv, dws_conv_only_hidden=spec.dws_conv_only_hidden,
+                             dws_conv_kernel_size=spec.dws_conv_kernel_size, drop_cell_update=0))))
+
+
+def sub(t: torch.Tensor, stride: int) -> np.ndarray:
+    return t.contiguous().reshape(-1)[::stride].numpy().copy()
+
+
+def run_backbone_case(name, case):
+    spec = spec_of(case)
+    torch.manual_seed(0)
+    ref = build_recurrent_backbone(ref_cfg(spec)).eval()
+    params = bo.synth_params(spec, case['seed'], case.get('gamma_mode', 'uniform'))
+    ref_keys = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    assert ref_keys == bo.param_shapes(spec), 'oracle.param_shapes disagrees with the reference'
+    ref.load_state_dict(params, strict=True)
+    b, h, w, L = case['batch'], case['height'], case['width'], case['steps']
+    stride = case.get('sub', 1)
+    out = {}
+    r_states, o_states = None, None
+    worst = 0.0
+    with torch.no_grad():
+        for step in range(L):
+            x = bo.synth_events_tensor(case['seed'] * 1000 + step, b, spec.input_channels, h, w).float()
+            mask = None
+            if spec.enable_masking:
+                rs = np.random.RandomState(case['seed'] + 77 + step)
+                mask = torch.from_numpy(rs.uniform(size=(b, h // 4, w // 4)) < 0.2)
+            r_out, r_states = ref(x, r_states, mask)
+            o_out, o_states = bo.backbone_forward(x, o_states, params, spec, mask)
+            if case.get('reset_at') == step:       # harness-style in-place reset of sample 0
+                for (hh, cc) in r_states:
+                    hh[0] = 0
+                    cc[0] = 0
+                for (hh, cc) in o_states:
+                    hh[0] = 0
+                    cc[0] = 0
+            for s in range(4):
+                for a, bb in ((r_out[s + 1], o_out[s + 1]), (r_states[s][0], o_states[s][0]),
+                              (r_states[s][1], o_states[s][1])):
+                    worst = max(worst, float((a - bb).abs().max()))
+            if step in case.get('save_steps', [L - 1]):
+                for s in range(4):
+                    hh, cc = r_states[s]
+                    out[f'step{step}_h{s}'] = sub(hh, stride)
+                    out[f'step{step}_c{s}'] = sub(cc, stride)
+                    out[f'step{step}_h{s}_sum'] = np.float64(hh.double().sum().item())
+                    out[f'step{step}_c{s}_sum'] = np.float64(cc.double().sum().item())
+                    out[f'step{step}_h{s}_abssum'] = np.float64(hh.double().abs().sum().item())
+    assert worst < 2e-5, (name, worst)
+    np.savez_compressed(os.path.join(GOLD, f'backbone_{name}.npz'), **out)
+    print(f'backbone {name}: oracle-vs-reference max abs diff {worst:.2e}; '
+          f'{sum(v.size for v in out.values())} values saved')
+
+
+def run_voxel_case(name, case):
+    x, y, p, t = make_voxel_events(case)
+    out = {}
+    for fast in (True, False):
+        sh = StackedHistogram(case['bins'], case['height'], case['width'], case.get('cutoff', 10), fast)
+        ref = sh.construct(*(torch.from_numpy(a) for a in (x, y, p, t))).numpy()
+        mine = vo.stacked_histogram(x, y, p, t, case['bins'], case['height'], case['width'],
+                                    case.get('cutoff', 10), fast)
+        assert ref.dtype == np.uint8 and ref.shape == (2 * case['bins'], case['height'], case['width'])
+        assert np.array_equal(ref, mine), name
+        out['fast' if fast else 'slow'] = ref
+    np.savez_compressed(os.path.join(GOLD, f'voxel_{name}.npz'), **out)
+    print(f'voxel {name}: bit-exact; n={len(x)} max={out["fast"].max()}')
+
+
+if __name__ == '__main__':
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    for n, c in VOXEL_CASES.items():
+        run_voxel_case(n, c)
+    for n, c in BACKBONE_CASES.items():
+        run_backbone_case(n, c)

@@ -1,0 +1,66 @@
+"""Golden-fixture case table shared by oracle/make_golden.py (which mints tests/golden/*.npz
+from the real reference) and the tests (which replay the same seeded inputs)."""
+import numpy as np
+
+from oracle import backbone_oracle as bo
+from oracle import voxel_oracle as vo
+
+# partition_size = (H/32, W/32) * 1/partition_split_32  (config/modifier.py:36-41)
+BACKBONE_CASES = {
+    # tiny, every stage small; P=6 (exercises heavy window padding 6->64)
+    'tiny_p6': dict(embed_dim=32, dim_head=32, height=64, width=96, partition=(2, 3), batch=2,
+                    steps=3, seed=11, save_steps=[0, 2]),
+    # RVT-S style head dim 24, P=20
+    'small_dh24': dict(embed_dim=48, dim_head=24, height=128, width=160, partition=(4, 5), batch=1,
+                       steps=2, seed=12),
+    # depthwise 3x3 on the hidden state only (reference default when dws_conv=True)
+    'dws_hidden': dict(embed_dim=32, dim_head=32, height=64, width=96, partition=(2, 3), batch=2,
+                       steps=3, seed=13, dws_conv=True, dws_only_hidden=True, reset_at=1),
+    # depthwise 3x3 on cat(x, h)
+    'dws_xh': dict(embed_dim=32, dim_head=32, height=64, width=96, partition=(2, 3), batch=1,
+                   steps=2, seed=14, dws_conv=True, dws_only_hidden=False),
+    # reference-default LayerScale init 1e-5 + token masking in stage 1
+    'ls_init_mask': dict(embed_dim=32, dim_head=32, height=64, width=96, partition=(2, 3), batch=2,
+                         steps=2, seed=15, gamma_mode='init', enable_masking=True),
+    # BASELINE configs[0]: RVT-Tiny Gen1 256x320 (P=80), bs 1, seq_len 5
+    'rvt_t_gen1': dict(embed_dim=32, dim_head=32, height=256, width=320, partition=(8, 10), batch=1,
+                       steps=5, seed=16, sub=7),
+    # RVT-Base 1Mpx 384x640 (P=60), bs 1, 2 steps
+    'rvt_b_1mpx': dict(embed_dim=64, dim_head=32, height=384, width=640, partition=(6, 10), batch=1,
+                       steps=2, seed=17, sub=13),
+}
+
+
+def spec_of(case) -> bo.BackboneSpec:
+    return bo.BackboneSpec(embed_dim=case['embed_dim'], dim_head=case['dim_head'],
+                           partition_size=tuple(case['partition']),
+                           dws_conv=case.get('dws_conv', False),
+                           dws_conv_only_hidden=case.get('dws_only_hidden', True),
+                           enable_masking=case.get('enable_masking', False))
+
+
+VOXEL_CASES = {
+    'uniform': dict(n=200000, height=72, width=128, bins=10, seed=1),
+    'hot': dict(n=300000, height=48, width=64, bins=10, seed=2, hot_fraction=0.3, hot_pixels=2),
+    'single': dict(n=1, height=10, width=12, bins=10, seed=3),
+    'same_ts': dict(n=1000, height=16, width=16, bins=10, seed=4, same_timestamp=True),
+    'empty': dict(n=0, height=8, width=8, bins=10, seed=5),
+    'bins3_cut255': dict(n=100000, height=20, width=24, bins=3, seed=6, cutoff=None,
+                         hot_fraction=0.5, hot_pixels=1),
+    'big_t': dict(n=50000, height=32, width=32, bins=10, seed=7, t_offset=1 << 40, t_span=(1 << 31) + 12345),
+}
+
+
+def make_voxel_events(case):
+    n = case['n']
+    if n == 0:
+        z = np.zeros(0, np.int64)
+        return z, z.copy(), z.copy(), z.copy()
+    x, y, p, t = vo.synth_events(case['seed'], n, case['height'], case['width'],
+                                 t_span=case.get('t_span', 50000),
+                                 hot_fraction=case.get('hot_fraction', 0.0),
+                                 hot_pixels=case.get('hot_pixels', 16))
+    if case.get('same_timestamp'):
+        t = np.full(n, 12345, np.int64)
+    t = t + np.int64(case.get('t_offset', 0))
+    return x, y, p, t

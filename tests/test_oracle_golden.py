@@ -1,0 +1,68 @@
+"""CPU: the oracle restatements reproduce the REFERENCE's committed golden outputs
+(minted by oracle/make_golden.py from /root/reference)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import backbone_oracle as bo
+from oracle import voxel_oracle as vo
+from tests.golden_configs import BACKBONE_CASES, VOXEL_CASES, make_voxel_events, spec_of
+from tests.helpers import check_against_golden, GOLD
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize('name', list(BACKBONE_CASES))
+def test_backbone_oracle_matches_reference_golden(name):
+    case = BACKBONE_CASES[name]
+    spec = spec_of(case)
+    params = bo.synth_params(spec, case['seed'], case.get('gamma_mode', 'uniform'))
+
+    def step(x, states, mask):
+        with torch.no_grad():
+            return bo.backbone_forward(x, states, params, spec, mask)
+
+    worst = check_against_golden(name, case, step, tol=2e-5)
+    assert worst < 2e-5
+
+
+def test_param_counts_match_paper():
+    """SURVEY.md Appendix A sanity anchors: backbone params B/S/T."""
+    for embed, dh, n in ((64, 32, 12_784_768), (48, 24, 7_209_312), (32, 32, 3_220_032)):
+        shp = bo.param_shapes(bo.BackboneSpec(embed_dim=embed, dim_head=dh))
+        assert sum(int(np.prod(s)) for s in shp.values()) == n
+
+
+@pytest.fixture(scope='module')
+def c_oracle():
+    subprocess.check_call(['make', '-C', os.path.join(ROOT, 'oracle')], stdout=subprocess.DEVNULL)
+    return ctypes.CDLL(os.path.join(ROOT, 'oracle', '_build', 'libvoxel_oracle.so'))
+
+
+@pytest.mark.parametrize('name', list(VOXEL_CASES))
+@pytest.mark.parametrize('fast', [True, False])
+def test_voxel_oracles_match_reference_golden(name, fast, c_oracle):
+    case = VOXEL_CASES[name]
+    gold = np.load(os.path.join(GOLD, f'voxel_{name}.npz'))['fast' if fast else 'slow']
+    x, y, p, t = make_voxel_events(case)
+    got = vo.stacked_histogram(x, y, p, t, case['bins'], case['height'], case['width'],
+                               case.get('cutoff', 10), fast)
+    assert got.dtype == np.uint8 and np.array_equal(got, gold)
+    out = np.zeros(gold.size, np.uint8)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    cut = case.get('cutoff', 10)
+    rc = c_oracle.rvt_oracle_stacked_histogram(P(x), P(y), P(p), P(t), ctypes.c_int64(len(x)),
+                                               case['bins'], case['height'], case['width'],
+                                               0 if cut is None else cut, int(fast), P(out))
+    assert rc == 0 and np.array_equal(out.reshape(gold.shape), gold)
+
+
+def test_time_bin_fp32_edges():
+    """t == t1 clamps to the last bin; dt == 0 -> max(dt,1) (representations.py:102-109)."""
+    t = np.array([0, 4999, 5000, 49999, 50000], np.int64)
+    assert vo.time_bin_index(t, 10).tolist() == [0, 0, 1, 9, 9]
+    assert vo.time_bin_index(np.array([7, 7, 7], np.int64), 10).tolist() == [0, 0, 0]
