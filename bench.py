@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""bench.py — RVT hot-path throughput on B200 (contract: task statement §④ + base contract).
+
+Workload (BASELINE.json configs[1]): RVT-Base 1Mpx, event tensor 8 x 20 x 360 x 640 (uint8, zero
+padding to the model's 384x640 folded into the stem), seq_len 21, states carried, inference.
+One *step* = one 21-timestep sequence for the local batch (8 samples/GPU) = 168 frames/GPU.
+Batch-sharded over N GPUs with no data-path collective (weak scaling).
+
+  value : frames/s, whole job, inputs resident in HBM (774 MB of uint8 sequences > L2)
+  e2e   : frames/s through rvt_b200.RNNDetector.forward with HOST (pinned) uint8 inputs copied
+          H2D every timestep and the stage-4 feature map read back D2H every timestep
+  --impl reference : the reference's CPU path (oracle port, torch fp32, all host threads) on a
+          bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'RVT-B 1Mpx seq_len=21 backbone frames/sec'
+B_PER_GPU, SEQ_LEN, IN_C, IN_H, IN_W, PAD_H, PAD_W = 8, 21, 20, 360, 640, 384, 640
+LAUNCHES_PER_TIMESTEP = 4 * (1 + 2 * (3 + 2) + 1)     # per stage: conv+LN, 2 x (qkv, core, proj, fc1, fc2), lstm
+GFLOP_PER_FRAME = 20.62                                 # BASELINE.md §3 (algorithmic, MAC = 2 FLOP)
+
+
+def rvt_b_spec():
+    from oracle import backbone_oracle as bo
+    return bo.BackboneSpec(embed_dim=64, dim_head=32, partition_size=(6, 10))
+
+
+def make_cfg(spec):
+    from tests.test_host_cpu import make_cfg as mk
+    return mk(spec)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def cpu_reference_fps(n_timesteps, batch, threads):
+    """The reference's CPU implementation of the path (oracle port: torch fp32 eager ops, the same
+    ATen kernels the reference dispatches to), states carried; returns frames/s."""
+    from oracle import backbone_oracle as bo
+    spec = rvt_b_spec()
+    torch.set_num_threads(threads)
+    params = bo.synth_params(spec, 0)
+    xs = [torch.nn.functional.pad(bo.synth_events_tensor(i, batch, IN_C, IN_H, IN_W).float(),
+                                  (0, PAD_W - IN_W, 0, PAD_H - IN_H)) for i in range(n_timesteps + 1)]
+    st = None
+    with torch.inference_mode():
+        _, st = bo.backbone_forward(xs[0], st, params, spec)      # warm-up timestep
+        t0 = time.perf_counter()
+        for i in range(n_timesteps):
+            _, st = bo.backbone_forward(xs[1 + i], st, params, spec)
+        dt = time.perf_counter() - t0
+    return batch * n_timesteps / dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    n_ts = 2                     # bounded sample: 2 timesteps x 8 samples per "step"
+    vals = []
+    for _ in range(max(1, min(args.steps, 3))):
+        vals.append(cpu_reference_fps(n_ts, B_PER_GPU, cores))
+    v = sum(vals) / len(vals)
+    sample = f'{n_ts} timesteps x batch {B_PER_GPU} of the 21-timestep sequence per step (states carried), fp32'
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'frames/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * B_PER_GPU * SEQ_LEN / v,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'RVT-Base 1Mpx 360x640 (padded 384x640) T=10 seq_len=21 bs=8 inference, CPU'},
+        'cpu_baseline': {'value': v, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': v, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    import rvt_b200
+    from oracle import backbone_oracle as bo     # synthetic parameter / input generators only
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    spec = rvt_b_spec()
+    model = rvt_b200.RNNDetector(make_cfg(spec))
+    model.load_state_dict(bo.synth_params(spec, 0), strict=True)
+    model = model.to(dev).eval()
+    model.pad_to_hw = (PAD_H, PAD_W)
+
+    # synthetic uint8 event tensors: SEQ_LEN timesteps, resident on the device (37 MB each)
+    g = torch.Generator(device='cpu').manual_seed(1234 + rank)
+    seq_host = (torch.randint(1, 11, (SEQ_LEN, B_PER_GPU, IN_C, IN_H, IN_W), generator=g, dtype=torch.uint8) *
+                (torch.rand((SEQ_LEN, B_PER_GPU, IN_C, IN_H, IN_W), generator=g) < 0.1)).pin_memory()
+    seq_dev = seq_host.to(dev)
+
+    def run_sequence_resident():
+        st = None
+        for tstep in range(SEQ_LEN):
+            _, st = model(seq_dev[tstep], st)
+        return st
+
+    stage_buf = [torch.empty((B_PER_GPU, IN_C, IN_H, IN_W), dtype=torch.uint8, device=dev) for _ in range(2)]
+    feat_host = torch.empty((B_PER_GPU, 512, PAD_H // 32, PAD_W // 32), dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(dev)
+
+    def run_sequence_e2e():
+        """Public API with host buffers: H2D of each timestep's uint8 tensor (double-buffered on a
+        copy stream), forward, D2H of the stage-4 feature map every timestep."""
+        st = None
+        main_s = torch.cuda.current_stream(dev)
+        ev_ready = [torch.cuda.Event() for _ in range(2)]
+        ev_free = [torch.cuda.Event() for _ in range(2)]
+        with torch.cuda.stream(copy_stream):
+            stage_buf[0].copy_(seq_host[0], non_blocking=True)
+            ev_ready[0].record(copy_stream)
+        for tstep in range(SEQ_LEN):
+            cur, nxt = tstep & 1, (tstep + 1) & 1
+            if tstep + 1 < SEQ_LEN:
+                with torch.cuda.stream(copy_stream):
+                    if tstep >= 1:
+                        copy_stream.wait_event(ev_free[nxt])
+                    stage_buf[nxt].copy_(seq_host[tstep + 1], non_blocking=True)
+                    ev_ready[nxt].record(copy_stream)
+            main_s.wait_event(ev_ready[cur])
+            out, st = model(stage_buf[cur], st)
+            ev_free[cur].record(main_s)
+            feat_host.copy_(out[4], non_blocking=True)
+        return st
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        barrier()
+        return ms
+
+    with torch.inference_mode():
+        for _ in range(max(args.warmup, 3)):
+            run_sequence_resident()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        ms = timed(run_sequence_resident, args.steps)
+        clocks = sampler.stop() if rank == 0 else None
+        for _ in range(2):
+            run_sequence_e2e()
+        ms_e2e = timed(run_sequence_e2e, args.steps)
+
+    frames = B_PER_GPU * SEQ_LEN * args.steps * world
+    value = frames / (ms * 1e-3)
+    e2e = frames / (ms_e2e * 1e-3)
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
+        ach_tf = value / world * GFLOP_PER_FRAME / 1e3
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic',
+            'config': {'workload': 'RVT-Base 1Mpx 8x20x360x640 uint8 (model res 384x640) seq_len=21 bs=8/GPU '
+                                   'inference, states carried', 'frames_per_step': B_PER_GPU * SEQ_LEN,
+                       'l2_policy': 'inputs larger than L2 (774 MB of uint8 sequences per GPU)',
+                       'parallelism': f'batch-sharded x{world}, no collective'},
+            'e2e': {'value': e2e, 'unit': 'frames/s',
+                    'h2d_bytes_per_step': SEQ_LEN * B_PER_GPU * IN_C * IN_H * IN_W,
+                    'd2h_bytes_per_step': SEQ_LEN * feat_host.numel() * 4},
+            'gpu_launches': LAUNCHES_PER_TIMESTEP * SEQ_LEN * args.steps,
+            'clocks': clocks,
+            'roofline': {'bound': 'tensor', 'achieved': ach_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                         'frac': ach_tf / peak_tf, 'traffic': None,
+                         'note': 'whole-step algorithmic FLOPs (20.62 GFLOP/frame) / step time vs measured '
+                                 'sustained bf16 peak; per-kernel table in profiles/'},
+        }
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count()
+            v = cpu_reference_fps(2, B_PER_GPU, cores)
+            line['cpu_baseline'] = {'value': v, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
+                                    'sample': '2 timesteps x batch 8 (after 1 warm-up timestep), fp32 torch CPU'}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,95 @@
+/* rvt_b200 — C-ABI of the B200-native (sm_100a) RVT hot path.
+ *
+ * The reference (uzh-rpg/RVT) is pure Python/PyTorch and has no FFI of its own; every entry
+ * point below replaces the body of one reference function on the hot path
+ * and is what a ctypes/cffi binding on the reference side would bind.
+ * Plain pointers and sizes only: all pointers are DEVICE pointers unless noted, buffers are
+ * caller-allocated (no allocation inside), `stream` is a cudaStream_t passed as void*.
+ * Every function returns 0 on success or a cudaError_t / negative argument-error code;
+ * rvt_error_string() renders it.  Launches are asynchronous on `stream`.
+ *
+ * Tensors are channels-last ("NHWC", token-major): x[b][y][x][c].  fp32 residual stream and
+ * LSTM states; fp16 tensor-core operands with fp32 accumulation.
+ */
+#ifndef RVT_B200_H_
+#define RVT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RVT_B200_ABI_VERSION 1
+
+int rvt_abi_version(void);
+const char* rvt_error_string(int code);
+
+/* ---- tiling contract shared with the host-side weight packer (rvt_b200/packing.py) ---- */
+/* N-tile (columns per CTA) used for a Linear with n_total output features. */
+int rvt_tile_n(int n_total);
+/* Channels per CTA for the Conv-LSTM gate GEMM (tile = [f|i|o|g] x cw columns). */
+int rvt_lstm_cw(int dim);
+/* Rows one partition group occupies in a 128-row tile (64 or 128; <0 if P > 128). */
+int rvt_rows_per_group(int partition_tokens);
+/* Rows of the attention scratch matrices for B x H x W tokens and partition (ph, pw). */
+int64_t rvt_attention_scratch_rows(int batch, int height, int width, int ph, int pw);
+
+/* ---- a10: StackedHistogram.construct  (data/utils/representations.py:76-121) ----------
+ * x, y, pol, t: int64[n] device arrays (t sorted).  counts: u32[2*bins*H*W] scratch that must
+ * be zero on entry and is left zero on exit.  out: u8[2*bins*H*W] laid out [2*bins][H][W],
+ * channel = pol*bins + t_idx.  err_flag: device int, OR-ed with 1 (time not sorted),
+ * 2 (pol outside {0,1}), 4 (coordinate outside the frame); never cleared here. n == 0 -> zeros. */
+int rvt_stacked_histogram(const int64_t* x, const int64_t* y, const int64_t* pol, const int64_t* t,
+                          int64_t n, int bins, int height, int width, int count_cutoff, int fastmode,
+                          uint32_t* counts, uint8_t* out, int* err_flag, void* stream);
+
+/* ---- a3: ConvDownsampling_Cf2Cl.forward  (models/layers/maxvit/maxvit.py:143-178) -------
+ * Strided conv (no bias) + LayerNorm(C_out) [+ mask token, maxvit_rnn.py:174-176].
+ * in: in_nchw ? [B,Cin,Hin,Win] : [B,Hin,Win,Cin]; in_dtype 0=f32 1=u8 2=f16 (u8/f16 only
+ * with in_nchw).  Rows/cols of the virtual input beyond (Hin,Win) read as zero, which folds
+ * the harness' zero padding (utils/padding.py:29-44) into the conv.  out: f32 [B,Hout,Wout,Cout].
+ * w_packed: rvt_b200.packing.pack_conv_weight().  ln_w/ln_b may be NULL (norm_affine=False).
+ * token_mask: u8 [B,Hout,Wout] or NULL; mask_token: f32 [Cout]. */
+int rvt_downsample_cf2cl(const void* in, int in_dtype, int in_nchw, int batch, int cin, int hin, int win,
+                         int ksize, int stride, int pad, int hout, int wout, int cout,
+                         const void* w_packed, const float* ln_w, const float* ln_b, float eps,
+                         const uint8_t* token_mask, const float* mask_token, float* out, void* stream);
+
+/* ---- a4-a7: attention half of PartitionAttentionCl.forward  (maxvit.py:252-268, 273-354) -
+ * x <- x + gamma1 * proj(attn(partition(norm1(x))))   in place, x: f32 [B,H,W,C].
+ * grid = 0: window partition, 1: grid partition.  n1_w/n1_b NULL => norm1 = Identity.
+ * gamma1 NULL => LayerScale = Identity.  scratch_qkv: f16 [rows, 3C], scratch_o: f16 [rows, C]
+ * with rows = rvt_attention_scratch_rows(). */
+int rvt_partition_attention(float* x, int batch, int height, int width, int dim, int ph, int pw, int grid,
+                            int dim_head, const float* n1_w, const float* n1_b, float eps,
+                            const void* wqkv_packed, const float* bqkv, const void* wproj_packed,
+                            const float* bproj, const float* gamma1, void* scratch_qkv, void* scratch_o,
+                            void* stream);
+
+/* ---- a8: MLP half of PartitionAttentionCl.forward  (maxvit.py:85-118, 269) --------------
+ * x <- x + gamma2 * fc2(gelu(fc1(norm2(x))))   in place, x: f32 [n_tokens, C].
+ * scratch_hidden: f16 [round_up(n_tokens,128), hidden]. */
+int rvt_mlp_block(float* x, int64_t n_tokens, int dim, int hidden, const float* n2_w, const float* n2_b,
+                  float eps, const void* w1_packed, const float* b1, const void* w2_packed, const float* b2,
+                  const float* gamma2, void* scratch_hidden, void* stream);
+
+/* ---- a9: DWSConvLSTM2d.forward  (models/layers/rnn.py:36-69) ---------------------------
+ * x, h_prev, c_prev, h_out, c_out: f32 [B,H,W,C]; h_prev/c_prev NULL => zero state.
+ * dws_mode 0: no depthwise conv; 1: depthwise ks x ks (+bias) on h_prev only; 2: on cat(x,h).
+ * dw_w: f32 [ks*ks][D] (tap-major), dw_b: f32 [D], D = C (mode 1) or 2C (mode 2).
+ * w_packed / bias_tiled: rvt_b200.packing.pack_lstm_weight() (gate-interleaved tiles). */
+int rvt_dws_conv_lstm(const float* x, const float* h_prev, const float* c_prev, int batch, int height,
+                      int width, int dim, const void* w_packed, const float* bias_tiled, const float* dw_w,
+                      const float* dw_b, int dws_mode, int dws_ks, float* h_out, float* c_out, void* stream);
+
+/* ---- building block exposed for tests: D = A W^T + b, f16 in / f16 out ------------------
+ * a: f16 [m, k] row-major (k % 8 == 0), w_packed: pack_linear_weight(W[n,k]), out: f16
+ * [round_up(m,128), n]. act: 0 none, 1 exact-erf GELU. */
+int rvt_linear_f16(const void* a, int64_t m, int k, int n, const void* w_packed, const float* bias, int act,
+                   void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RVT_B200_H_ */

@@ -160,10 +160,13 @@ def partition_attention_cl(x: Tensor, p, prefix, part, window, dim_head, eps, od
     g1 = p.get(prefix + 'ls1.gamma')
     x = x + (a * g1 if g1 is not None else a)
     m = mlp_branch(x, p, prefix, eps, od)
+    g2 = p.get(prefix + 'ls2.gamma')
+    y = x + (m * g2 if g2 is not None else m)
     if taps is not None:
         taps[prefix + 'mlp_branch'] = m
-    g2 = p.get(prefix + 'ls2.gamma')
-    return x + (m * g2 if g2 is not None else m)
+        taps[prefix + 'x_attn'] = x
+        taps[prefix + 'x_mlp'] = y
+    return y
 
 
 # ---------------------------------------------------------------------------

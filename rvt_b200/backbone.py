@@ -1,0 +1,416 @@
+"""Drop-in mirror of the reference's recurrent backbone module API.
+
+``RNNDetector`` has the constructor, ``forward`` signature, ``get_stage_dims`` /
+``get_strides`` and the exact ``state_dict`` key names/shapes of
+``models/detection/recurrent_backbone/maxvit_rnn.py:23-105`` (reference), so released
+checkpoints load strictly and ``YoloXDetector.forward_backbone`` (detector.py:34-41) can call
+it unchanged.  All arithmetic runs in the sm_100a CUDA library through the C-ABI
+(include/rvt_b200.h); PyTorch only owns device memory, streams and parameters.  There is no
+CPU or PyTorch-op fallback: non-CUDA inputs raise.
+
+Numerics contract: fp32 residual stream and (h, c) states as in the reference
+under AMP; fp16 tensor-core operands with fp32 accumulation (the reference's
+``precision: 16``); fp32 LayerNorm / softmax / gates.
+
+Internal layout is channels-last; features and states are returned as logical-NCHW views with
+channels-last strides — the same strides the reference's own (h, c) have — so the harness'
+``state[idx] = 0`` in-place resets (modules/utils/detection.py:96-113) and feature indexing
+keep working.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib, packing
+
+LstmState = Optional[Tuple[torch.Tensor, torch.Tensor]]
+LstmStates = List[LstmState]
+
+
+def _cfg_get(cfg, key, default=None):
+    if hasattr(cfg, 'get'):
+        v = cfg.get(key, default)
+        return default if v is None else v
+    return getattr(cfg, key, default)
+
+
+def _cfg(cfg, key):
+    try:
+        return cfg[key]
+    except (TypeError, KeyError):
+        return getattr(cfg, key)
+
+
+class _Params(nn.Module):
+    """A named bag of parameters (keeps the reference's state_dict key names)."""
+
+    def __init__(self, **shapes):
+        super().__init__()
+        for name, shape in shapes.items():
+            self.register_parameter(name, nn.Parameter(torch.empty(*shape)))
+
+
+def _linear(n_out, n_in, bias=True):
+    m = _Params(weight=(n_out, n_in), **({'bias': (n_out,)} if bias else {}))
+    nn.init.kaiming_uniform_(m.weight, a=math.sqrt(5))
+    if bias:
+        bound = 1 / math.sqrt(n_in)
+        nn.init.uniform_(m.bias, -bound, bound)
+    return m
+
+
+def _layernorm(c, affine=True):
+    if not affine:
+        return nn.Module()
+    m = _Params(weight=(c,), bias=(c,))
+    nn.init.ones_(m.weight)
+    nn.init.zeros_(m.bias)
+    return m
+
+
+class _LayerScale(nn.Module):
+    def __init__(self, dim, init_values):
+        super().__init__()
+        self.gamma = nn.Parameter(init_values * torch.ones(dim))
+
+
+class _Downsample(nn.Module):
+    """ConvDownsampling_Cf2Cl parameters (maxvit.py:143-172)."""
+
+    def __init__(self, dim_in, dim_out, factor, cfg):
+        super().__init__()
+        assert factor in (2, 4, 8)
+        self.overlap = bool(_cfg_get(cfg, 'overlap', True))
+        self.norm_affine = bool(_cfg_get(cfg, 'norm_affine', True))
+        dtype = _cfg_get(cfg, 'type', 'patch')
+        if dtype != 'patch':
+            raise NotImplementedError(dtype)
+        self.factor = factor
+        self.kernel_size = (factor - 1) * 2 + 1 if self.overlap else factor
+        self.padding = self.kernel_size // 2 if self.overlap else 0
+        self.conv = _Params(weight=(dim_out, dim_in, self.kernel_size, self.kernel_size))
+        nn.init.kaiming_uniform_(self.conv.weight, a=math.sqrt(5))
+        self.norm = _layernorm(dim_out, self.norm_affine)
+
+
+class _SelfAttention(nn.Module):
+    def __init__(self, dim, dim_head, bias):
+        super().__init__()
+        self.qkv = _linear(3 * dim, dim, bias)
+        self.proj = _linear(dim, dim, bias)
+
+
+class _MLP(nn.Module):
+    """Non-gated MLP parameters with the reference's Sequential nesting (maxvit.py:103-115):
+    net.0.0 = Linear(C, 4C), net.1 = Dropout, net.2 = Linear(4C, C)."""
+
+    def __init__(self, dim, ratio, bias):
+        super().__init__()
+        inner = int(dim * ratio)
+        self.net = nn.ModuleList([nn.ModuleList([_linear(inner, dim, bias), nn.Identity()]), nn.Identity(),
+                                  _linear(dim, inner, bias)])
+
+
+class _PartitionAttention(nn.Module):
+    """PartitionAttentionCl parameters (maxvit.py:193-250)."""
+
+    def __init__(self, dim, window: bool, cfg, skip_first_norm: bool):
+        super().__init__()
+        if _cfg_get(cfg, 'use_torch_mha', False):
+            raise NotImplementedError('use_torch_mha=True (TorchMHSAWrapperCl) is not built; released configs use False')
+        if _cfg_get(cfg, 'mlp_gated', False):
+            raise NotImplementedError('mlp_gated=True (GLU) is not built; released configs use False')
+        act = _cfg_get(cfg, 'mlp_activation', 'gelu')
+        if act != 'gelu':
+            raise NotImplementedError(f'mlp_activation={act}; only gelu (released configs) is built')
+        for k in ('drop_path', 'drop_mlp'):
+            if float(_cfg_get(cfg, k, 0.0)) != 0.0:
+                raise NotImplementedError(f'{k} > 0 (training-time regulariser) is not built')
+        self.window = window
+        self.eps = float(_cfg_get(cfg, 'norm_eps', 1e-5))
+        self.dim_head = int(_cfg_get(cfg, 'dim_head', 32))
+        part = _cfg(cfg, 'partition_size')
+        self.partition_size = (part, part) if isinstance(part, int) else tuple(int(v) for v in part)
+        assert len(self.partition_size) == 2
+        bias = bool(_cfg_get(cfg, 'attention_bias', True))
+        ls = float(_cfg_get(cfg, 'ls_init_value', 1e-5))
+        self.norm1 = nn.Identity() if skip_first_norm else _layernorm(dim)
+        self.self_attn = _SelfAttention(dim, self.dim_head, bias)
+        self.ls1 = _LayerScale(dim, ls) if ls > 0 else nn.Identity()
+        self.norm2 = _layernorm(dim)
+        self.mlp = _MLP(dim, _cfg_get(cfg, 'mlp_ratio', 4), bool(_cfg_get(cfg, 'mlp_bias', True)))
+        self.ls2 = _LayerScale(dim, ls) if ls > 0 else nn.Identity()
+
+
+class _AttentionPair(nn.Module):
+    def __init__(self, dim, skip_first_norm, cfg):
+        super().__init__()
+        self.att_window = _PartitionAttention(dim, True, cfg, skip_first_norm)
+        self.att_grid = _PartitionAttention(dim, False, cfg, False)
+
+
+class _ConvLSTM(nn.Module):
+    """DWSConvLSTM2d parameters (rnn.py:11-34)."""
+
+    def __init__(self, dim, dws_conv, only_hidden, ks, drop):
+        super().__init__()
+        if float(drop) != 0.0:
+            raise NotImplementedError('drop_cell_update > 0 is not built')
+        self.dim, self.dws_conv, self.only_hidden, self.ks = dim, bool(dws_conv), bool(only_hidden), int(ks)
+        if self.dws_conv:
+            d = dim if self.only_hidden else 2 * dim
+            self.conv3x3_dws = _Params(weight=(d, 1, ks, ks), bias=(d,))
+            nn.init.kaiming_uniform_(self.conv3x3_dws.weight, a=math.sqrt(5))
+            nn.init.uniform_(self.conv3x3_dws.bias, -1 / ks, 1 / ks)
+        else:
+            self.conv3x3_dws = nn.Identity()
+        self.conv1x1 = _Params(weight=(4 * dim, 2 * dim, 1, 1), bias=(4 * dim,))
+        nn.init.kaiming_uniform_(self.conv1x1.weight, a=math.sqrt(5))
+        nn.init.uniform_(self.conv1x1.bias, -1 / math.sqrt(2 * dim), 1 / math.sqrt(2 * dim))
+
+
+class RNNDetectorStage(nn.Module):
+    """Mirror of maxvit_rnn.py:130-182; NCHW in/out at the API."""
+
+    def __init__(self, dim_in, stage_dim, spatial_downsample_factor, num_blocks, enable_token_masking,
+                 T_max_chrono_init, stage_cfg):
+        super().__init__()
+        assert isinstance(num_blocks, int) and num_blocks > 0
+        lstm_cfg = _cfg(stage_cfg, 'lstm')
+        self.dim_in, self.dim = dim_in, stage_dim
+        self.downsample_cf2cl = _Downsample(dim_in, stage_dim, spatial_downsample_factor, _cfg(stage_cfg, 'downsample'))
+        self.att_blocks = nn.ModuleList([_AttentionPair(stage_dim, i == 0, _cfg(stage_cfg, 'attention'))
+                                         for i in range(num_blocks)])
+        self.lstm = _ConvLSTM(stage_dim, _cfg(lstm_cfg, 'dws_conv'), _cfg(lstm_cfg, 'dws_conv_only_hidden'),
+                              _cfg(lstm_cfg, 'dws_conv_kernel_size'), _cfg_get(lstm_cfg, 'drop_cell_update', 0))
+        if enable_token_masking:
+            self.mask_token = nn.Parameter(torch.zeros(1, 1, 1, stage_dim))
+            nn.init.normal_(self.mask_token, std=.02)
+        else:
+            self.mask_token = None
+
+
+class RNNDetector(nn.Module):
+    """B200-native ``MaxViTRNNDetector`` (reference maxvit_rnn.py:23-105)."""
+
+    def __init__(self, mdl_config):
+        super().__init__()
+        in_channels = _cfg(mdl_config, 'input_channels')
+        embed_dim = _cfg(mdl_config, 'embed_dim')
+        dim_multiplier = tuple(_cfg(mdl_config, 'dim_multiplier'))
+        num_blocks = tuple(_cfg(mdl_config, 'num_blocks'))
+        t_max = tuple(_cfg(mdl_config, 'T_max_chrono_init'))      # read, unused (as in the reference)
+        enable_masking = _cfg(mdl_config, 'enable_masking')
+        num_stages = len(num_blocks)
+        assert num_stages == 4
+        assert isinstance(embed_dim, int)
+        assert num_stages == len(dim_multiplier) == len(t_max)
+        # the reference's optional torch.compile switch (maxvit_rnn.py:43-52) has no meaning here:
+        # the step is already a fixed sequence of fused kernels (CUDA-graph capturable).
+        patch_size = _cfg(_cfg(mdl_config, 'stem'), 'patch_size')
+        self.stage_dims = [embed_dim * x for x in dim_multiplier]
+        self.stages = nn.ModuleList()
+        self.strides = []
+        input_dim, stride = in_channels, 1
+        for i, (nb, tm) in enumerate(zip(num_blocks, t_max)):
+            f = patch_size if i == 0 else 2
+            self.stages.append(RNNDetectorStage(input_dim, self.stage_dims[i], f, nb, enable_masking and i == 0,
+                                                tm, _cfg(mdl_config, 'stage')))
+            stride *= f
+            self.strides.append(stride)
+            input_dim = self.stage_dims[i]
+        self.num_stages = num_stages
+        self._packed = None
+        self._packed_key = None
+        self._scratch: Dict[str, torch.Tensor] = {}
+        # Optional: model input resolution (config `in_res_hw`).  When set, an un-padded event
+        # tensor (e.g. 360x640) is accepted and the bottom/right zero padding the harness would
+        # add (utils/padding.py:29-44) is folded into the stem conv's bounds checks.
+        self.pad_to_hw: Optional[Tuple[int, int]] = None
+        # test hook: when a dict, forward() stores clones of the residual stream after every
+        # operator (keys mirror oracle.backbone_oracle taps) so parity failures localise.
+        self.debug_taps: Optional[Dict[str, torch.Tensor]] = None
+
+    # ---- reference API -------------------------------------------------------------------
+    def get_stage_dims(self, stages: Tuple[int, ...]) -> Tuple[int, ...]:
+        idx = [x - 1 for x in stages]
+        assert min(idx) >= 0 and max(idx) < len(self.stages), idx
+        return tuple(self.stage_dims[i] for i in idx)
+
+    def get_strides(self, stages: Tuple[int, ...]) -> Tuple[int, ...]:
+        idx = [x - 1 for x in stages]
+        assert min(idx) >= 0 and max(idx) < len(self.stages), idx
+        return tuple(self.strides[i] for i in idx)
+
+    # ---- packed weights ------------------------------------------------------------------
+    def _param_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _ensure_packed(self, device):
+        key = self._param_key()
+        if self._packed is not None and key == self._packed_key:
+            return self._packed
+        L = _lib.lib()
+        f32 = lambda t: None if t is None else t.detach().to(device=device, dtype=torch.float32).contiguous()
+        packed = []
+        for s, st in enumerate(self.stages):
+            c = st.dim
+            d = st.downsample_cf2cl
+            e = {'conv_w': packing.pack_conv_weight(d.conv.weight.to(device), channels_last_input=s > 0),
+                 'ds_ln_w': f32(getattr(d.norm, 'weight', None)), 'ds_ln_b': f32(getattr(d.norm, 'bias', None)),
+                 'mask_token': f32(st.mask_token.reshape(-1)) if st.mask_token is not None else None,
+                 'blocks': []}
+            for pair in st.att_blocks:
+                for att in (pair.att_window, pair.att_grid):
+                    sa, mlp = att.self_attn, att.mlp
+                    fc1, fc2 = mlp.net[0][0], mlp.net[2]
+                    e['blocks'].append({
+                        'grid': 0 if att.window else 1, 'part': att.partition_size, 'dh': att.dim_head, 'eps': att.eps,
+                        'n1_w': f32(getattr(att.norm1, 'weight', None)), 'n1_b': f32(getattr(att.norm1, 'bias', None)),
+                        'wqkv': packing.pack_linear_weight(sa.qkv.weight.to(device), L.rvt_tile_n(3 * c)),
+                        'bqkv': f32(getattr(sa.qkv, 'bias', None)),
+                        'wproj': packing.pack_linear_weight(sa.proj.weight.to(device), L.rvt_tile_n(c)),
+                        'bproj': f32(getattr(sa.proj, 'bias', None)),
+                        'g1': f32(getattr(att.ls1, 'gamma', None)),
+                        'n2_w': f32(att.norm2.weight), 'n2_b': f32(att.norm2.bias),
+                        'hidden': fc1.weight.shape[0],
+                        'w1': packing.pack_linear_weight(fc1.weight.to(device), L.rvt_tile_n(fc1.weight.shape[0])),
+                        'b1': f32(getattr(fc1, 'bias', None)),
+                        'w2': packing.pack_linear_weight(fc2.weight.to(device), L.rvt_tile_n(c)),
+                        'b2': f32(getattr(fc2, 'bias', None)),
+                        'g2': f32(getattr(att.ls2, 'gamma', None)),
+                    })
+            lw, lb = packing.pack_lstm_weight(st.lstm.conv1x1.weight.to(device), st.lstm.conv1x1.bias.to(device),
+                                              L.rvt_lstm_cw(c))
+            e['lstm_w'], e['lstm_b'] = lw, lb
+            if st.lstm.dws_conv:
+                e['dw_w'] = packing.pack_dw_weight(st.lstm.conv3x3_dws.weight.to(device))
+                e['dw_b'] = f32(st.lstm.conv3x3_dws.bias)
+                e['dws_mode'] = 1 if st.lstm.only_hidden else 2
+            else:
+                e['dw_w'] = e['dw_b'] = None
+                e['dws_mode'] = 0
+            packed.append(e)
+        self._packed, self._packed_key = packed, key
+        return packed
+
+    def _scratch_buf(self, name, numel, dtype, device):
+        buf = self._scratch.get(name)
+        if buf is None or buf.numel() < numel or buf.device != device or buf.dtype != dtype:
+            buf = torch.empty(numel, dtype=dtype, device=device)
+            self._scratch[name] = buf
+        return buf
+
+    # ---- forward ---------------------------------------------------------------------------
+    @staticmethod
+    def _as_nhwc_f32(t: torch.Tensor) -> torch.Tensor:
+        """logical NCHW state -> contiguous [B,H,W,C] fp32 (free when already channels-last fp32)."""
+        v = t.detach().permute(0, 2, 3, 1)
+        if v.dtype != torch.float32 or not v.is_contiguous():
+            v = v.to(torch.float32).contiguous()
+        return v
+
+    def forward(self, x: torch.Tensor, prev_states: Optional[LstmStates] = None,
+                token_mask: Optional[torch.Tensor] = None):
+        if not x.is_cuda:
+            raise RuntimeError('rvt_b200.RNNDetector runs on CUDA (sm_100a) only; there is no CPU fallback')
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError(
+                'rvt_b200.RNNDetector: backward kernels are not built yet (DESIGN.md §7); call under '
+                'torch.no_grad() / torch.inference_mode() as validation.py:82 does')
+        if prev_states is None:
+            prev_states = [None] * self.num_stages
+        assert len(prev_states) == self.num_stages
+        assert x.dim() == 4
+        L = _lib.lib()
+        dev = x.device
+        packed = self._ensure_packed(dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        if x.dtype == torch.uint8:
+            in_dtype = 1
+        elif x.dtype == torch.float16:
+            in_dtype = 2
+        else:
+            in_dtype = 0
+            if x.dtype != torch.float32:
+                x = x.to(torch.float32)
+        x = x.contiguous()
+        b, cin, hin, win = x.shape
+        assert cin == self.stages[0].dim_in
+        states: LstmStates = []
+        output: Dict[int, torch.Tensor] = {}
+        cur, cur_nchw, cur_dtype = x, 1, in_dtype
+        for s, (st, pk) in enumerate(zip(self.stages, packed)):
+            d = st.downsample_cf2cl
+            c = st.dim
+            vh, vw = hin, win
+            if s == 0 and self.pad_to_hw is not None:
+                vh, vw = self.pad_to_hw
+                assert vh >= hin and vw >= win, 'input larger than pad_to_hw'
+            hout = (vh + 2 * d.padding - d.kernel_size) // d.factor + 1
+            wout = (vw + 2 * d.padding - d.kernel_size) // d.factor + 1
+            xs = torch.empty((b, hout, wout, c), dtype=torch.float32, device=dev)
+            mask_ptr = None
+            if s == 0 and token_mask is not None:
+                assert st.mask_token is not None, 'No mask token present in this stage'
+                tm = token_mask.to(device=dev, dtype=torch.uint8).contiguous()
+                assert tm.shape == (b, hout, wout)
+                mask_ptr = tm
+            _lib.check(L.rvt_downsample_cf2cl(
+                _lib.ptr(cur), cur_dtype, cur_nchw, b, st.dim_in, hin, win, d.kernel_size, d.factor, d.padding,
+                hout, wout, c, _lib.ptr(pk['conv_w']), _lib.ptr(pk['ds_ln_w']), _lib.ptr(pk['ds_ln_b']), 1e-5,
+                _lib.ptr(mask_ptr), _lib.ptr(pk['mask_token']), _lib.ptr(xs), stream), 'downsample_cf2cl')
+            n_tok = b * hout * wout
+            taps = self.debug_taps
+            if taps is not None:
+                taps[f'stages.{s}.downsample'] = xs.clone()
+            for bi, blk in enumerate(pk['blocks']):
+                tap_prefix = f"stages.{s}.att_blocks.{bi // 2}.{'att_grid' if blk['grid'] else 'att_window'}."
+                ph, pw = blk['part']
+                rows = L.rvt_attention_scratch_rows(b, hout, wout, ph, pw)
+                if rows < 0:
+                    raise RuntimeError(f'rvt_b200: partition {ph}x{pw} does not tile {hout}x{wout} or exceeds 128 tokens')
+                sq = self._scratch_buf('qkv', rows * 3 * c, torch.float16, dev)
+                so = self._scratch_buf('o', rows * c, torch.float16, dev)
+                _lib.check(L.rvt_partition_attention(
+                    _lib.ptr(xs), b, hout, wout, c, ph, pw, blk['grid'], blk['dh'], _lib.ptr(blk['n1_w']),
+                    _lib.ptr(blk['n1_b']), blk['eps'], _lib.ptr(blk['wqkv']), _lib.ptr(blk['bqkv']),
+                    _lib.ptr(blk['wproj']), _lib.ptr(blk['bproj']), _lib.ptr(blk['g1']), _lib.ptr(sq), _lib.ptr(so),
+                    stream), 'partition_attention')
+                if taps is not None:
+                    taps[tap_prefix + 'x_attn'] = xs.clone()
+                hid = blk['hidden']
+                sh = self._scratch_buf('hidden', ((n_tok + 127) // 128) * 128 * hid, torch.float16, dev)
+                _lib.check(L.rvt_mlp_block(
+                    _lib.ptr(xs), n_tok, c, hid, _lib.ptr(blk['n2_w']), _lib.ptr(blk['n2_b']), blk['eps'],
+                    _lib.ptr(blk['w1']), _lib.ptr(blk['b1']), _lib.ptr(blk['w2']), _lib.ptr(blk['b2']),
+                    _lib.ptr(blk['g2']), _lib.ptr(sh), stream), 'mlp_block')
+                if taps is not None:
+                    taps[tap_prefix + 'x_mlp'] = xs.clone()
+            hp = cp = None
+            if prev_states[s] is not None:
+                hp, cp = (self._as_nhwc_f32(t) for t in prev_states[s])
+                assert hp.shape == xs.shape and cp.shape == xs.shape
+            h_new = torch.empty_like(xs)
+            c_new = torch.empty_like(xs)
+            _lib.check(L.rvt_dws_conv_lstm(
+                _lib.ptr(xs), _lib.ptr(hp), _lib.ptr(cp), b, hout, wout, c, _lib.ptr(pk['lstm_w']),
+                _lib.ptr(pk['lstm_b']), _lib.ptr(pk['dw_w']), _lib.ptr(pk['dw_b']), pk['dws_mode'], st.lstm.ks,
+                _lib.ptr(h_new), _lib.ptr(c_new), stream), 'dws_conv_lstm')
+            h_nchw, c_nchw = h_new.permute(0, 3, 1, 2), c_new.permute(0, 3, 1, 2)
+            states.append((h_nchw, c_nchw))
+            output[s + 1] = h_nchw
+            cur, cur_nchw, cur_dtype = h_new, 0, 0
+            hin, win = hout, wout
+        return output, states
+
+
+def build_recurrent_backbone(backbone_cfg):
+    """Mirror of models/detection/recurrent_backbone/__init__.py:6-11."""
+    if _cfg(backbone_cfg, 'name') == 'MaxViTRNN':
+        return RNNDetector(backbone_cfg)
+    raise NotImplementedError

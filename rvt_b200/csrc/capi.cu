@@ -1,0 +1,241 @@
+// C-ABI entry points (include/rvt_b200.h): argument checks + kernel launches. No allocation,
+// no synchronisation, no torch types.
+#include "../../include/rvt_b200.h"
+
+#include <cuda_runtime.h>
+
+#include "attention_core.cuh"
+#include "gemm_fused.cuh"
+#include "voxel.cuh"
+
+using namespace rvt;
+
+namespace {
+
+constexpr int kErrBadArg = -1;
+constexpr int kErrUnsupported = -2;
+constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
+
+inline int cdiv(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
+
+template <int LOADER, int EPI>
+int launch_gemm(GemmArgs a, int n_mtiles, int n_ntiles, cudaStream_t st) {
+  a.KC = cdiv(a.K, 64);
+  a.tmem_cols = static_cast<int>(tmem_cols_pow2(static_cast<uint32_t>(a.BN)));
+  a.ab_fmt = 0;  // fp16 operands
+  int stages = a.KC < 4 ? a.KC : 4;
+  while (stages > 2 && gemm_smem_bytes(stages, a.BN) > 100 * 1024) --stages;
+  while (stages > 1 && gemm_smem_bytes(stages, a.BN) > static_cast<size_t>(kMaxSmem)) --stages;
+  a.stages = stages;
+  const size_t smem = gemm_smem_bytes(stages, a.BN);
+  if (smem > static_cast<size_t>(kMaxSmem) || a.BN > 512 || a.BN % 16 != 0) return kErrUnsupported;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_fused_kernel<LOADER, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set = true;
+  }
+  if (n_mtiles <= 0 || n_ntiles <= 0) return 0;
+  gemm_fused_kernel<LOADER, EPI><<<dim3(n_mtiles, n_ntiles), 160, smem, st>>>(a);
+  return static_cast<int>(cudaGetLastError());
+}
+
+RowMap identity_map(int64_t n_tokens, int H, int W) {
+  RowMap m{};
+  m.mode = MAP_IDENTITY;
+  m.H = H; m.W = W; m.ph = m.pw = 1; m.ny = H; m.nx = W; m.P = 1; m.rows_per_win = 1;
+  m.n_groups = 0; m.n_tokens = static_cast<int>(n_tokens);
+  return m;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rvt_abi_version(void) { return RVT_B200_ABI_VERSION; }
+
+const char* rvt_error_string(int code) {
+  if (code == 0) return "ok";
+  if (code == kErrBadArg) return "rvt_b200: bad argument";
+  if (code == kErrUnsupported) return "rvt_b200: unsupported shape (see DESIGN.md limits)";
+  return cudaGetErrorString(static_cast<cudaError_t>(code));
+}
+
+int rvt_tile_n(int n_total) {
+  for (int bn = 256; bn >= 16; bn -= 16)
+    if (n_total % bn == 0) return bn;
+  return -1;
+}
+
+int rvt_lstm_cw(int dim) {
+  for (int cw = 64; cw >= 16; cw -= 16)
+    if (dim % cw == 0) return cw;
+  return -1;
+}
+
+int rvt_rows_per_group(int p) { return p <= 64 ? 64 : (p <= 128 ? 128 : -1); }
+
+int64_t rvt_attention_scratch_rows(int batch, int height, int width, int ph, int pw) {
+  const int rpg = rvt_rows_per_group(ph * pw);
+  if (rpg < 0 || ph <= 0 || pw <= 0 || height % ph || width % pw) return -1;
+  const int64_t groups = static_cast<int64_t>(batch) * (height / ph) * (width / pw);
+  return (groups * rpg + 127) / 128 * 128;
+}
+
+int rvt_stacked_histogram(const int64_t* x, const int64_t* y, const int64_t* pol, const int64_t* t, int64_t n,
+                          int bins, int height, int width, int count_cutoff, int fastmode, uint32_t* counts,
+                          uint8_t* out, int* err_flag, void* stream) {
+  if (bins < 1 || height < 1 || width < 1 || n < 0 || !counts || !out || !err_flag) return kErrBadArg;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t n_out = 2 * static_cast<int64_t>(bins) * height * width;
+  const int cutoff = count_cutoff <= 0 ? 255 : (count_cutoff > 255 ? 255 : count_cutoff);
+  if (n > 0) {
+    if (!x || !y || !pol || !t) return kErrBadArg;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = static_cast<int64_t>(sms) * 8;  // 8 resident CTAs of 256 threads per SM
+    if (blocks > cap) blocks = cap;
+    voxel_accumulate_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, y, pol, t, n, bins, height, width, counts, err_flag);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  const int64_t fin_threads = (n_out + 15) / 16;
+  voxel_finalize_kernel<<<static_cast<unsigned>((fin_threads + 255) / 256), 256, 0, st>>>(counts, out, n_out, cutoff, fastmode);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int rvt_downsample_cf2cl(const void* in, int in_dtype, int in_nchw, int batch, int cin, int hin, int win, int ksize,
+                         int stride, int pad, int hout, int wout, int cout, const void* w_packed, const float* ln_w,
+                         const float* ln_b, float eps, const uint8_t* token_mask, const float* mask_token,
+                         float* out, void* stream) {
+  if (!in || !w_packed || !out || batch < 1 || cout % 16 != 0 || cout > 512) return kErrBadArg;
+  if (!in_nchw && (in_dtype != 0 || cin % 8 != 0)) return kErrUnsupported;
+  if ((ln_w == nullptr) != (ln_b == nullptr)) return kErrBadArg;
+  GemmArgs a{};
+  a.K = cin * ksize * ksize;
+  a.BN = cout;
+  a.Wp = static_cast<const __half*>(w_packed);
+  a.bias = nullptr;
+  const int64_t n_tok = static_cast<int64_t>(batch) * hout * wout;
+  a.map = identity_map(n_tok, hout, wout);
+  a.cin = in; a.in_dtype = in_dtype; a.in_nchw = in_nchw;
+  a.Cin = cin; a.Hin = hin; a.Win = win; a.KS = ksize; a.cstride = stride; a.cpad = pad; a.Hout = hout; a.Wout = wout;
+  a.yout = out; a.eln_w = ln_w; a.eln_b = ln_b; a.eeps = eps; a.token_mask = token_mask; a.mask_token = mask_token;
+  return launch_gemm<LD_CONV, EP_LN>(a, cdiv(n_tok, 128), 1, static_cast<cudaStream_t>(stream));
+}
+
+int rvt_partition_attention(float* x, int batch, int height, int width, int dim, int ph, int pw, int grid,
+                            int dim_head, const float* n1_w, const float* n1_b, float eps, const void* wqkv_packed,
+                            const float* bqkv, const void* wproj_packed, const float* bproj, const float* gamma1,
+                            void* scratch_qkv, void* scratch_o, void* stream) {
+  if (!x || !wqkv_packed || !wproj_packed || !scratch_qkv || !scratch_o) return kErrBadArg;
+  if (dim % 8 != 0 || dim > 512 || dim_head % 8 != 0 || dim_head > 64 || dim % dim_head != 0) return kErrUnsupported;
+  const int64_t rows = rvt_attention_scratch_rows(batch, height, width, ph, pw);
+  if (rows < 0) return kErrUnsupported;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int P = ph * pw, rpg = rvt_rows_per_group(P);
+  RowMap m{};
+  m.mode = grid ? MAP_GRID : MAP_WINDOW;
+  m.H = height; m.W = width; m.ph = ph; m.pw = pw; m.ny = height / ph; m.nx = width / pw; m.P = P;
+  m.rows_per_win = rpg; m.n_groups = batch * m.ny * m.nx; m.n_tokens = batch * height * width;
+  const int n_mtiles = static_cast<int>(rows / 128);
+
+  // 1) qkv = Linear(norm1(x)) on partition-ordered rows  (maxvit.py:234,254-257,347)
+  {
+    GemmArgs a{};
+    a.K = dim; a.BN = rvt_tile_n(3 * dim);
+    a.Wp = static_cast<const __half*>(wqkv_packed); a.bias = bqkv; a.map = m;
+    a.x = x; a.C = dim; a.ln_w = n1_w; a.ln_b = n1_b; a.eps = eps; a.do_ln = n1_w != nullptr;
+    a.o16 = static_cast<__half*>(scratch_qkv); a.ldo = 3 * dim; a.act = 0;
+    int rc = launch_gemm<LD_LN, EP_F16>(a, n_mtiles, 3 * dim / a.BN, st);
+    if (rc) return rc;
+  }
+  // 2) per-(tile, head) softmax(q k^T * scale) v   (maxvit.py:349-352)
+  {
+    AttnArgs at{};
+    at.qkv = static_cast<const __half*>(scratch_qkv); at.out = static_cast<__half*>(scratch_o);
+    at.C = dim; at.dh = dim_head; at.nh = dim / dim_head; at.P = P; at.rows_per_win = rpg;
+    at.nkeys = rpg == 64 ? 128 : ((P + 15) / 16) * 16;
+    at.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(dim_head));
+    at.ab_fmt = 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(attention_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      attr_set = true;
+    }
+    attention_core_kernel<<<dim3(n_mtiles, at.nh), 128, kAttnSmemBytes, st>>>(at);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  // 3) x[token] += gamma1 * (proj(o) + b)  scattered back = partition reverse (maxvit.py:259-262,268,353)
+  {
+    GemmArgs a{};
+    a.K = dim; a.BN = rvt_tile_n(dim);
+    a.Wp = static_cast<const __half*>(wproj_packed); a.bias = bproj; a.map = m;
+    a.a16 = static_cast<const __half*>(scratch_o); a.lda = dim; a.a_rows = static_cast<int>(rows);
+    a.C = dim; a.res = x; a.xout = x; a.gamma = gamma1;
+    return launch_gemm<LD_F16, EP_RES>(a, n_mtiles, dim / a.BN, st);
+  }
+}
+
+int rvt_mlp_block(float* x, int64_t n_tokens, int dim, int hidden, const float* n2_w, const float* n2_b, float eps,
+                  const void* w1_packed, const float* b1, const void* w2_packed, const float* b2, const float* gamma2,
+                  void* scratch_hidden, void* stream) {
+  if (!x || !w1_packed || !w2_packed || !scratch_hidden || !n2_w || !n2_b) return kErrBadArg;
+  if (dim % 8 != 0 || dim > 512 || hidden % 16 != 0) return kErrUnsupported;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n_mtiles = cdiv(n_tokens, 128);
+  RowMap m = identity_map(n_tokens, 1, static_cast<int>(n_tokens));
+  {
+    GemmArgs a{};
+    a.K = dim; a.BN = rvt_tile_n(hidden);
+    a.Wp = static_cast<const __half*>(w1_packed); a.bias = b1; a.map = m;
+    a.x = x; a.C = dim; a.ln_w = n2_w; a.ln_b = n2_b; a.eps = eps; a.do_ln = 1;
+    a.o16 = static_cast<__half*>(scratch_hidden); a.ldo = hidden; a.act = 1;
+    int rc = launch_gemm<LD_LN, EP_F16>(a, n_mtiles, hidden / a.BN, st);
+    if (rc) return rc;
+  }
+  {
+    GemmArgs a{};
+    a.K = hidden; a.BN = rvt_tile_n(dim);
+    a.Wp = static_cast<const __half*>(w2_packed); a.bias = b2; a.map = m;
+    a.a16 = static_cast<const __half*>(scratch_hidden); a.lda = hidden; a.a_rows = n_mtiles * 128;
+    a.C = dim; a.res = x; a.xout = x; a.gamma = gamma2;
+    return launch_gemm<LD_F16, EP_RES>(a, n_mtiles, dim / a.BN, st);
+  }
+}
+
+int rvt_dws_conv_lstm(const float* x, const float* h_prev, const float* c_prev, int batch, int height, int width,
+                      int dim, const void* w_packed, const float* bias_tiled, const float* dw_w, const float* dw_b,
+                      int dws_mode, int dws_ks, float* h_out, float* c_out, void* stream) {
+  if (!x || !w_packed || !bias_tiled || !h_out || !c_out) return kErrBadArg;
+  if (dim % 16 != 0 || dws_mode < 0 || dws_mode > 2) return kErrUnsupported;
+  if (dws_mode != 0 && (!dw_w || !dw_b || dws_ks % 2 == 0)) return kErrBadArg;
+  const int cw = rvt_lstm_cw(dim);
+  if (cw < 0) return kErrUnsupported;
+  const int64_t n_tok = static_cast<int64_t>(batch) * height * width;
+  GemmArgs a{};
+  a.K = 2 * dim; a.BN = 4 * cw;
+  a.Wp = static_cast<const __half*>(w_packed); a.bias = bias_tiled;
+  a.map = identity_map(n_tok, height, width);
+  a.x = x; a.C = dim; a.hprev = h_prev; a.dw_w = dw_w; a.dw_b = dw_b; a.dws_mode = dws_mode; a.dws_ks = dws_ks;
+  a.cprev = c_prev; a.hout = h_out; a.cout = c_out; a.cw = cw;
+  return launch_gemm<LD_XH, EP_LSTM>(a, cdiv(n_tok, 128), dim / cw, static_cast<cudaStream_t>(stream));
+}
+
+int rvt_linear_f16(const void* av, int64_t m, int k, int n, const void* w_packed, const float* bias, int act, void* out,
+                   void* stream) {
+  if (!av || !w_packed || !out || k % 8 != 0) return kErrBadArg;
+  GemmArgs a{};
+  a.K = k; a.BN = rvt_tile_n(n);
+  if (a.BN < 0) return kErrUnsupported;
+  a.Wp = static_cast<const __half*>(w_packed); a.bias = bias;
+  a.a16 = static_cast<const __half*>(av); a.lda = k; a.a_rows = static_cast<int>(m);
+  a.o16 = static_cast<__half*>(out); a.ldo = n; a.act = act;
+  return launch_gemm<LD_F16, EP_F16>(a, cdiv(m, 128), n / a.BN, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"
