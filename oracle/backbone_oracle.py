@@ -204,12 +204,12 @@ def stage_forward(x_nchw, state, token_mask, p, s: int, spec: BackboneSpec, od=N
     pre = f'stages.{s}.'
     factor = spec.patch_size if s == 0 else 2
     x = downsample_cf2cl(x_nchw, p, pre + 'downsample_cf2cl.', factor, spec.overlap, 1e-5, od)
-    if taps is not None:
-        taps[pre + 'downsample'] = x
     if token_mask is not None:                          # maxvit_rnn.py:174-176
         assert pre + 'mask_token' in p, 'No mask token present in this stage'
         x = x.clone()
         x[token_mask] = p[pre + 'mask_token'].reshape(-1)
+    if taps is not None:
+        taps[pre + 'downsample'] = x                    # after the mask token, as the CUDA op emits it
     for b in range(spec.num_blocks[s]):
         bp = f'{pre}att_blocks.{b}.'
         x = partition_attention_cl(x, p, bp + 'att_window.', spec.partition_size, True,

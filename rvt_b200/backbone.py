@@ -25,7 +25,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 import torch.nn as nn
 
-from . import _lib, packing
+from . import _lib, ops, packing
 
 LstmState = Optional[Tuple[torch.Tensor, torch.Tensor]]
 LstmStates = List[LstmState]
@@ -326,86 +326,51 @@ class RNNDetector(nn.Module):
             prev_states = [None] * self.num_stages
         assert len(prev_states) == self.num_stages
         assert x.dim() == 4
-        L = _lib.lib()
         dev = x.device
         packed = self._ensure_packed(dev)
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        if x.dtype == torch.uint8:
-            in_dtype = 1
-        elif x.dtype == torch.float16:
-            in_dtype = 2
-        else:
-            in_dtype = 0
-            if x.dtype != torch.float32:
-                x = x.to(torch.float32)
+        if x.dtype not in (torch.uint8, torch.float16, torch.float32):
+            x = x.to(torch.float32)
         x = x.contiguous()
-        b, cin, hin, win = x.shape
-        assert cin == self.stages[0].dim_in
+        b = x.shape[0]
+        assert x.shape[1] == self.stages[0].dim_in
         states: LstmStates = []
         output: Dict[int, torch.Tensor] = {}
-        cur, cur_nchw, cur_dtype = x, 1, in_dtype
+        taps = self.debug_taps
+        cur, cur_nchw = x, True
         for s, (st, pk) in enumerate(zip(self.stages, packed)):
             d = st.downsample_cf2cl
             c = st.dim
-            vh, vw = hin, win
-            if s == 0 and self.pad_to_hw is not None:
-                vh, vw = self.pad_to_hw
-                assert vh >= hin and vw >= win, 'input larger than pad_to_hw'
-            hout = (vh + 2 * d.padding - d.kernel_size) // d.factor + 1
-            wout = (vw + 2 * d.padding - d.kernel_size) // d.factor + 1
-            xs = torch.empty((b, hout, wout, c), dtype=torch.float32, device=dev)
-            mask_ptr = None
+            xs = ops.downsample_cf2cl(
+                cur, cur_nchw, pk['conv_w'], c, d.kernel_size, d.factor, d.padding, pk['ds_ln_w'], pk['ds_ln_b'],
+                virtual_hw=self.pad_to_hw if s == 0 else None,
+                token_mask=token_mask if s == 0 else None, mask_token=pk['mask_token'])
             if s == 0 and token_mask is not None:
                 assert st.mask_token is not None, 'No mask token present in this stage'
-                tm = token_mask.to(device=dev, dtype=torch.uint8).contiguous()
-                assert tm.shape == (b, hout, wout)
-                mask_ptr = tm
-            _lib.check(L.rvt_downsample_cf2cl(
-                _lib.ptr(cur), cur_dtype, cur_nchw, b, st.dim_in, hin, win, d.kernel_size, d.factor, d.padding,
-                hout, wout, c, _lib.ptr(pk['conv_w']), _lib.ptr(pk['ds_ln_w']), _lib.ptr(pk['ds_ln_b']), 1e-5,
-                _lib.ptr(mask_ptr), _lib.ptr(pk['mask_token']), _lib.ptr(xs), stream), 'downsample_cf2cl')
-            n_tok = b * hout * wout
-            taps = self.debug_taps
+            _, hh, ww, _ = xs.shape
+            n_tok = b * hh * ww
             if taps is not None:
                 taps[f'stages.{s}.downsample'] = xs.clone()
             for bi, blk in enumerate(pk['blocks']):
                 tap_prefix = f"stages.{s}.att_blocks.{bi // 2}.{'att_grid' if blk['grid'] else 'att_window'}."
-                ph, pw = blk['part']
-                rows = L.rvt_attention_scratch_rows(b, hout, wout, ph, pw)
-                if rows < 0:
-                    raise RuntimeError(f'rvt_b200: partition {ph}x{pw} does not tile {hout}x{wout} or exceeds 128 tokens')
+                rows = ops.attention_scratch_rows(b, hh, ww, blk['part'])
                 sq = self._scratch_buf('qkv', rows * 3 * c, torch.float16, dev)
                 so = self._scratch_buf('o', rows * c, torch.float16, dev)
-                _lib.check(L.rvt_partition_attention(
-                    _lib.ptr(xs), b, hout, wout, c, ph, pw, blk['grid'], blk['dh'], _lib.ptr(blk['n1_w']),
-                    _lib.ptr(blk['n1_b']), blk['eps'], _lib.ptr(blk['wqkv']), _lib.ptr(blk['bqkv']),
-                    _lib.ptr(blk['wproj']), _lib.ptr(blk['bproj']), _lib.ptr(blk['g1']), _lib.ptr(sq), _lib.ptr(so),
-                    stream), 'partition_attention')
+                ops.partition_attention_(xs, blk, sq, so)
                 if taps is not None:
                     taps[tap_prefix + 'x_attn'] = xs.clone()
-                hid = blk['hidden']
-                sh = self._scratch_buf('hidden', ((n_tok + 127) // 128) * 128 * hid, torch.float16, dev)
-                _lib.check(L.rvt_mlp_block(
-                    _lib.ptr(xs), n_tok, c, hid, _lib.ptr(blk['n2_w']), _lib.ptr(blk['n2_b']), blk['eps'],
-                    _lib.ptr(blk['w1']), _lib.ptr(blk['b1']), _lib.ptr(blk['w2']), _lib.ptr(blk['b2']),
-                    _lib.ptr(blk['g2']), _lib.ptr(sh), stream), 'mlp_block')
+                sh = self._scratch_buf('hidden', ((n_tok + 127) // 128) * 128 * blk['hidden'], torch.float16, dev)
+                ops.mlp_block_(xs, blk, sh)
                 if taps is not None:
                     taps[tap_prefix + 'x_mlp'] = xs.clone()
             hp = cp = None
             if prev_states[s] is not None:
                 hp, cp = (self._as_nhwc_f32(t) for t in prev_states[s])
                 assert hp.shape == xs.shape and cp.shape == xs.shape
-            h_new = torch.empty_like(xs)
-            c_new = torch.empty_like(xs)
-            _lib.check(L.rvt_dws_conv_lstm(
-                _lib.ptr(xs), _lib.ptr(hp), _lib.ptr(cp), b, hout, wout, c, _lib.ptr(pk['lstm_w']),
-                _lib.ptr(pk['lstm_b']), _lib.ptr(pk['dw_w']), _lib.ptr(pk['dw_b']), pk['dws_mode'], st.lstm.ks,
-                _lib.ptr(h_new), _lib.ptr(c_new), stream), 'dws_conv_lstm')
+            h_new, c_new = ops.dws_conv_lstm(xs, hp, cp, pk, st.lstm.ks)
             h_nchw, c_nchw = h_new.permute(0, 3, 1, 2), c_new.permute(0, 3, 1, 2)
             states.append((h_nchw, c_nchw))
             output[s + 1] = h_nchw
-            cur, cur_nchw, cur_dtype = h_new, 0, 0
-            hin, win = hout, wout
+            cur, cur_nchw = h_new, False
         return output, states
 
 

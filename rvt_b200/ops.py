@@ -1,0 +1,92 @@
+"""Thin tensor-level wrappers over the C-ABI operators (include/rvt_b200.h).  One function per
+reference function on the hot path; used by rvt_b200.backbone and by the parity
+tests.  Channels-last fp32 tensors [B, H, W, C]; CUDA only."""
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+_IN_DTYPES = {torch.float32: 0, torch.uint8: 1, torch.float16: 2}
+
+
+def _stream(t: torch.Tensor):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def downsample_cf2cl(x: torch.Tensor, x_is_nchw: bool, conv_w_packed: torch.Tensor, cout: int, ksize: int,
+                     stride: int, pad: int, ln_w: Optional[torch.Tensor], ln_b: Optional[torch.Tensor],
+                     virtual_hw: Optional[Tuple[int, int]] = None, token_mask: Optional[torch.Tensor] = None,
+                     mask_token: Optional[torch.Tensor] = None, eps: float = 1e-5) -> torch.Tensor:
+    """ConvDownsampling_Cf2Cl.forward (maxvit.py:174-178) [+ mask token, maxvit_rnn.py:174-176].
+    x: [B,Cin,H,W] (f32/u8/f16) if x_is_nchw else [B,H,W,Cin] f32.  -> f32 [B,Hout,Wout,cout]."""
+    assert x.is_cuda and x.is_contiguous() and x.dtype in _IN_DTYPES
+    if x_is_nchw:
+        b, cin, hin, win = x.shape
+    else:
+        b, hin, win, cin = x.shape
+    vh, vw = virtual_hw if virtual_hw is not None else (hin, win)
+    assert vh >= hin and vw >= win, 'input larger than the model resolution'
+    hout = (vh + 2 * pad - ksize) // stride + 1
+    wout = (vw + 2 * pad - ksize) // stride + 1
+    out = torch.empty((b, hout, wout, cout), dtype=torch.float32, device=x.device)
+    if token_mask is not None:
+        token_mask = token_mask.to(device=x.device, dtype=torch.uint8).contiguous()
+        assert tuple(token_mask.shape) == (b, hout, wout) and mask_token is not None
+    L = _lib.lib()
+    _lib.check(L.rvt_downsample_cf2cl(
+        _lib.ptr(x), _IN_DTYPES[x.dtype], int(x_is_nchw), b, cin, hin, win, ksize, stride, pad, hout, wout, cout,
+        _lib.ptr(conv_w_packed), _lib.ptr(ln_w), _lib.ptr(ln_b), eps, _lib.ptr(token_mask), _lib.ptr(mask_token),
+        _lib.ptr(out), _stream(x)), 'downsample_cf2cl')
+    return out
+
+
+def attention_scratch_rows(b, h, w, part) -> int:
+    rows = _lib.lib().rvt_attention_scratch_rows(b, h, w, part[0], part[1])
+    if rows < 0:
+        raise RuntimeError(f'rvt_b200: partition {part} does not tile {h}x{w} or exceeds 128 tokens')
+    return rows
+
+
+def partition_attention_(x: torch.Tensor, blk: dict, scratch_qkv: torch.Tensor, scratch_o: torch.Tensor) -> None:
+    """In place: x += ls1(proj(attn(partition(norm1(x)))))  (maxvit.py:252-268)."""
+    assert x.is_cuda and x.is_contiguous() and x.dtype == torch.float32
+    b, h, w, c = x.shape
+    ph, pw = blk['part']
+    rows = attention_scratch_rows(b, h, w, (ph, pw))
+    assert scratch_qkv.numel() >= rows * 3 * c and scratch_o.numel() >= rows * c
+    L = _lib.lib()
+    _lib.check(L.rvt_partition_attention(
+        _lib.ptr(x), b, h, w, c, ph, pw, blk['grid'], blk['dh'], _lib.ptr(blk['n1_w']), _lib.ptr(blk['n1_b']),
+        blk['eps'], _lib.ptr(blk['wqkv']), _lib.ptr(blk['bqkv']), _lib.ptr(blk['wproj']), _lib.ptr(blk['bproj']),
+        _lib.ptr(blk['g1']), _lib.ptr(scratch_qkv), _lib.ptr(scratch_o), _stream(x)), 'partition_attention')
+
+
+def mlp_block_(x: torch.Tensor, blk: dict, scratch_hidden: torch.Tensor) -> None:
+    """In place: x += ls2(mlp(norm2(x)))  (maxvit.py:269)."""
+    assert x.is_cuda and x.is_contiguous() and x.dtype == torch.float32
+    c = x.shape[-1]
+    n_tok = x.numel() // c
+    hid = blk['hidden']
+    assert scratch_hidden.numel() >= ((n_tok + 127) // 128) * 128 * hid
+    L = _lib.lib()
+    _lib.check(L.rvt_mlp_block(
+        _lib.ptr(x), n_tok, c, hid, _lib.ptr(blk['n2_w']), _lib.ptr(blk['n2_b']), blk['eps'], _lib.ptr(blk['w1']),
+        _lib.ptr(blk['b1']), _lib.ptr(blk['w2']), _lib.ptr(blk['b2']), _lib.ptr(blk['g2']),
+        _lib.ptr(scratch_hidden), _stream(x)), 'mlp_block')
+
+
+def dws_conv_lstm(x: torch.Tensor, h_prev: Optional[torch.Tensor], c_prev: Optional[torch.Tensor], pk: dict,
+                  dws_ks: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """DWSConvLSTM2d.forward (rnn.py:36-69) on channels-last tensors -> (h_t, c_t)."""
+    assert x.is_cuda and x.is_contiguous() and x.dtype == torch.float32
+    b, h, w, c = x.shape
+    for t in (h_prev, c_prev):
+        assert t is None or (t.shape == x.shape and t.is_contiguous() and t.dtype == torch.float32)
+    h_new, c_new = torch.empty_like(x), torch.empty_like(x)
+    L = _lib.lib()
+    _lib.check(L.rvt_dws_conv_lstm(
+        _lib.ptr(x), _lib.ptr(h_prev), _lib.ptr(c_prev), b, h, w, c, _lib.ptr(pk['lstm_w']), _lib.ptr(pk['lstm_b']),
+        _lib.ptr(pk['dw_w']), _lib.ptr(pk['dw_b']), pk['dws_mode'], dws_ks, _lib.ptr(h_new), _lib.ptr(c_new),
+        _stream(x)), 'dws_conv_lstm')
+    return h_new, c_new
