@@ -26,8 +26,8 @@ int rvt_abi_version(void);
 const char* rvt_error_string(int code);
 
 /* ---- tiling contract shared with the host-side weight packer (rvt_b200/packing.py) ---- */
-/* N-tile (columns per CTA) used for a Linear with n_total output features. */
-int rvt_tile_n(int n_total);
+/* N-tile (columns per CTA) used for a Linear with n_total output and k input features. */
+int rvt_tile_n(int n_total, int k);
 /* Channels per CTA for the Conv-LSTM gate GEMM (tile = [f|i|o|g] x cw columns). */
 int rvt_lstm_cw(int dim);
 /* Rows one partition group occupies in a 128-row tile (64 or 128; <0 if P > 128). */
@@ -50,11 +50,15 @@ int rvt_stacked_histogram(const int64_t* x, const int64_t* y, const int64_t* pol
  * with in_nchw).  Rows/cols of the virtual input beyond (Hin,Win) read as zero, which folds
  * the harness' zero padding (utils/padding.py:29-44) into the conv.  out: f32 [B,Hout,Wout,Cout].
  * w_packed: rvt_b200.packing.pack_conv_weight().  ln_w/ln_b may be NULL (norm_affine=False).
- * token_mask: u8 [B,Hout,Wout] or NULL; mask_token: f32 [Cout]. */
+ * token_mask: u8 [B,Hout,Wout] or NULL; mask_token: f32 [Cout].
+ * s2d_scratch (stem fast path, in_nchw only): f16 [B, Hin, Wout, stride*Cin] workspace; when given
+ * the input is first re-laid out space-to-depth so every conv tap is a 16-byte vector load, and
+ * w_packed must come from packing.pack_stem_weight_s2d().  NULL selects the generic gather path. */
 int rvt_downsample_cf2cl(const void* in, int in_dtype, int in_nchw, int batch, int cin, int hin, int win,
                          int ksize, int stride, int pad, int hout, int wout, int cout,
                          const void* w_packed, const float* ln_w, const float* ln_b, float eps,
-                         const uint8_t* token_mask, const float* mask_token, float* out, void* stream);
+                         const uint8_t* token_mask, const float* mask_token, float* out,
+                         void* s2d_scratch, void* stream);
 
 /* ---- a4-a7: attention half of PartitionAttentionCl.forward  (maxvit.py:252-268, 273-354) -
  * x <- x + gamma1 * proj(attn(partition(norm1(x))))   in place, x: f32 [B,H,W,C].

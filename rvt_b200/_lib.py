@@ -13,13 +13,13 @@ _vp, _i, _i64, _f = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float
 SIGNATURES = {
     'rvt_abi_version': (_i, []),
     'rvt_error_string': (_c.c_char_p, [_i]),
-    'rvt_tile_n': (_i, [_i]),
+    'rvt_tile_n': (_i, [_i, _i]),
     'rvt_lstm_cw': (_i, [_i]),
     'rvt_rows_per_group': (_i, [_i]),
     'rvt_attention_scratch_rows': (_i64, [_i, _i, _i, _i, _i]),
     'rvt_stacked_histogram': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     'rvt_downsample_cf2cl': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f,
-                                   _vp, _vp, _vp, _vp]),
+                                   _vp, _vp, _vp, _vp, _vp]),
     'rvt_partition_attention': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp,
                                       _vp, _vp, _vp, _vp]),
     'rvt_mlp_block': (_i, [_vp, _i64, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -261,6 +261,8 @@ class RNNDetector(nn.Module):
             c = st.dim
             d = st.downsample_cf2cl
             e = {'conv_w': packing.pack_conv_weight(d.conv.weight.to(device), channels_last_input=s > 0),
+                 'conv_w_s2d': (packing.pack_stem_weight_s2d(d.conv.weight.to(device), d.factor)
+                                if s == 0 and (d.factor * st.dim_in) % 8 == 0 else None),
                  'ds_ln_w': f32(getattr(d.norm, 'weight', None)), 'ds_ln_b': f32(getattr(d.norm, 'bias', None)),
                  'mask_token': f32(st.mask_token.reshape(-1)) if st.mask_token is not None else None,
                  'blocks': []}
@@ -271,16 +273,16 @@ class RNNDetector(nn.Module):
                     e['blocks'].append({
                         'grid': 0 if att.window else 1, 'part': att.partition_size, 'dh': att.dim_head, 'eps': att.eps,
                         'n1_w': f32(getattr(att.norm1, 'weight', None)), 'n1_b': f32(getattr(att.norm1, 'bias', None)),
-                        'wqkv': packing.pack_linear_weight(sa.qkv.weight.to(device), L.rvt_tile_n(3 * c)),
+                        'wqkv': packing.pack_linear_weight(sa.qkv.weight.to(device), L.rvt_tile_n(3 * c, c)),
                         'bqkv': f32(getattr(sa.qkv, 'bias', None)),
-                        'wproj': packing.pack_linear_weight(sa.proj.weight.to(device), L.rvt_tile_n(c)),
+                        'wproj': packing.pack_linear_weight(sa.proj.weight.to(device), L.rvt_tile_n(c, c)),
                         'bproj': f32(getattr(sa.proj, 'bias', None)),
                         'g1': f32(getattr(att.ls1, 'gamma', None)),
                         'n2_w': f32(att.norm2.weight), 'n2_b': f32(att.norm2.bias),
                         'hidden': fc1.weight.shape[0],
-                        'w1': packing.pack_linear_weight(fc1.weight.to(device), L.rvt_tile_n(fc1.weight.shape[0])),
+                        'w1': packing.pack_linear_weight(fc1.weight.to(device), L.rvt_tile_n(fc1.weight.shape[0], c)),
                         'b1': f32(getattr(fc1, 'bias', None)),
-                        'w2': packing.pack_linear_weight(fc2.weight.to(device), L.rvt_tile_n(c)),
+                        'w2': packing.pack_linear_weight(fc2.weight.to(device), L.rvt_tile_n(c, fc2.weight.shape[1])),
                         'b2': f32(getattr(fc2, 'bias', None)),
                         'g2': f32(getattr(att.ls2, 'gamma', None)),
                     })
@@ -340,10 +342,16 @@ class RNNDetector(nn.Module):
         for s, (st, pk) in enumerate(zip(self.stages, packed)):
             d = st.downsample_cf2cl
             c = st.dim
+            conv_w, s2d = pk['conv_w'], None
+            if s == 0 and pk['conv_w_s2d'] is not None:
+                vw = self.pad_to_hw[1] if self.pad_to_hw is not None else cur.shape[3]
+                if ops.stem_uses_s2d(st.dim_in, d.factor, d.kernel_size, d.padding, vw):
+                    conv_w = pk['conv_w_s2d']
+                    s2d = self._scratch_buf('s2d', b * cur.shape[2] * vw * st.dim_in, torch.float16, dev)
             xs = ops.downsample_cf2cl(
-                cur, cur_nchw, pk['conv_w'], c, d.kernel_size, d.factor, d.padding, pk['ds_ln_w'], pk['ds_ln_b'],
+                cur, cur_nchw, conv_w, c, d.kernel_size, d.factor, d.padding, pk['ds_ln_w'], pk['ds_ln_b'],
                 virtual_hw=self.pad_to_hw if s == 0 else None,
-                token_mask=token_mask if s == 0 else None, mask_token=pk['mask_token'])
+                token_mask=token_mask if s == 0 else None, mask_token=pk['mask_token'], s2d_scratch=s2d)
             if s == 0 and token_mask is not None:
                 assert st.mask_token is not None, 'No mask token present in this stage'
             _, hh, ww, _ = xs.shape

@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(128) attention_core_kernel(const __grid_consta
     for (int q = 0; q < 16; ++q) {
       const int key = c0 + q;
       float p = 0.f;
-      if (key >= key_lo && key < key_hi) p = exp2f((v[q] - mx) * a.scale_log2e);
+      if (key >= key_lo && key < key_hi) p = ex2_approx((v[q] - mx) * a.scale_log2e);
       // the probabilities are rounded to fp16 for the PV MMA; normalise by the sum of the
       // rounded values so each row of P/sum sums to one exactly as seen by the tensor core
       const float pr = __half2float(__float2half_rn(p));
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(128) attention_core_kernel(const __grid_consta
     st_smem_16B(sP + atom * 16384 + sw128_offset(t, ch + 1), pack_h2(v[8], v[9]), pack_h2(v[10], v[11]),
                 pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
   }
-  const float inv = 1.0f / sum;
+  const float inv = rcp_approx(sum);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();

@@ -33,10 +33,12 @@ int launch_gemm(GemmArgs a, int n_mtiles, int n_ntiles, cudaStream_t st) {
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_fused_kernel<LOADER, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) return static_cast<int>(e);
+    cudaFuncSetAttribute(gemm_fused_kernel<LOADER, EPI>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
     attr_set = true;
   }
   if (n_mtiles <= 0 || n_ntiles <= 0) return 0;
-  gemm_fused_kernel<LOADER, EPI><<<dim3(n_mtiles, n_ntiles), 160, smem, st>>>(a);
+  gemm_fused_kernel<LOADER, EPI><<<dim3(n_mtiles, n_ntiles), kGemmThreads, smem, st>>>(a);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -61,8 +63,12 @@ const char* rvt_error_string(int code) {
   return cudaGetErrorString(static_cast<cudaError_t>(code));
 }
 
-int rvt_tile_n(int n_total) {
-  for (int bn = 256; bn >= 16; bn -= 16)
+int rvt_tile_n(int n_total, int k) {
+  // Narrow stages (dim <= 128) have many 128-row tiles: one wide N-tile per CTA.  Wide stages
+  // (dim >= 256) have few row tiles: cut N finer so the grid still covers the 148 SMs.
+  const int dim = n_total < k ? n_total : k;
+  const int cap = dim <= 128 ? 128 : (n_total >= 1024 ? 128 : 64);   // <=128 TMEM columns -> 4 CTAs / SM
+  for (int bn = cap; bn >= 16; bn -= 16)
     if (n_total % bn == 0) return bn;
   return -1;
 }
@@ -109,21 +115,41 @@ int rvt_stacked_histogram(const int64_t* x, const int64_t* y, const int64_t* pol
 int rvt_downsample_cf2cl(const void* in, int in_dtype, int in_nchw, int batch, int cin, int hin, int win, int ksize,
                          int stride, int pad, int hout, int wout, int cout, const void* w_packed, const float* ln_w,
                          const float* ln_b, float eps, const uint8_t* token_mask, const float* mask_token,
-                         float* out, void* stream) {
+                         float* out, void* s2d_scratch, void* stream) {
   if (!in || !w_packed || !out || batch < 1 || cout % 16 != 0 || cout > 512) return kErrBadArg;
-  if (!in_nchw && (in_dtype != 0 || cin % 8 != 0)) return kErrUnsupported;
+  if (!in_nchw && (in_dtype == 1 || cin % 8 != 0)) return kErrUnsupported;
   if ((ln_w == nullptr) != (ln_b == nullptr)) return kErrBadArg;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   GemmArgs a{};
-  a.K = cin * ksize * ksize;
   a.BN = cout;
   a.Wp = static_cast<const __half*>(w_packed);
   a.bias = nullptr;
   const int64_t n_tok = static_cast<int64_t>(batch) * hout * wout;
   a.map = identity_map(n_tok, hout, wout);
-  a.cin = in; a.in_dtype = in_dtype; a.in_nchw = in_nchw;
-  a.Cin = cin; a.Hin = hin; a.Win = win; a.KS = ksize; a.cstride = stride; a.cpad = pad; a.Hout = hout; a.Wout = wout;
+  a.Hout = hout; a.Wout = wout;
+  if (s2d_scratch) {
+    // space-to-depth stem: [B,Cin,H,W] -> f16 [B,H,Wg,f*Cin], then a (ks x 2)-tap vectorised conv
+    const bool overlap = ksize == 2 * stride - 1 && pad == stride - 1;
+    const bool patch = ksize == stride && pad == 0;
+    if (!in_nchw || !(overlap || patch) || 64 % stride != 0 || (stride * cin) % 8 != 0) return kErrUnsupported;
+    const int wg = wout;
+    const size_t smem = static_cast<size_t>(cin) * (kS2dStrip + 2) * sizeof(__half);
+    if (smem > 48 * 1024) return kErrUnsupported;
+    stem_s2d_kernel<<<dim3((wg * stride + kS2dStrip - 1) / kS2dStrip, hin, batch), 256, smem, st>>>(in, in_dtype, cin, hin, win, wg, stride,
+                                                                           static_cast<__half*>(s2d_scratch));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return static_cast<int>(e);
+    a.cin = s2d_scratch; a.in_dtype = 2; a.in_nchw = 0;
+    a.Cin = stride * cin; a.Hin = hin; a.Win = wg;
+    a.KSy = ksize; a.KSx = overlap ? 2 : 1; a.sy = stride; a.sx = 1; a.pady = pad; a.padx = overlap ? 1 : 0;
+  } else {
+    a.cin = in; a.in_dtype = in_dtype; a.in_nchw = in_nchw;
+    a.Cin = cin; a.Hin = hin; a.Win = win;
+    a.KSy = a.KSx = ksize; a.sy = a.sx = stride; a.pady = a.padx = pad;
+  }
+  a.K = a.Cin * a.KSy * a.KSx;
   a.yout = out; a.eln_w = ln_w; a.eln_b = ln_b; a.eeps = eps; a.token_mask = token_mask; a.mask_token = mask_token;
-  return launch_gemm<LD_CONV, EP_LN>(a, cdiv(n_tok, 128), 1, static_cast<cudaStream_t>(stream));
+  return launch_gemm<LD_CONV, EP_LN>(a, cdiv(n_tok, 128), 1, st);
 }
 
 int rvt_partition_attention(float* x, int batch, int height, int width, int dim, int ph, int pw, int grid,
@@ -145,7 +171,7 @@ int rvt_partition_attention(float* x, int batch, int height, int width, int dim,
   // 1) qkv = Linear(norm1(x)) on partition-ordered rows  (maxvit.py:234,254-257,347)
   {
     GemmArgs a{};
-    a.K = dim; a.BN = rvt_tile_n(3 * dim);
+    a.K = dim; a.BN = rvt_tile_n(3 * dim, dim);
     a.Wp = static_cast<const __half*>(wqkv_packed); a.bias = bqkv; a.map = m;
     a.x = x; a.C = dim; a.ln_w = n1_w; a.ln_b = n1_b; a.eps = eps; a.do_ln = n1_w != nullptr;
     a.o16 = static_cast<__half*>(scratch_qkv); a.ldo = 3 * dim; a.act = 0;
@@ -164,6 +190,7 @@ int rvt_partition_attention(float* x, int batch, int height, int width, int dim,
     if (!attr_set) {
       cudaError_t e = cudaFuncSetAttribute(attention_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
       if (e != cudaSuccess) return static_cast<int>(e);
+      cudaFuncSetAttribute(attention_core_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       attr_set = true;
     }
     attention_core_kernel<<<dim3(n_mtiles, at.nh), 128, kAttnSmemBytes, st>>>(at);
@@ -173,7 +200,7 @@ int rvt_partition_attention(float* x, int batch, int height, int width, int dim,
   // 3) x[token] += gamma1 * (proj(o) + b)  scattered back = partition reverse (maxvit.py:259-262,268,353)
   {
     GemmArgs a{};
-    a.K = dim; a.BN = rvt_tile_n(dim);
+    a.K = dim; a.BN = rvt_tile_n(dim, dim);
     a.Wp = static_cast<const __half*>(wproj_packed); a.bias = bproj; a.map = m;
     a.a16 = static_cast<const __half*>(scratch_o); a.lda = dim; a.a_rows = static_cast<int>(rows);
     a.C = dim; a.res = x; a.xout = x; a.gamma = gamma1;
@@ -191,7 +218,7 @@ int rvt_mlp_block(float* x, int64_t n_tokens, int dim, int hidden, const float* 
   RowMap m = identity_map(n_tokens, 1, static_cast<int>(n_tokens));
   {
     GemmArgs a{};
-    a.K = dim; a.BN = rvt_tile_n(hidden);
+    a.K = dim; a.BN = rvt_tile_n(hidden, dim);
     a.Wp = static_cast<const __half*>(w1_packed); a.bias = b1; a.map = m;
     a.x = x; a.C = dim; a.ln_w = n2_w; a.ln_b = n2_b; a.eps = eps; a.do_ln = 1;
     a.o16 = static_cast<__half*>(scratch_hidden); a.ldo = hidden; a.act = 1;
@@ -200,7 +227,7 @@ int rvt_mlp_block(float* x, int64_t n_tokens, int dim, int hidden, const float* 
   }
   {
     GemmArgs a{};
-    a.K = hidden; a.BN = rvt_tile_n(dim);
+    a.K = hidden; a.BN = rvt_tile_n(dim, hidden);
     a.Wp = static_cast<const __half*>(w2_packed); a.bias = b2; a.map = m;
     a.a16 = static_cast<const __half*>(scratch_hidden); a.lda = hidden; a.a_rows = n_mtiles * 128;
     a.C = dim; a.res = x; a.xout = x; a.gamma = gamma2;
@@ -230,7 +257,7 @@ int rvt_linear_f16(const void* av, int64_t m, int k, int n, const void* w_packed
                    void* stream) {
   if (!av || !w_packed || !out || k % 8 != 0) return kErrBadArg;
   GemmArgs a{};
-  a.K = k; a.BN = rvt_tile_n(n);
+  a.K = k; a.BN = rvt_tile_n(n, k);
   if (a.BN < 0) return kErrUnsupported;
   a.Wp = static_cast<const __half*>(w_packed); a.bias = bias;
   a.a16 = static_cast<const __half*>(av); a.lda = k; a.a_rows = static_cast<int>(m);

@@ -66,8 +66,8 @@ struct GemmArgs {
   const float* ln_w; const float* ln_b; float eps; int do_ln;
   // LD_XH
   const float* hprev; const float* dw_w; const float* dw_b; int dws_mode; int dws_ks;
-  // LD_CONV
-  const void* cin; int in_dtype; int in_nchw; int Cin, Hin, Win, KS, cstride, cpad, Hout, Wout;
+  // LD_CONV (rectangular kernel / stride / pad so the space-to-depth stem maps onto it)
+  const void* cin; int in_dtype; int in_nchw; int Cin, Hin, Win, KSy, KSx, sy, sx, pady, padx, Hout, Wout;
   // EP_F16
   __half* o16; int ldo; int act;
   // EP_RES
@@ -82,13 +82,38 @@ struct GemmArgs {
 constexpr int kMaxStages = 6;
 constexpr uint32_t kATileBytes = 128 * 128;   // 128 rows x 64 fp16
 
+constexpr int kWorkers = 256;                 // 8 producer / epilogue warps
+constexpr int kGemmThreads = kWorkers + 32;   // + the MMA-issuing warp
+
 __host__ __device__ inline size_t gemm_smem_bytes(int stages, int BN) {
   return 1024 /*align slack*/ + static_cast<size_t>(stages) * (kATileBytes + static_cast<size_t>(BN) * 128) +
          2 * 128 * sizeof(float) + (2 * kMaxStages + 1) * sizeof(uint64_t) + 16;
 }
 
-__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
-__device__ __forceinline__ float sigmoid_acc(float v) { return 1.0f / (1.0f + expf(-v)); }
+// Exact-erf GELU (F.gelu default, layers/activations.py:138-145) with erf from Abramowitz &
+// Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the fp16 rounding of the GELU output):
+//   q = 0.5 * (1 - erf(|v|/sqrt2)) = 0.5 * poly(t) * exp(-v^2/2),  t = 1 / (1 + p |v|/sqrt2)
+//   gelu(v) = v >= 0 ? v - v q : v q                        (~16 instructions, 2 MUFU)
+__device__ __forceinline__ float gelu_erf(float v) {
+  const float u = fabsf(v) * 0.70710678118654752f;
+  const float t = rcp_approx(fmaf(0.3275911f, u, 1.0f));
+  float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  const float q = p * t * ex2_approx(u * u * -1.4426950408889634f);
+  const float r = v * q;
+  return v >= 0.f ? v - r : r;
+}
+__device__ __forceinline__ float sigmoid_acc(float v) { return rcp_approx(1.0f + ex2_approx(v * -1.4426950408889634f)); }
+__device__ __forceinline__ float tanh_acc(float v) { return fmaf(2.0f, sigmoid_acc(2.0f * v), -1.0f); }
+__device__ __forceinline__ void load16(const float* p, float* v) {   // p 16-byte aligned
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p) + q);
+    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+  }
+}
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -128,10 +153,24 @@ __device__ __forceinline__ void dwconv8(const float* __restrict__ src, int Csrc,
 }
 
 // ----------------------------------------------------------------------------------------
-// The kernel
+// The kernel.  288 threads: warps 0-7 are workers (A-tile producers, then epilogue), warp 8
+// issues the MMAs.  Worker thread `tid` builds chunk j = tid&7 of rows (tid>>3) + 32*i, i<4.
+// In the epilogue worker warp w owns TMEM lanes 32*(w&3).. and the column half (w>>2).
 // ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void load8(const float* p, float* v) {
+  const float4 v0 = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 v1 = __ldg(reinterpret_cast<const float4*>(p + 4));
+  v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
+}
+__device__ __forceinline__ float red8(float s) {   // sum over the 8 lanes that share a row
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  return s;
+}
+
 template <int LOADER, int EPI>
-__global__ void __launch_bounds__(160) gemm_fused_kernel(const __grid_constant__ GemmArgs a) {
+__global__ void __launch_bounds__(kGemmThreads, 3) gemm_fused_kernel(const __grid_constant__ GemmArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
@@ -145,80 +184,91 @@ __global__ void __launch_bounds__(160) gemm_fused_kernel(const __grid_constant__
   const uint32_t sA_addr = base_addr;
   const uint32_t sB_addr = base_addr + stages * kATileBytes;
   uint8_t* sB = sm + stages * kATileBytes;
-  float* s_mean = reinterpret_cast<float*>(sB + static_cast<size_t>(stages) * b_bytes);
-  float* s_rstd = s_mean + 128;
-  uint64_t* full = reinterpret_cast<uint64_t*>(s_rstd + 128);
+  float* s_red = reinterpret_cast<float*>(sB + static_cast<size_t>(stages) * b_bytes);   // [2][128]
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_red + 256);
   uint64_t* empty = full + kMaxStages;
   uint64_t* accum = empty + kMaxStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
 
   if (tid == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], kWorkers); mbar_init(&empty[s], 1); }
     mbar_init(accum, 1);
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, a.tmem_cols);
+  if (warp == 8) tmem_alloc(tmem_slot, a.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // =========================== A-tile producers ===========================
     const int j = tid & 7;          // 16-byte chunk (8 fp16) inside the 64-wide K chunk
-    const int r0 = tid >> 3;        // rows r0 + 16*i, i = 0..7
-    int tok[8];
+    const int r0 = tid >> 3;        // rows r0 + 32*i, i = 0..3
+    int tok[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int row = mt * 128 + r0 + 16 * i;
+    for (int i = 0; i < 4; ++i) {
+      const int row = mt * 128 + r0 + 32 * i;
       if (LOADER == LD_F16) tok[i] = row < a.a_rows ? row : -1;
       else tok[i] = row_to_token(a.map, row);
     }
 
+    // LayerNorm statistics, two-pass, entirely in registers + 3 shuffles (the 8 lanes tid&7
+    // of a row sit in one warp).  KC == 1 keeps the row values for the tile build.
+    float mean[4] = {0.f, 0.f, 0.f, 0.f}, rstd[4] = {1.f, 1.f, 1.f, 1.f};
+    float keep[4][8];
     if (LOADER == LD_LN && a.do_ln) {
-      // per-row LayerNorm statistics (two-pass in registers; C <= 512 -> <= 16 values / lane)
       const int C = a.C;
-      for (int rr = 0; rr < 32; ++rr) {
-        const int r = warp * 32 + rr;
-        const int t = row_to_token(a.map, mt * 128 + r);
-        float v[16];
-        float s = 0.f;
+      float s1[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int kc = 0; kc < KC; ++kc) {
+        const int k0 = kc * 64 + j * 8;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const int c = lane + 32 * q;
-          v[q] = (t >= 0 && c < C) ? __ldg(a.x + static_cast<size_t>(t) * C + c) : 0.f;
-          s += v[q];
+        for (int i = 0; i < 4; ++i) {
+          float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (tok[i] >= 0 && k0 < C) load8(a.x + static_cast<size_t>(tok[i]) * C + k0, v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { s1[i] += v[e]; if (KC == 1) keep[i][e] = v[e]; }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        const float mean = s / C;
-        float ss = 0.f;
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const int c = lane + 32 * q;
-          const float d = (c < C) ? v[q] - mean : 0.f;
-          ss += d * d;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        if (lane == 0) { s_mean[r] = mean; s_rstd[r] = rsqrtf(ss / C + a.eps); }
       }
-      named_bar_sync(1, 128);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) mean[i] = red8(s1[i]) / C;
+      float s2[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int kc = 0; kc < KC; ++kc) {
+        const int k0 = kc * 64 + j * 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float v[8];
+          if (KC == 1) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = keep[i][e];
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = mean[i];
+            if (tok[i] >= 0 && k0 < C) load8(a.x + static_cast<size_t>(tok[i]) * C + k0, v);
+          }
+          if (k0 < C) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { const float d = v[e] - mean[i]; s2[i] += d * d; }
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rstd[i] = rsqrtf(red8(s2[i]) / C + a.eps);
     }
 
-    // conv: per-row input window origin
-    int cb[8], ciy[8], cix[8];
+    // conv / lstm: per-row spatial origin
+    int cb[4], ciy[4], cix[4];
     if (LOADER == LD_CONV || LOADER == LD_XH) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         const int hw = (LOADER == LD_CONV) ? a.Hout * a.Wout : a.map.H * a.map.W;
         const int wd = (LOADER == LD_CONV) ? a.Wout : a.map.W;
         const int t = tok[i] < 0 ? 0 : tok[i];
         const int b = t / hw, rem = t - b * hw;
         const int oy = rem / wd, ox = rem - oy * wd;
         cb[i] = b;
-        ciy[i] = (LOADER == LD_CONV) ? oy * a.cstride - a.cpad : oy;
-        cix[i] = (LOADER == LD_CONV) ? ox * a.cstride - a.cpad : ox;
+        ciy[i] = (LOADER == LD_CONV) ? oy * a.sy - a.pady : oy;
+        cix[i] = (LOADER == LD_CONV) ? ox * a.sx - a.padx : ox;
       }
     }
 
@@ -236,38 +286,32 @@ __global__ void __launch_bounds__(160) gemm_fused_kernel(const __grid_constant__
 
       if (LOADER == LD_F16) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 4; ++i) {
           uint4 v = make_uint4(0, 0, 0, 0);
           if (tok[i] >= 0 && k0 < a.K)
             v = __ldg(reinterpret_cast<const uint4*>(a.a16 + static_cast<size_t>(tok[i]) * a.lda + k0));
-          st_smem_16B(tile + sw128_offset(r0 + 16 * i, j), v.x, v.y, v.z, v.w);
+          st_smem_16B(tile + sw128_offset(r0 + 32 * i, j), v.x, v.y, v.z, v.w);
         }
       } else if (LOADER == LD_LN) {
         const bool kv = k0 < a.C;
         float g[8], bb[8];
-        if (a.do_ln && kv) {
-          const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.ln_w + k0));
-          const float4 g1 = __ldg(reinterpret_cast<const float4*>(a.ln_w + k0 + 4));
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.ln_b + k0));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.ln_b + k0 + 4));
-          g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
-          bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
-        }
+        if (a.do_ln && kv) { load8(a.ln_w + k0, g); load8(a.ln_b + k0, bb); }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 4; ++i) {
           float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
           if (tok[i] >= 0 && kv) {
-            const float* p = a.x + static_cast<size_t>(tok[i]) * a.C + k0;
-            const float4 v0 = __ldg(reinterpret_cast<const float4*>(p));
-            const float4 v1 = __ldg(reinterpret_cast<const float4*>(p + 4));
-            v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
-            if (a.do_ln) {
-              const float mu = s_mean[r0 + 16 * i], rs = s_rstd[r0 + 16 * i];
+            if (a.do_ln && KC == 1) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = (v[e] - mu) * rs * g[e] + bb[e];
+              for (int e = 0; e < 8; ++e) v[e] = keep[i][e];
+            } else {
+              load8(a.x + static_cast<size_t>(tok[i]) * a.C + k0, v);
+            }
+            if (a.do_ln) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = (v[e] - mean[i]) * rstd[i] * g[e] + bb[e];
             }
           }
-          st_smem_16B(tile + sw128_offset(r0 + 16 * i, j), pack_h2(v[0], v[1]), pack_h2(v[2], v[3]),
+          st_smem_16B(tile + sw128_offset(r0 + 32 * i, j), pack_h2(v[0], v[1]), pack_h2(v[2], v[3]),
                       pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
         }
       } else if (LOADER == LD_XH) {
@@ -278,7 +322,7 @@ __global__ void __launch_bounds__(160) gemm_fused_kernel(const __grid_constant__
         const bool conv_this = kv && ((a.dws_mode == 1 && is_h) || a.dws_mode == 2);
         const float* src = is_h ? a.hprev : a.x;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 4; ++i) {
           float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
           if (tok[i] >= 0 && kv) {
             if (conv_this) {
@@ -286,29 +330,28 @@ __global__ void __launch_bounds__(160) gemm_fused_kernel(const __grid_constant__
               dwconv8(src, C, ch, a.dw_w, a.dw_b, D, a.dws_mode == 2 ? k0 : ch, a.dws_ks, cb[i], ciy[i], cix[i],
                       a.map.H, a.map.W, v);
             } else if (src != nullptr) {
-              const float* p = src + static_cast<size_t>(tok[i]) * C + ch;
-              const float4 v0 = __ldg(reinterpret_cast<const float4*>(p));
-              const float4 v1 = __ldg(reinterpret_cast<const float4*>(p + 4));
-              v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
+              load8(src + static_cast<size_t>(tok[i]) * C + ch, v);
             }
           }
-          st_smem_16B(tile + sw128_offset(r0 + 16 * i, j), pack_h2(v[0], v[1]), pack_h2(v[2], v[3]),
+          st_smem_16B(tile + sw128_offset(r0 + 32 * i, j), pack_h2(v[0], v[1]), pack_h2(v[2], v[3]),
                       pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
         }
       } else {  // LD_CONV
-        __half hv[8][8];
-        const int KS = a.KS, Cin = a.Cin, Hin = a.Hin, Win = a.Win;
+        const int KSy = a.KSy, KSx = a.KSx, Cin = a.Cin, Hin = a.Hin, Win = a.Win;
         if (a.in_nchw) {
-          // k = ci*KS*KS + ky*KS + kx  (natural [Cout, Cin, KS, KS] weight order); scalar gathers
-          const int kk = KS * KS;
+          // k = ci*KSy*KSx + ky*KSx + kx  (natural [Cout, Cin, KS, KS] weight order); scalar gathers.
+          // Generic fallback for channels-first inputs; the stem normally goes through the
+          // space-to-depth transform (stem_s2d_kernel) and the channels-last branch below.
+          __half hv[4][8];
+          const int kk = KSy * KSx;
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int k = k0 + e;
             const int ci = k / kk, rem = k - ci * kk;
-            const int ky = rem / KS, kx = rem - ky * KS;
+            const int ky = rem / KSx, kx = rem - ky * KSx;
             const bool kv = k < a.K;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < 4; ++i) {
               const int iy = ciy[i] + ky, ix = cix[i] + kx;
               float f = 0.f;
               if (kv && tok[i] >= 0 && iy >= 0 && iy < Hin && ix >= 0 && ix < Win) {
@@ -320,30 +363,32 @@ __global__ void __launch_bounds__(160) gemm_fused_kernel(const __grid_constant__
               hv[i][e] = __float2half_rn(f);
             }
           }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t* u = reinterpret_cast<const uint32_t*>(&hv[i][0]);
+            st_smem_16B(tile + sw128_offset(r0 + 32 * i, j), u[0], u[1], u[2], u[3]);
+          }
         } else {
-          // channels-last input, k = (ky*KS + kx)*Cin + ci, Cin % 8 == 0
+          // channels-last input (f32 or f16), k = (ky*KSx + kx)*Cin + ci, Cin % 8 == 0
           const int tap = k0 / Cin, ci = k0 - tap * Cin;
-          const int ky = tap / KS, kx = tap - ky * KS;
+          const int ky = tap / KSx, kx = tap - ky * KSx;
           const bool kv = k0 < a.K;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 4; ++i) {
             const int iy = ciy[i] + ky, ix = cix[i] + kx;
-            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            uint4 o = make_uint4(0, 0, 0, 0);
             if (kv && tok[i] >= 0 && iy >= 0 && iy < Hin && ix >= 0 && ix < Win) {
-              const float* p = reinterpret_cast<const float*>(a.cin) +
-                               (static_cast<size_t>(cb[i] * Hin + iy) * Win + ix) * Cin + ci;
-              const float4 v0 = __ldg(reinterpret_cast<const float4*>(p));
-              const float4 v1 = __ldg(reinterpret_cast<const float4*>(p + 4));
-              v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
+              const size_t off = (static_cast<size_t>(cb[i] * Hin + iy) * Win + ix) * Cin + ci;
+              if (a.in_dtype == 2) {
+                o = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.cin) + off));
+              } else {
+                float v[8];
+                load8(reinterpret_cast<const float*>(a.cin) + off, v);
+                o = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+              }
             }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) hv[i][e] = __float2half_rn(v[e]);
+            st_smem_16B(tile + sw128_offset(r0 + 32 * i, j), o.x, o.y, o.z, o.w);
           }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint32_t* u = reinterpret_cast<const uint32_t*>(&hv[i][0]);
-          st_smem_16B(tile + sw128_offset(r0 + 16 * i, j), u[0], u[1], u[2], u[3]);
         }
       }
       fence_proxy_async_smem();
@@ -353,144 +398,160 @@ __global__ void __launch_bounds__(160) gemm_fused_kernel(const __grid_constant__
     // =========================== epilogue ===========================
     mbar_wait(accum, 0);
     tc_fence_after();
-    const int row = mt * 128 + tid;
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const int q = warp & 3, hsel = warp >> 2;
+    const int erow = q * 32 + lane;                 // accumulator row == TMEM lane
+    const int row = mt * 128 + erow;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const int etok = (EPI == EP_F16) ? row : row_to_token(a.map, row);
+    const int csplit = ((BN / 16 + 1) / 2) * 16;
+    const int cbeg = hsel ? csplit : 0, cend = hsel ? BN : csplit;
 
     if (EPI == EP_F16) {
       __half* dst = a.o16 + static_cast<size_t>(row) * a.ldo + nt * BN;
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        const int w = min(32, BN - c0);
-        float v[32];
-        if (w == 32) tmem_ld_x32(trow + c0, v); else tmem_ld_x16(trow + c0, v);
+      for (int c0 = cbeg; c0 < cend; c0 += 16) {
+        float v[16];
+        tmem_ld_x16(trow + c0, v);
         tmem_ld_wait();
+        if (a.bias) {
+          float bv[16];
+          load16(a.bias + nt * BN + c0, bv);
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          if (q < w) {
-            float t = v[q] + (a.bias ? __ldg(a.bias + nt * BN + c0 + q) : 0.f);
-            if (a.act == 1) t = gelu_erf(t);
-            v[q] = t;
-          }
+          for (int e = 0; e < 16; ++e) v[e] += bv[e];
         }
+        if (a.act == 1) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (q * 8 < w) {
-            uint4 o;
-            o.x = pack_h2(v[q * 8 + 0], v[q * 8 + 1]); o.y = pack_h2(v[q * 8 + 2], v[q * 8 + 3]);
-            o.z = pack_h2(v[q * 8 + 4], v[q * 8 + 5]); o.w = pack_h2(v[q * 8 + 6], v[q * 8 + 7]);
-            *reinterpret_cast<uint4*>(dst + c0 + q * 8) = o;
-          }
+          for (int e = 0; e < 16; ++e) v[e] = gelu_erf(v[e]);
         }
+        *reinterpret_cast<uint4*>(dst + c0) =
+            make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+        *reinterpret_cast<uint4*>(dst + c0 + 8) =
+            make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
       }
     } else if (EPI == EP_RES) {
       const int C = a.C;
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        const int w = min(32, BN - c0);
-        float v[32];
-        if (w == 32) tmem_ld_x32(trow + c0, v); else tmem_ld_x16(trow + c0, v);
+      for (int c0 = cbeg; c0 < cend; c0 += 16) {
+        float v[16];
+        tmem_ld_x16(trow + c0, v);
         tmem_ld_wait();
         if (etok >= 0) {
           const int col = nt * BN + c0;
           const float* rp = a.res + static_cast<size_t>(etok) * C + col;
           float* op = a.xout + static_cast<size_t>(etok) * C + col;
+          if (a.bias) {
+            float bv[16];
+            load16(a.bias + col, bv);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            if (q * 4 < w) {
-              const float4 r = *reinterpret_cast<const float4*>(rp + q * 4);  // plain load: res may alias xout
-              float4 o;
-              float acc[4] = {v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]};
-              float rr[4] = {r.x, r.y, r.z, r.w};
+            for (int e = 0; e < 16; ++e) v[e] += bv[e];
+          }
+          if (a.gamma) {
+            float gv[16];
+            load16(a.gamma + col, gv);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float t = acc[e] + (a.bias ? __ldg(a.bias + col + q * 4 + e) : 0.f);
-                if (a.gamma) t *= __ldg(a.gamma + col + q * 4 + e);
-                rr[e] += t;
-              }
-              o.x = rr[0]; o.y = rr[1]; o.z = rr[2]; o.w = rr[3];
-              *reinterpret_cast<float4*>(op + q * 4) = o;
-            }
+            for (int e = 0; e < 16; ++e) v[e] *= gv[e];
+          }
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            const float4 r = *reinterpret_cast<const float4*>(rp + qd * 4);  // plain load: res may alias xout
+            *reinterpret_cast<float4*>(op + qd * 4) =
+                make_float4(r.x + v[qd * 4], r.y + v[qd * 4 + 1], r.z + v[qd * 4 + 2], r.w + v[qd * 4 + 3]);
           }
         }
       }
     } else if (EPI == EP_LN) {
-      // LayerNorm over the BN == C conv output channels held in this thread's TMEM lane
+      // LayerNorm over the BN == C conv output channels: each half reduces its columns, the two
+      // partials of a row are exchanged through shared memory.
       float s = 0.f;
-      for (int c0 = 0; c0 < BN; c0 += 16) {
+      for (int c0 = cbeg; c0 < cend; c0 += 16) {
         float v[16];
         tmem_ld_x16(trow + c0, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 16; ++q) s += v[q];
+        for (int e = 0; e < 16; ++e) s += v[e];
       }
-      const float mean = s / BN;
+      s_red[hsel * 128 + erow] = s;
+      named_bar_sync(1, kWorkers);
+      const float mean_o = (s_red[erow] + s_red[128 + erow]) / BN;
+      named_bar_sync(2, kWorkers);
       float ss = 0.f;
-      for (int c0 = 0; c0 < BN; c0 += 16) {
+      for (int c0 = cbeg; c0 < cend; c0 += 16) {
         float v[16];
         tmem_ld_x16(trow + c0, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 16; ++q) { const float d = v[q] - mean; ss += d * d; }
+        for (int e = 0; e < 16; ++e) { const float d = v[e] - mean_o; ss += d * d; }
       }
-      const float rstd = rsqrtf(ss / BN + a.eeps);
+      s_red[hsel * 128 + erow] = ss;
+      named_bar_sync(1, kWorkers);
+      const float rstd_o = rsqrtf((s_red[erow] + s_red[128 + erow]) / BN + a.eeps);
       const bool masked = (etok >= 0) && a.token_mask && a.token_mask[etok];
-      for (int c0 = 0; c0 < BN; c0 += 16) {
+      for (int c0 = cbeg; c0 < cend; c0 += 16) {
         float v[16];
         tmem_ld_x16(trow + c0, v);
         tmem_ld_wait();
         if (etok >= 0) {
           float* op = a.yout + static_cast<size_t>(etok) * BN + c0;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float o[4];
+          for (int e = 0; e < 16; ++e) v[e] = (v[e] - mean_o) * rstd_o;
+          if (a.eln_w) {
+            float wv[16], bv[16];
+            load16(a.eln_w + c0, wv);
+            load16(a.eln_b + c0, bv);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int c = c0 + q * 4 + e;
-              float t = (v[q * 4 + e] - mean) * rstd;
-              if (a.eln_w) t = t * __ldg(a.eln_w + c) + __ldg(a.eln_b + c);
-              if (masked) t = __ldg(a.mask_token + c);
-              o[e] = t;
-            }
-            *reinterpret_cast<float4*>(op + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+            for (int e = 0; e < 16; ++e) v[e] = fmaf(v[e], wv[e], bv[e]);
           }
+          if (masked) load16(a.mask_token + c0, v);
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd)
+            *reinterpret_cast<float4*>(op + qd * 4) = make_float4(v[qd * 4], v[qd * 4 + 1], v[qd * 4 + 2], v[qd * 4 + 3]);
         }
       }
     } else {  // EP_LSTM: tile columns = [f | i | o | g] x cw channels  (rnn.py:57-67)
       const int cw = a.cw, C = a.C;
-      for (int j0 = 0; j0 < cw; j0 += 16) {
-        float f[16], ig[16], og[16], g[16];
-        tmem_ld_x16(trow + j0, f);
-        tmem_ld_x16(trow + cw + j0, ig);
-        tmem_ld_x16(trow + 2 * cw + j0, og);
-        tmem_ld_x16(trow + 3 * cw + j0, g);
+      const int jsplit = ((cw / 16 + 1) / 2) * 16;
+      const int jbeg = hsel ? jsplit : 0, jend = hsel ? cw : jsplit;
+      for (int j0 = jbeg; j0 < jend; j0 += 8) {
+        float f[8], ig[8], og[8], g[8];
+        tmem_ld_x8(trow + j0, f);
+        tmem_ld_x8(trow + cw + j0, ig);
+        tmem_ld_x8(trow + 2 * cw + j0, og);
+        tmem_ld_x8(trow + 3 * cw + j0, g);
         tmem_ld_wait();
         if (etok >= 0) {
           const int ch0 = nt * cw + j0;
           const float* bt = a.bias + nt * BN;
           const size_t off = static_cast<size_t>(etok) * C + ch0;
+          {
+            float bv[8];
+            load8(bt + j0, bv);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float4 cp = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a.cprev) cp = __ldg(reinterpret_cast<const float4*>(a.cprev + off + q * 4));
-            const float cpv[4] = {cp.x, cp.y, cp.z, cp.w};
-            float hn[4], cn[4];
+            for (int e = 0; e < 8; ++e) f[e] += bv[e];
+            load8(bt + cw + j0, bv);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int jj = j0 + q * 4 + e;
-              const float fg = sigmoid_acc(f[q * 4 + e] + __ldg(bt + jj));
-              const float i_ = sigmoid_acc(ig[q * 4 + e] + __ldg(bt + cw + jj));
-              const float o_ = sigmoid_acc(og[q * 4 + e] + __ldg(bt + 2 * cw + jj));
-              const float g_ = tanhf(g[q * 4 + e] + __ldg(bt + 3 * cw + jj));
-              cn[e] = fg * cpv[e] + i_ * g_;
-              hn[e] = o_ * tanhf(cn[e]);
-            }
-            *reinterpret_cast<float4*>(a.cout + off + q * 4) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-            *reinterpret_cast<float4*>(a.hout + off + q * 4) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+            for (int e = 0; e < 8; ++e) ig[e] += bv[e];
+            load8(bt + 2 * cw + j0, bv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) og[e] += bv[e];
+            load8(bt + 3 * cw + j0, bv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) g[e] += bv[e];
           }
+          float cpv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (a.cprev) load8(a.cprev + off, cpv);
+          float hn[8], cn[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            cn[e] = sigmoid_acc(f[e]) * cpv[e] + sigmoid_acc(ig[e]) * tanh_acc(g[e]);
+            hn[e] = sigmoid_acc(og[e]) * tanh_acc(cn[e]);
+          }
+          *reinterpret_cast<float4*>(a.cout + off) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+          *reinterpret_cast<float4*>(a.cout + off + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+          *reinterpret_cast<float4*>(a.hout + off) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+          *reinterpret_cast<float4*>(a.hout + off + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
         }
       }
     }
   } else {
-    // =========================== MMA issuer (warp 4, one lane) ===========================
+    // =========================== MMA issuer (warp 8, one lane) ===========================
     if (lane == 0) {
       const int n0 = BN > 256 ? 256 : BN;
       const int n1 = BN - n0;
@@ -520,7 +581,51 @@ __global__ void __launch_bounds__(160) gemm_fused_kernel(const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, a.tmem_cols);
+  if (warp == 8) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+// ----------------------------------------------------------------------------------------
+// Stem space-to-depth: channels-first event tensor [B, Cin, H, W] (u8 / f32 / f16) ->
+// fp16 [B, H, Wg, f*Cin] with Wg = ceil(Wv / f), element (b, y, g, sub*Cin + ci) =
+// in[b, ci, y, g*f + sub] (zero beyond W).  After it the overlapping (2f-1)x(2f-1)/stride-f stem
+// conv (maxvit.py:160-171) is a (2f-1) x 2 tap, stride (f, 1) conv over f*Cin channels whose
+// taps are 16-byte-vector loads (weights re-packed to match, packing.pack_stem_weight_s2d).
+// One CTA per (b, y, 64-pixel strip); transposes through shared memory so both the global reads
+// (along W) and the global writes (along channels) are coalesced.
+// ----------------------------------------------------------------------------------------
+constexpr int kS2dStrip = 256;   // pixels per CTA strip
+__global__ void __launch_bounds__(256) stem_s2d_kernel(const void* __restrict__ in, int in_dtype, int Cin, int H, int W,
+                                                       int Wg, int f, __half* __restrict__ out) {
+  extern __shared__ __half s_tile[];            // [Cin][kS2dStrip + 2]
+  const int strip = blockIdx.x, y = blockIdx.y, b = blockIdx.z;
+  const int x0 = strip * kS2dStrip;
+  const int tid = threadIdx.x;
+  const int pitch = kS2dStrip + 2;
+  for (int ci = 0; ci < Cin; ++ci) {             // one coalesced 256-pixel row segment per channel
+    const int x = x0 + tid;
+    float v = 0.f;
+    if (x < W) {
+      const size_t off = ((static_cast<size_t>(b) * Cin + ci) * H + y) * W + x;
+      if (in_dtype == 1) v = static_cast<float>(__ldg(reinterpret_cast<const uint8_t*>(in) + off));
+      else if (in_dtype == 2) v = __half2float(__ldg(reinterpret_cast<const __half*>(in) + off));
+      else v = __ldg(reinterpret_cast<const float*>(in) + off);
+    }
+    s_tile[ci * pitch + tid] = __float2half_rn(v);
+  }
+  __syncthreads();
+  const int gpc = kS2dStrip / f;                 // groups per strip (f divides 64)
+  const int cg = f * Cin;                        // channels per group (even: 16-byte aligned groups)
+  const int g0 = strip * gpc;
+  const int ngrp = min(gpc, Wg - g0);
+  __half2* out2 = reinterpret_cast<__half2*>(out + ((static_cast<size_t>(b) * H + y) * Wg + g0) * cg);
+  for (int idx = tid; idx < ngrp * (cg >> 1); idx += 256) {
+    const int e = idx * 2;
+    const int gl = e / cg, c = e - gl * cg;
+    const int c1 = c + 1;
+    const int sub0 = c / Cin, ci0 = c - sub0 * Cin;
+    const int sub1 = c1 / Cin, ci1 = c1 - sub1 * Cin;
+    out2[idx] = __halves2half2(s_tile[ci0 * pitch + gl * f + sub0], s_tile[ci1 * pitch + gl * f + sub1]);
+  }
 }
 
 }  // namespace rvt

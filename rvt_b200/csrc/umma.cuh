@@ -111,6 +111,14 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float* v) {
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+
 // ----------------------------------------------------------------------------------------
 // UMMA (tcgen05.mma) — operands in shared memory, K-major, 128-byte swizzle.
 //
@@ -166,6 +174,16 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 // ----------------------------------------------------------------------------------------
 // small helpers
 // ----------------------------------------------------------------------------------------
+__device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP, ~1 ulp
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {   // MUFU.EX2, ~2 ulp
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);

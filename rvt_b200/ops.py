@@ -17,10 +17,13 @@ def _stream(t: torch.Tensor):
 def downsample_cf2cl(x: torch.Tensor, x_is_nchw: bool, conv_w_packed: torch.Tensor, cout: int, ksize: int,
                      stride: int, pad: int, ln_w: Optional[torch.Tensor], ln_b: Optional[torch.Tensor],
                      virtual_hw: Optional[Tuple[int, int]] = None, token_mask: Optional[torch.Tensor] = None,
-                     mask_token: Optional[torch.Tensor] = None, eps: float = 1e-5) -> torch.Tensor:
+                     mask_token: Optional[torch.Tensor] = None, eps: float = 1e-5,
+                     s2d_scratch: Optional[torch.Tensor] = None) -> torch.Tensor:
     """ConvDownsampling_Cf2Cl.forward (maxvit.py:174-178) [+ mask token, maxvit_rnn.py:174-176].
     x: [B,Cin,H,W] (f32/u8/f16) if x_is_nchw else [B,H,W,Cin] f32.  -> f32 [B,Hout,Wout,cout]."""
     assert x.is_cuda and x.is_contiguous() and x.dtype in _IN_DTYPES
+    if s2d_scratch is not None:
+        assert x_is_nchw and s2d_scratch.dtype == torch.float16
     if x_is_nchw:
         b, cin, hin, win = x.shape
     else:
@@ -37,8 +40,16 @@ def downsample_cf2cl(x: torch.Tensor, x_is_nchw: bool, conv_w_packed: torch.Tens
     _lib.check(L.rvt_downsample_cf2cl(
         _lib.ptr(x), _IN_DTYPES[x.dtype], int(x_is_nchw), b, cin, hin, win, ksize, stride, pad, hout, wout, cout,
         _lib.ptr(conv_w_packed), _lib.ptr(ln_w), _lib.ptr(ln_b), eps, _lib.ptr(token_mask), _lib.ptr(mask_token),
-        _lib.ptr(out), _stream(x)), 'downsample_cf2cl')
+        _lib.ptr(out), _lib.ptr(s2d_scratch), _stream(x)), 'downsample_cf2cl')
     return out
+
+
+def stem_uses_s2d(cin: int, factor: int, ksize: int, pad: int, virtual_w: int) -> bool:
+    """The space-to-depth stem path applies to the reference's two stem geometries when the
+    grouped channel count is 16-byte aligned."""
+    overlap = ksize == 2 * factor - 1 and pad == factor - 1
+    patch = ksize == factor and pad == 0
+    return (overlap or patch) and 64 % factor == 0 and (factor * cin) % 8 == 0 and virtual_w % factor == 0
 
 
 def attention_scratch_rows(b, h, w, part) -> int:

@@ -58,3 +58,25 @@ def pack_dw_weight(w: torch.Tensor) -> torch.Tensor:
     """depthwise weight [D, 1, ks, ks] -> tap-major [ks*ks, D] fp32."""
     d, _, ks, _ = w.shape
     return w.detach().float().reshape(d, ks * ks).t().contiguous()
+
+
+def pack_stem_weight_s2d(w: torch.Tensor, factor: int) -> torch.Tensor:
+    """Stem conv weight [Cout, Cin, KS, KS] for the space-to-depth input layout
+    [B, H, W/f, f*Cin] (csrc/gemm_fused.cuh stem_s2d_kernel): K order (ky, t, sub, ci) where the
+    x-tap t in {0,1} selects pixel group ox-1+t and sub the pixel inside the group.
+    Overlapping stem (KS = 2f-1, pad f-1): kx = sub-1 for t=0 (sub>=1), kx = sub+f-1 for t=1.
+    Patch stem (KS = f, pad 0): single x-tap, kx = sub."""
+    co, cin, ks, _ = w.shape
+    f = factor
+    wf = w.detach().float()
+    if ks == 2 * f - 1:
+        w2 = torch.zeros(co, ks, 2, f, cin, device=w.device)
+        for sub in range(1, f):
+            w2[:, :, 0, sub, :] = wf[:, :, :, sub - 1].permute(0, 2, 1)
+        for sub in range(f):
+            w2[:, :, 1, sub, :] = wf[:, :, :, sub + f - 1].permute(0, 2, 1)
+    elif ks == f:
+        w2 = wf.permute(0, 2, 3, 1).reshape(co, ks, 1, f, cin)
+    else:
+        raise ValueError('unsupported stem geometry')
+    return _swizzle_tiles(w2.reshape(co, -1), co)

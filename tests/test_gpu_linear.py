@@ -17,7 +17,7 @@ def run_linear(a16, w, bias, act=0):
     m, k = a16.shape
     n = w.shape[0]
     dev = a16.device
-    wp = packing.pack_linear_weight(w.to(dev), L.rvt_tile_n(n))
+    wp = packing.pack_linear_weight(w.to(dev), L.rvt_tile_n(n, k))
     out = torch.zeros(((m + 127) // 128) * 128, n, dtype=torch.float16, device=dev)
     _lib.check(L.rvt_linear_f16(_lib.ptr(a16), m, k, n, _lib.ptr(wp), _lib.ptr(bias), act, _lib.ptr(out),
                                 torch.cuda.current_stream().cuda_stream), 'linear_f16')

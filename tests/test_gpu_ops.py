@@ -57,10 +57,16 @@ def test_each_operator_with_oracle_inputs(name):
         for s, (st, pk) in enumerate(zip(m.stages, packed)):
             d = st.downsample_cf2cl
             pre = f'stages.{s}.'
+            tm = mask.to(dev) if (mask is not None and s == 0) else None
             got = ops.downsample_cf2cl(cur, cur_nchw, pk['conv_w'], st.dim, d.kernel_size, d.factor, d.padding,
-                                       pk['ds_ln_w'], pk['ds_ln_b'], token_mask=mask.to(dev) if (mask is not None and s == 0) else None,
-                                       mask_token=pk['mask_token'])
+                                       pk['ds_ln_w'], pk['ds_ln_b'], token_mask=tm, mask_token=pk['mask_token'])
             rec(step, pre + 'downsample', got, taps[pre + 'downsample'])
+            if s == 0:      # stem fast path (space-to-depth) and uint8 input must agree with the generic gather path
+                s2d = torch.empty(cur.numel(), dtype=torch.float16, device=dev)
+                got2 = ops.downsample_cf2cl(cur.to(torch.uint8), True, pk['conv_w_s2d'], st.dim, d.kernel_size, d.factor,
+                                            d.padding, pk['ds_ln_w'], pk['ds_ln_b'], token_mask=tm,
+                                            mask_token=pk['mask_token'], s2d_scratch=s2d)
+                rec(step, pre + 'downsample(s2d,u8)', got2, taps[pre + 'downsample'])
             xin = taps[pre + 'downsample']
             b, hh, ww, c = xin.shape
             for bi, blk in enumerate(pk['blocks']):
