@@ -28,6 +28,11 @@ const char* rvt_error_string(int code);
 /* ---- tiling contract shared with the host-side weight packer (rvt_b200/packing.py) ---- */
 /* N-tile (columns per CTA) used for a Linear with n_total output and k input features. */
 int rvt_tile_n(int n_total, int k);
+/* N-tiles the MLP weights must be packed with (fc1 [hidden, dim], fc2 [dim, hidden]); returns 1 when
+ * rvt_mlp_block runs as one fused kernel (dim <= 128), 0 for the two-GEMM path. */
+int rvt_mlp_tiles(int dim, int hidden, int* bn_fc1, int* bn_fc2);
+/* N-tile of the downsample conv with cout output channels (cout itself = fused LayerNorm). */
+int rvt_conv_tile_n(int cout);
 /* Channels per CTA for the Conv-LSTM gate GEMM (tile = [f|i|o|g] x cw columns). */
 int rvt_lstm_cw(int dim);
 /* Rows one partition group occupies in a 128-row tile (64 or 128; <0 if P > 128). */
@@ -63,20 +68,22 @@ int rvt_downsample_cf2cl(const void* in, int in_dtype, int in_nchw, int batch, i
 /* ---- a4-a7: attention half of PartitionAttentionCl.forward  (maxvit.py:252-268, 273-354) -
  * x <- x + gamma1 * proj(attn(partition(norm1(x))))   in place, x: f32 [B,H,W,C].
  * grid = 0: window partition, 1: grid partition.  n1_w/n1_b NULL => norm1 = Identity.
- * gamma1 NULL => LayerScale = Identity.  scratch_qkv: f16 [rows, 3C], scratch_o: f16 [rows, C]
- * with rows = rvt_attention_scratch_rows(). */
+ * gamma1 NULL => LayerScale = Identity.  scratch_qkv: f16 [rows, 3C], scratch_o and scratch_xn:
+ * f16 [rows, C], rows = rvt_attention_scratch_rows() (scratch_xn is only touched when C >= 256). */
 int rvt_partition_attention(float* x, int batch, int height, int width, int dim, int ph, int pw, int grid,
                             int dim_head, const float* n1_w, const float* n1_b, float eps,
                             const void* wqkv_packed, const float* bqkv, const void* wproj_packed,
                             const float* bproj, const float* gamma1, void* scratch_qkv, void* scratch_o,
-                            void* stream);
+                            void* scratch_xn, void* stream);
 
 /* ---- a8: MLP half of PartitionAttentionCl.forward  (maxvit.py:85-118, 269) --------------
  * x <- x + gamma2 * fc2(gelu(fc1(norm2(x))))   in place, x: f32 [n_tokens, C].
- * scratch_hidden: f16 [round_up(n_tokens,128), hidden]. */
+ * w1_packed / w2_packed: pack_linear_weight() with the N-tiles from rvt_mlp_tiles().
+ * scratch_hidden: f16 [round_up(n_tokens,128), hidden]; scratch_xn: f16 [round_up(n_tokens,128), C]
+ * (only touched when C >= 256). */
 int rvt_mlp_block(float* x, int64_t n_tokens, int dim, int hidden, const float* n2_w, const float* n2_b,
                   float eps, const void* w1_packed, const float* b1, const void* w2_packed, const float* b2,
-                  const float* gamma2, void* scratch_hidden, void* stream);
+                  const float* gamma2, void* scratch_hidden, void* scratch_xn, void* stream);
 
 /* ---- a9: DWSConvLSTM2d.forward  (models/layers/rnn.py:36-69) ---------------------------
  * x, h_prev, c_prev, h_out, c_out: f32 [B,H,W,C]; h_prev/c_prev NULL => zero state.

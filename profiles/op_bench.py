@@ -83,10 +83,11 @@ def main():
             rows_s = ops.attention_scratch_rows(B, ho, wo, blk['part'])
             sq = torch.empty(rows_s * 3 * c, dtype=torch.float16, device=dev)
             so = torch.empty(rows_s * c, dtype=torch.float16, device=dev)
+            sxn = torch.empty(max(rows_s, ((n + 127) // 128) * 128) * c, dtype=torch.float16, device=dev)
             sh = torch.empty(((n + 127) // 128) * 128 * 4 * c, dtype=torch.float16, device=dev)
             P = blk['part'][0] * blk['part'][1]
-            timeit('attn', s, lambda: ops.partition_attention_(xs, blk, sq, so), 8 * n * c * c + 4 * n * P * c, 2 * n * c * 4)
-            timeit('mlp', s, lambda: ops.mlp_block_(xs, blk, sh), 16 * n * c * c, 2 * n * c * 4)
+            timeit('attn', s, lambda: ops.partition_attention_(xs, blk, sq, so, sxn), 8 * n * c * c + 4 * n * P * c, 2 * n * c * 4)
+            timeit('mlp', s, lambda: ops.mlp_block_(xs, blk, sh, sxn), 16 * n * c * c, 2 * n * c * 4)
             hp, cp = torch.randn_like(xs), torch.randn_like(xs)
             timeit('lstm', s, lambda: ops.dws_conv_lstm(xs, hp, cp, pk, 3), 16 * n * c * c, 5 * n * c * 4)
             h, w, cin = ho, wo, c

@@ -14,6 +14,8 @@ SIGNATURES = {
     'rvt_abi_version': (_i, []),
     'rvt_error_string': (_c.c_char_p, [_i]),
     'rvt_tile_n': (_i, [_i, _i]),
+    'rvt_mlp_tiles': (_i, [_i, _i, _vp, _vp]),
+    'rvt_conv_tile_n': (_i, [_i]),
     'rvt_lstm_cw': (_i, [_i]),
     'rvt_rows_per_group': (_i, [_i]),
     'rvt_attention_scratch_rows': (_i64, [_i, _i, _i, _i, _i]),
@@ -21,8 +23,8 @@ SIGNATURES = {
     'rvt_downsample_cf2cl': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f,
                                    _vp, _vp, _vp, _vp, _vp]),
     'rvt_partition_attention': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp,
-                                      _vp, _vp, _vp, _vp]),
-    'rvt_mlp_block': (_i, [_vp, _i64, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                                      _vp, _vp, _vp, _vp, _vp]),
+    'rvt_mlp_block': (_i, [_vp, _i64, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'rvt_dws_conv_lstm': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     'rvt_linear_f16': (_i, [_vp, _i64, _i, _i, _vp, _vp, _i, _vp, _vp]),
 }
@@ -57,3 +59,10 @@ def check(code: int, what: str):
 def ptr(t):
     """Device pointer of a tensor (None -> NULL)."""
     return None if t is None else t.data_ptr()
+
+
+def mlp_tiles(dim: int, hidden: int):
+    """(bn_fc1, bn_fc2, fused) — the N-tiles rvt_mlp_block expects its weights packed with."""
+    b1, b2 = ctypes.c_int(0), ctypes.c_int(0)
+    fused = lib().rvt_mlp_tiles(dim, hidden, ctypes.addressof(b1), ctypes.addressof(b2))
+    return b1.value, b2.value, bool(fused)

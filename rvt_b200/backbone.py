@@ -260,7 +260,8 @@ class RNNDetector(nn.Module):
         for s, st in enumerate(self.stages):
             c = st.dim
             d = st.downsample_cf2cl
-            e = {'conv_w': packing.pack_conv_weight(d.conv.weight.to(device), channels_last_input=s > 0),
+            e = {'conv_w': packing.pack_conv_weight(d.conv.weight.to(device), channels_last_input=s > 0,
+                                                    bn=L.rvt_conv_tile_n(c)),
                  'conv_w_s2d': (packing.pack_stem_weight_s2d(d.conv.weight.to(device), d.factor)
                                 if s == 0 and (d.factor * st.dim_in) % 8 == 0 else None),
                  'ds_ln_w': f32(getattr(d.norm, 'weight', None)), 'ds_ln_b': f32(getattr(d.norm, 'bias', None)),
@@ -270,6 +271,7 @@ class RNNDetector(nn.Module):
                 for att in (pair.att_window, pair.att_grid):
                     sa, mlp = att.self_attn, att.mlp
                     fc1, fc2 = mlp.net[0][0], mlp.net[2]
+                    bn1, bn2, _ = _lib.mlp_tiles(c, fc1.weight.shape[0])
                     e['blocks'].append({
                         'grid': 0 if att.window else 1, 'part': att.partition_size, 'dh': att.dim_head, 'eps': att.eps,
                         'n1_w': f32(getattr(att.norm1, 'weight', None)), 'n1_b': f32(getattr(att.norm1, 'bias', None)),
@@ -280,9 +282,9 @@ class RNNDetector(nn.Module):
                         'g1': f32(getattr(att.ls1, 'gamma', None)),
                         'n2_w': f32(att.norm2.weight), 'n2_b': f32(att.norm2.bias),
                         'hidden': fc1.weight.shape[0],
-                        'w1': packing.pack_linear_weight(fc1.weight.to(device), L.rvt_tile_n(fc1.weight.shape[0], c)),
+                        'w1': packing.pack_linear_weight(fc1.weight.to(device), bn1),
                         'b1': f32(getattr(fc1, 'bias', None)),
-                        'w2': packing.pack_linear_weight(fc2.weight.to(device), L.rvt_tile_n(c, fc2.weight.shape[1])),
+                        'w2': packing.pack_linear_weight(fc2.weight.to(device), bn2),
                         'b2': f32(getattr(fc2, 'bias', None)),
                         'g2': f32(getattr(att.ls2, 'gamma', None)),
                     })
@@ -363,11 +365,12 @@ class RNNDetector(nn.Module):
                 rows = ops.attention_scratch_rows(b, hh, ww, blk['part'])
                 sq = self._scratch_buf('qkv', rows * 3 * c, torch.float16, dev)
                 so = self._scratch_buf('o', rows * c, torch.float16, dev)
-                ops.partition_attention_(xs, blk, sq, so)
+                sx = self._scratch_buf('xn', max(rows, ((n_tok + 127) // 128) * 128) * c, torch.float16, dev)
+                ops.partition_attention_(xs, blk, sq, so, sx)
                 if taps is not None:
                     taps[tap_prefix + 'x_attn'] = xs.clone()
                 sh = self._scratch_buf('hidden', ((n_tok + 127) // 128) * 128 * blk['hidden'], torch.float16, dev)
-                ops.mlp_block_(xs, blk, sh)
+                ops.mlp_block_(xs, blk, sh, sx)
                 if taps is not None:
                     taps[tap_prefix + 'x_mlp'] = xs.clone()
             hp = cp = None

@@ -6,6 +6,7 @@
 
 #include "attention_core.cuh"
 #include "gemm_fused.cuh"
+#include "mlp_fused.cuh"
 #include "voxel.cuh"
 
 using namespace rvt;
@@ -42,6 +43,20 @@ int launch_gemm(GemmArgs a, int n_mtiles, int n_ntiles, cudaStream_t st) {
   return static_cast<int>(cudaGetLastError());
 }
 
+// Stages at least this wide normalise / cast their GEMM A operands once (ln_rows_kernel) instead
+// of inside every N-tile CTA, and run the downsample conv N-split with a separate LayerNorm.
+constexpr int kWideDim = 256;
+
+template <bool OUT_F16>
+int launch_ln_rows(const float* x, const RowMap& map, int64_t n_rows, int C, int do_ln, const float* w, const float* b,
+                   float eps, void* out, const uint8_t* mask, const float* mask_token, cudaStream_t st) {
+  if (C % 128 != 0 || C > 512) return kErrUnsupported;
+  if (n_rows <= 0) return 0;
+  ln_rows_kernel<OUT_F16><<<static_cast<unsigned>((n_rows + 7) / 8), 256, 0, st>>>(x, map, static_cast<int>(n_rows), C, do_ln, w,
+                                                                                  b, eps, out, mask, mask_token);
+  return static_cast<int>(cudaGetLastError());
+}
+
 RowMap identity_map(int64_t n_tokens, int H, int W) {
   RowMap m{};
   m.mode = MAP_IDENTITY;
@@ -72,6 +87,17 @@ int rvt_tile_n(int n_total, int k) {
     if (n_total % bn == 0) return bn;
   return -1;
 }
+
+int rvt_mlp_tiles(int dim, int hidden, int* bn_fc1, int* bn_fc2) {
+  // Narrow stages run the fused MLP kernel (mlp_fused.cuh): fc1 in 64-column chunks, fc2 as one
+  // N-tile of `dim` rows.  Wide stages keep two N-split GEMM launches.
+  const bool fused = dim <= 128 && dim % 16 == 0 && hidden % 64 == 0;
+  if (bn_fc1) *bn_fc1 = fused ? kMlpHC : rvt_tile_n(hidden, dim);
+  if (bn_fc2) *bn_fc2 = fused ? dim : rvt_tile_n(dim, hidden);
+  return fused ? 1 : 0;
+}
+
+int rvt_conv_tile_n(int cout) { return (cout >= kWideDim && cout % 128 == 0) ? 64 : cout; }
 
 int rvt_lstm_cw(int dim) {
   for (int cw = 64; cw >= 16; cw -= 16)
@@ -149,13 +175,21 @@ int rvt_downsample_cf2cl(const void* in, int in_dtype, int in_nchw, int batch, i
   }
   a.K = a.Cin * a.KSy * a.KSx;
   a.yout = out; a.eln_w = ln_w; a.eln_b = ln_b; a.eeps = eps; a.token_mask = token_mask; a.mask_token = mask_token;
+  if (cout >= kWideDim && cout % 128 == 0) {
+    // few row tiles: split N across CTAs (raw fp32 conv output), then LayerNorm the rows in place
+    a.BN = rvt_conv_tile_n(cout);
+    a.ldo = cout;
+    int rc = launch_gemm<LD_CONV, EP_RAW>(a, cdiv(n_tok, 128), cout / a.BN, st);
+    if (rc) return rc;
+    return launch_ln_rows<false>(out, a.map, n_tok, cout, 1, ln_w, ln_b, eps, out, token_mask, mask_token, st);
+  }
   return launch_gemm<LD_CONV, EP_LN>(a, cdiv(n_tok, 128), 1, st);
 }
 
 int rvt_partition_attention(float* x, int batch, int height, int width, int dim, int ph, int pw, int grid,
                             int dim_head, const float* n1_w, const float* n1_b, float eps, const void* wqkv_packed,
                             const float* bqkv, const void* wproj_packed, const float* bproj, const float* gamma1,
-                            void* scratch_qkv, void* scratch_o, void* stream) {
+                            void* scratch_qkv, void* scratch_o, void* scratch_xn, void* stream) {
   if (!x || !wqkv_packed || !wproj_packed || !scratch_qkv || !scratch_o) return kErrBadArg;
   if (dim % 8 != 0 || dim > 512 || dim_head % 8 != 0 || dim_head > 64 || dim % dim_head != 0) return kErrUnsupported;
   const int64_t rows = rvt_attention_scratch_rows(batch, height, width, ph, pw);
@@ -173,9 +207,18 @@ int rvt_partition_attention(float* x, int batch, int height, int width, int dim,
     GemmArgs a{};
     a.K = dim; a.BN = rvt_tile_n(3 * dim, dim);
     a.Wp = static_cast<const __half*>(wqkv_packed); a.bias = bqkv; a.map = m;
-    a.x = x; a.C = dim; a.ln_w = n1_w; a.ln_b = n1_b; a.eps = eps; a.do_ln = n1_w != nullptr;
     a.o16 = static_cast<__half*>(scratch_qkv); a.ldo = 3 * dim; a.act = 0;
-    int rc = launch_gemm<LD_LN, EP_F16>(a, n_mtiles, 3 * dim / a.BN, st);
+    int rc;
+    if (dim >= kWideDim && dim % 128 == 0) {
+      if (!scratch_xn) return kErrBadArg;
+      rc = launch_ln_rows<true>(x, m, rows, dim, n1_w != nullptr, n1_w, n1_b, eps, scratch_xn, nullptr, nullptr, st);
+      if (rc) return rc;
+      a.a16 = static_cast<const __half*>(scratch_xn); a.lda = dim; a.a_rows = static_cast<int>(rows);
+      rc = launch_gemm<LD_F16, EP_F16>(a, n_mtiles, 3 * dim / a.BN, st);
+    } else {
+      a.x = x; a.C = dim; a.ln_w = n1_w; a.ln_b = n1_b; a.eps = eps; a.do_ln = n1_w != nullptr;
+      rc = launch_gemm<LD_LN, EP_F16>(a, n_mtiles, 3 * dim / a.BN, st);
+    }
     if (rc) return rc;
   }
   // 2) per-(tile, head) softmax(q k^T * scale) v   (maxvit.py:349-352)
@@ -210,24 +253,57 @@ int rvt_partition_attention(float* x, int batch, int height, int width, int dim,
 
 int rvt_mlp_block(float* x, int64_t n_tokens, int dim, int hidden, const float* n2_w, const float* n2_b, float eps,
                   const void* w1_packed, const float* b1, const void* w2_packed, const float* b2, const float* gamma2,
-                  void* scratch_hidden, void* stream) {
+                  void* scratch_hidden, void* scratch_xn, void* stream) {
   if (!x || !w1_packed || !w2_packed || !scratch_hidden || !n2_w || !n2_b) return kErrBadArg;
   if (dim % 8 != 0 || dim > 512 || hidden % 16 != 0) return kErrUnsupported;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int n_mtiles = cdiv(n_tokens, 128);
+  int bn1 = 0, bn2 = 0;
+  if (rvt_mlp_tiles(dim, hidden, &bn1, &bn2)) {
+    MlpArgs ma{};
+    ma.x = x; ma.n_tokens = static_cast<int>(n_tokens); ma.C = dim; ma.hidden = hidden;
+    ma.ln_w = n2_w; ma.ln_b = n2_b; ma.eps = eps;
+    ma.w1p = static_cast<const __half*>(w1_packed); ma.b1 = b1;
+    ma.w2p = static_cast<const __half*>(w2_packed); ma.b2 = b2; ma.gamma = gamma2;
+    if (!b1 || !b2) return kErrUnsupported;
+    int stages = hidden / kMlpHC < 4 ? hidden / kMlpHC : 4;
+    while (stages > 2 && mlp_smem_bytes(dim, stages) > 110 * 1024) --stages;
+    ma.stages = stages;
+    const size_t smem = mlp_smem_bytes(dim, stages);
+    if (smem > static_cast<size_t>(kMaxSmem)) return kErrUnsupported;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      attr_set = true;
+    }
+    if (n_mtiles <= 0) return 0;
+    mlp_fused_kernel<<<n_mtiles, kMlpThreads, smem, st>>>(ma);
+    return static_cast<int>(cudaGetLastError());
+  }
   RowMap m = identity_map(n_tokens, 1, static_cast<int>(n_tokens));
   {
     GemmArgs a{};
-    a.K = dim; a.BN = rvt_tile_n(hidden, dim);
+    a.K = dim; a.BN = bn1;
     a.Wp = static_cast<const __half*>(w1_packed); a.bias = b1; a.map = m;
-    a.x = x; a.C = dim; a.ln_w = n2_w; a.ln_b = n2_b; a.eps = eps; a.do_ln = 1;
     a.o16 = static_cast<__half*>(scratch_hidden); a.ldo = hidden; a.act = 1;
-    int rc = launch_gemm<LD_LN, EP_F16>(a, n_mtiles, hidden / a.BN, st);
+    int rc;
+    if (dim >= kWideDim && dim % 128 == 0) {
+      if (!scratch_xn) return kErrBadArg;
+      rc = launch_ln_rows<true>(x, m, static_cast<int64_t>(n_mtiles) * 128, dim, 1, n2_w, n2_b, eps, scratch_xn, nullptr, nullptr, st);
+      if (rc) return rc;
+      a.a16 = static_cast<const __half*>(scratch_xn); a.lda = dim; a.a_rows = n_mtiles * 128;
+      rc = launch_gemm<LD_F16, EP_F16>(a, n_mtiles, hidden / a.BN, st);
+    } else {
+      a.x = x; a.C = dim; a.ln_w = n2_w; a.ln_b = n2_b; a.eps = eps; a.do_ln = 1;
+      rc = launch_gemm<LD_LN, EP_F16>(a, n_mtiles, hidden / a.BN, st);
+    }
     if (rc) return rc;
   }
   {
     GemmArgs a{};
-    a.K = hidden; a.BN = rvt_tile_n(dim, hidden);
+    a.K = hidden; a.BN = bn2;
     a.Wp = static_cast<const __half*>(w2_packed); a.bias = b2; a.map = m;
     a.a16 = static_cast<const __half*>(scratch_hidden); a.lda = hidden; a.a_rows = n_mtiles * 128;
     a.C = dim; a.res = x; a.xout = x; a.gamma = gamma2;

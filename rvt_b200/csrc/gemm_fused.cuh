@@ -14,6 +14,7 @@
 //                     scattered back through the partition map = window/grid reverse)
 //            EP_LN  : LayerNorm over the C output channels of the conv (+ mask token)
 //            EP_LSTM: gates -> (h_t, c_t)  (rnn.py:57-67)
+//            EP_RAW : plain fp32 store (N-split conv of the wide stages; LN follows in ln_rows_kernel)
 //
 // Roles: warps 0-3 build A tiles (registers -> swizzled smem) and later run the epilogue
 // (thread t owns accumulator row t = TMEM lane t); thread 0 also streams the pre-packed
@@ -24,7 +25,7 @@
 namespace rvt {
 
 enum { LD_F16 = 0, LD_LN = 1, LD_CONV = 2, LD_XH = 3 };
-enum { EP_F16 = 0, EP_RES = 1, EP_LN = 2, EP_LSTM = 3 };
+enum { EP_F16 = 0, EP_RES = 1, EP_LN = 2, EP_LSTM = 3, EP_RAW = 4 };
 enum { MAP_IDENTITY = 0, MAP_WINDOW = 1, MAP_GRID = 2 };
 
 // tile row -> token of a [B, H, W, C] channels-last tensor
@@ -457,6 +458,18 @@ __global__ void __launch_bounds__(kGemmThreads, 3) gemm_fused_kernel(const __gri
           }
         }
       }
+    } else if (EPI == EP_RAW) {
+      for (int c0 = cbeg; c0 < cend; c0 += 16) {
+        float v[16];
+        tmem_ld_x16(trow + c0, v);
+        tmem_ld_wait();
+        if (etok >= 0) {
+          float* op = a.yout + static_cast<size_t>(etok) * a.ldo + nt * BN + c0;
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd)
+            *reinterpret_cast<float4*>(op + qd * 4) = make_float4(v[qd * 4], v[qd * 4 + 1], v[qd * 4 + 2], v[qd * 4 + 3]);
+        }
+      }
     } else if (EPI == EP_LN) {
       // LayerNorm over the BN == C conv output channels: each half reduces its columns, the two
       // partials of a row are exchanged through shared memory.
@@ -582,6 +595,85 @@ __global__ void __launch_bounds__(kGemmThreads, 3) gemm_fused_kernel(const __gri
   tc_fence_before();
   __syncthreads();
   if (warp == 8) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+// ----------------------------------------------------------------------------------------
+// Row LayerNorm / cast, one warp per output row (wide stages, C >= 256: normalise ONCE into the
+// fp16 operand matrix instead of inside every N-tile CTA of the following GEMM).
+//   out row r <- LN(x[token(r)]) (x itself when !do_ln; affine iff ln_w); rows with no token -> zeros.
+//   OUT_F16: fp16 [n_rows, C] (GEMM A operand, rows in `map` order);  else fp32 in token order
+//   (conv output LayerNorm, maxvit.py:172,177, + mask token maxvit_rnn.py:174-176), in place OK.
+// C % 128 == 0, C <= 512.
+// ----------------------------------------------------------------------------------------
+template <bool OUT_F16>
+__global__ void __launch_bounds__(256) ln_rows_kernel(const float* x, RowMap map, int n_rows, int C, int do_ln, const float* __restrict__ ln_w,
+                                                      const float* __restrict__ ln_b, float eps, void* out,
+                                                      const uint8_t* __restrict__ token_mask,
+                                                      const float* __restrict__ mask_token) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n_rows) return;
+  const int tok = row_to_token(map, row);
+  const int ng = C >> 7;                       // float4 groups per lane (<= 4)
+  float v[16];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g < ng && tok >= 0) t = *reinterpret_cast<const float4*>(x + static_cast<size_t>(tok) * C + g * 128 + lane * 4);
+    v[4 * g] = t.x; v[4 * g + 1] = t.y; v[4 * g + 2] = t.z; v[4 * g + 3] = t.w;
+  }
+  if (do_ln) {
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) s += v[e];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / C;
+    float ss = 0.f;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (g < ng) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float d = v[4 * g + e] - mean; ss += d * d; }
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss / C + eps);
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (g < ng) {
+        float4 w = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ln_w != nullptr) {
+          w = __ldg(reinterpret_cast<const float4*>(ln_w + g * 128 + lane * 4));
+          b = __ldg(reinterpret_cast<const float4*>(ln_b + g * 128 + lane * 4));
+        }
+        v[4 * g] = (v[4 * g] - mean) * rstd * w.x + b.x;
+        v[4 * g + 1] = (v[4 * g + 1] - mean) * rstd * w.y + b.y;
+        v[4 * g + 2] = (v[4 * g + 2] - mean) * rstd * w.z + b.z;
+        v[4 * g + 3] = (v[4 * g + 3] - mean) * rstd * w.w + b.w;
+      }
+  }
+  if (tok < 0) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = 0.f;
+  }
+  if (OUT_F16) {
+    __half* o = reinterpret_cast<__half*>(out) + static_cast<size_t>(row) * C;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (g < ng)
+        *reinterpret_cast<uint2*>(o + g * 128 + lane * 4) = make_uint2(pack_h2(v[4 * g], v[4 * g + 1]), pack_h2(v[4 * g + 2], v[4 * g + 3]));
+  } else if (tok >= 0) {
+    const bool masked = token_mask != nullptr && token_mask[tok];
+    float* o = reinterpret_cast<float*>(out) + static_cast<size_t>(tok) * C;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (g < ng) {
+        float4 t = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+        if (masked) t = __ldg(reinterpret_cast<const float4*>(mask_token + g * 128 + lane * 4));
+        *reinterpret_cast<float4*>(o + g * 128 + lane * 4) = t;
+      }
+  }
 }
 
 // ----------------------------------------------------------------------------------------

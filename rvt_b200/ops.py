@@ -59,7 +59,8 @@ def attention_scratch_rows(b, h, w, part) -> int:
     return rows
 
 
-def partition_attention_(x: torch.Tensor, blk: dict, scratch_qkv: torch.Tensor, scratch_o: torch.Tensor) -> None:
+def partition_attention_(x: torch.Tensor, blk: dict, scratch_qkv: torch.Tensor, scratch_o: torch.Tensor,
+                         scratch_xn: Optional[torch.Tensor] = None) -> None:
     """In place: x += ls1(proj(attn(partition(norm1(x)))))  (maxvit.py:252-268)."""
     assert x.is_cuda and x.is_contiguous() and x.dtype == torch.float32
     b, h, w, c = x.shape
@@ -70,10 +71,12 @@ def partition_attention_(x: torch.Tensor, blk: dict, scratch_qkv: torch.Tensor, 
     _lib.check(L.rvt_partition_attention(
         _lib.ptr(x), b, h, w, c, ph, pw, blk['grid'], blk['dh'], _lib.ptr(blk['n1_w']), _lib.ptr(blk['n1_b']),
         blk['eps'], _lib.ptr(blk['wqkv']), _lib.ptr(blk['bqkv']), _lib.ptr(blk['wproj']), _lib.ptr(blk['bproj']),
-        _lib.ptr(blk['g1']), _lib.ptr(scratch_qkv), _lib.ptr(scratch_o), _stream(x)), 'partition_attention')
+        _lib.ptr(blk['g1']), _lib.ptr(scratch_qkv), _lib.ptr(scratch_o), _lib.ptr(scratch_xn), _stream(x)),
+        'partition_attention')
 
 
-def mlp_block_(x: torch.Tensor, blk: dict, scratch_hidden: torch.Tensor) -> None:
+def mlp_block_(x: torch.Tensor, blk: dict, scratch_hidden: torch.Tensor,
+               scratch_xn: Optional[torch.Tensor] = None) -> None:
     """In place: x += ls2(mlp(norm2(x)))  (maxvit.py:269)."""
     assert x.is_cuda and x.is_contiguous() and x.dtype == torch.float32
     c = x.shape[-1]
@@ -84,7 +87,7 @@ def mlp_block_(x: torch.Tensor, blk: dict, scratch_hidden: torch.Tensor) -> None
     _lib.check(L.rvt_mlp_block(
         _lib.ptr(x), n_tok, c, hid, _lib.ptr(blk['n2_w']), _lib.ptr(blk['n2_b']), blk['eps'], _lib.ptr(blk['w1']),
         _lib.ptr(blk['b1']), _lib.ptr(blk['w2']), _lib.ptr(blk['b2']), _lib.ptr(blk['g2']),
-        _lib.ptr(scratch_hidden), _stream(x)), 'mlp_block')
+        _lib.ptr(scratch_hidden), _lib.ptr(scratch_xn), _stream(x)), 'mlp_block')
 
 
 def dws_conv_lstm(x: torch.Tensor, h_prev: Optional[torch.Tensor], c_prev: Optional[torch.Tensor], pk: dict,

@@ -28,14 +28,14 @@ def pack_linear_weight(w: torch.Tensor, bn: int) -> torch.Tensor:
     return _swizzle_tiles(w.detach().float(), bn)
 
 
-def pack_conv_weight(w: torch.Tensor, channels_last_input: bool) -> torch.Tensor:
-    """Conv2d weight [Cout, Cin, KS, KS] -> one n-tile of Cout rows.
+def pack_conv_weight(w: torch.Tensor, channels_last_input: bool, bn: int = 0) -> torch.Tensor:
+    """Conv2d weight [Cout, Cin, KS, KS] -> n-tiles of bn rows (default: one tile of Cout rows).
     K order matches the im2col loader: (ci, ky, kx) for NCHW input, (ky, kx, ci) for NHWC."""
     assert w.dim() == 4
     co = w.shape[0]
     w2 = w.detach().float().permute(0, 2, 3, 1).reshape(co, -1) if channels_last_input \
         else w.detach().float().reshape(co, -1)
-    return _swizzle_tiles(w2, co)
+    return _swizzle_tiles(w2, bn or co)
 
 
 def lstm_row_order(dim: int, cw: int) -> torch.Tensor:

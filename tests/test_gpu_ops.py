@@ -74,12 +74,13 @@ def test_each_operator_with_oracle_inputs(name):
                 rows_s = ops.attention_scratch_rows(b, hh, ww, blk['part'])
                 sq = torch.empty(rows_s * 3 * c, dtype=torch.float16, device=dev)
                 so = torch.empty(rows_s * c, dtype=torch.float16, device=dev)
+                sxn = torch.empty(max(rows_s, ((b * hh * ww + 127) // 128) * 128) * c, dtype=torch.float16, device=dev)
                 xg = xin.to(dev).contiguous()
-                ops.partition_attention_(xg, blk, sq, so)
+                ops.partition_attention_(xg, blk, sq, so, sxn)
                 rec(step, tp + 'x_attn', xg, taps[tp + 'x_attn'])
                 xg = taps[tp + 'x_attn'].to(dev).contiguous()
                 sh = torch.empty(((b * hh * ww + 127) // 128) * 128 * blk['hidden'], dtype=torch.float16, device=dev)
-                ops.mlp_block_(xg, blk, sh)
+                ops.mlp_block_(xg, blk, sh, sxn)
                 rec(step, tp + 'x_mlp', xg, taps[tp + 'x_mlp'])
                 xin = taps[tp + 'x_mlp']
             hp = cp = None
