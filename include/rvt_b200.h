@@ -28,6 +28,10 @@ const char* rvt_error_string(int code);
 /* ---- tiling contract shared with the host-side weight packer (rvt_b200/packing.py) ---- */
 /* N-tile (columns per CTA) used for a Linear with n_total output and k input features. */
 int rvt_tile_n(int n_total, int k);
+/* 1 when rvt_partition_attention runs as one fused kernel (dim <= 128, dim_head <= 32): then
+ * wqkv_packed / bqkv must come from packing.pack_qkv_weight() (per-head [q|k|v] tiles, head dim
+ * zero-padded to 32), wproj_packed from pack_linear_weight(bn = dim), and no scratch is touched. */
+int rvt_attention_is_fused(int dim, int dim_head);
 /* N-tiles the MLP weights must be packed with (fc1 [hidden, dim], fc2 [dim, hidden]); returns 1 when
  * rvt_mlp_block runs as one fused kernel (dim <= 128), 0 for the two-GEMM path. */
 int rvt_mlp_tiles(int dim, int hidden, int* bn_fc1, int* bn_fc2);

@@ -14,6 +14,7 @@ SIGNATURES = {
     'rvt_abi_version': (_i, []),
     'rvt_error_string': (_c.c_char_p, [_i]),
     'rvt_tile_n': (_i, [_i, _i]),
+    'rvt_attention_is_fused': (_i, [_i, _i]),
     'rvt_mlp_tiles': (_i, [_i, _i, _vp, _vp]),
     'rvt_conv_tile_n': (_i, [_i]),
     'rvt_lstm_cw': (_i, [_i]),

@@ -272,12 +272,19 @@ class RNNDetector(nn.Module):
                     sa, mlp = att.self_attn, att.mlp
                     fc1, fc2 = mlp.net[0][0], mlp.net[2]
                     bn1, bn2, _ = _lib.mlp_tiles(c, fc1.weight.shape[0])
+                    if L.rvt_attention_is_fused(c, att.dim_head):
+                        wqkv, bqkv = packing.pack_qkv_weight(sa.qkv.weight.to(device),
+                                                             getattr(sa.qkv, 'bias', None), att.dim_head)
+                        bqkv = bqkv.to(device)
+                        wproj = packing.pack_linear_weight(sa.proj.weight.to(device), c)
+                    else:
+                        wqkv = packing.pack_linear_weight(sa.qkv.weight.to(device), L.rvt_tile_n(3 * c, c))
+                        bqkv = f32(getattr(sa.qkv, 'bias', None))
+                        wproj = packing.pack_linear_weight(sa.proj.weight.to(device), L.rvt_tile_n(c, c))
                     e['blocks'].append({
                         'grid': 0 if att.window else 1, 'part': att.partition_size, 'dh': att.dim_head, 'eps': att.eps,
                         'n1_w': f32(getattr(att.norm1, 'weight', None)), 'n1_b': f32(getattr(att.norm1, 'bias', None)),
-                        'wqkv': packing.pack_linear_weight(sa.qkv.weight.to(device), L.rvt_tile_n(3 * c, c)),
-                        'bqkv': f32(getattr(sa.qkv, 'bias', None)),
-                        'wproj': packing.pack_linear_weight(sa.proj.weight.to(device), L.rvt_tile_n(c, c)),
+                        'wqkv': wqkv, 'bqkv': bqkv, 'wproj': wproj,
                         'bproj': f32(getattr(sa.proj, 'bias', None)),
                         'g1': f32(getattr(att.ls1, 'gamma', None)),
                         'n2_w': f32(att.norm2.weight), 'n2_b': f32(att.norm2.bias),

@@ -7,6 +7,7 @@
 #include "attention_core.cuh"
 #include "gemm_fused.cuh"
 #include "mlp_fused.cuh"
+#include "attn_fused.cuh"
 #include "voxel.cuh"
 
 using namespace rvt;
@@ -86,6 +87,11 @@ int rvt_tile_n(int n_total, int k) {
   for (int bn = cap; bn >= 16; bn -= 16)
     if (n_total % bn == 0) return bn;
   return -1;
+}
+
+int rvt_attention_is_fused(int dim, int dim_head) {
+  // attn_fused.cuh: one launch per attention block; weights from packing.pack_qkv_weight()
+  return (dim <= 128 && dim % 16 == 0 && dim_head <= kAfDhp && dim_head % 8 == 0 && dim % dim_head == 0) ? 1 : 0;
 }
 
 int rvt_mlp_tiles(int dim, int hidden, int* bn_fc1, int* bn_fc2) {
@@ -190,7 +196,8 @@ int rvt_partition_attention(float* x, int batch, int height, int width, int dim,
                             int dim_head, const float* n1_w, const float* n1_b, float eps, const void* wqkv_packed,
                             const float* bqkv, const void* wproj_packed, const float* bproj, const float* gamma1,
                             void* scratch_qkv, void* scratch_o, void* scratch_xn, void* stream) {
-  if (!x || !wqkv_packed || !wproj_packed || !scratch_qkv || !scratch_o) return kErrBadArg;
+  if (!x || !wqkv_packed || !wproj_packed) return kErrBadArg;
+  if (!rvt_attention_is_fused(dim, dim_head) && (!scratch_qkv || !scratch_o)) return kErrBadArg;
   if (dim % 8 != 0 || dim > 512 || dim_head % 8 != 0 || dim_head > 64 || dim % dim_head != 0) return kErrUnsupported;
   const int64_t rows = rvt_attention_scratch_rows(batch, height, width, ph, pw);
   if (rows < 0) return kErrUnsupported;
@@ -201,6 +208,27 @@ int rvt_partition_attention(float* x, int batch, int height, int width, int dim,
   m.H = height; m.W = width; m.ph = ph; m.pw = pw; m.ny = height / ph; m.nx = width / pw; m.P = P;
   m.rows_per_win = rpg; m.n_groups = batch * m.ny * m.nx; m.n_tokens = batch * height * width;
   const int n_mtiles = static_cast<int>(rows / 128);
+
+  if (rvt_attention_is_fused(dim, dim_head)) {
+    AttnFusedArgs fa{};
+    fa.x = x; fa.map = m; fa.C = dim; fa.dh = dim_head; fa.nh = dim / dim_head;
+    fa.ln_w = n1_w; fa.ln_b = n1_b; fa.eps = eps; fa.do_ln = n1_w != nullptr;
+    fa.wqkv = static_cast<const __half*>(wqkv_packed); fa.bqkv = bqkv;
+    fa.wproj = static_cast<const __half*>(wproj_packed); fa.bproj = bproj; fa.gamma = gamma1;
+    fa.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(dim_head));
+    if (!bqkv) return kErrBadArg;   // padded bias vector is mandatory on the fused path (zeros if the layer has none)
+    const size_t smem = attn_fused_smem_bytes(dim);
+    if (smem > static_cast<size_t>(kMaxSmem)) return kErrUnsupported;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      attr_set = true;
+    }
+    attn_fused_kernel<<<n_mtiles, kAfThreads, smem, st>>>(fa);
+    return static_cast<int>(cudaGetLastError());
+  }
 
   // 1) qkv = Linear(norm1(x)) on partition-ordered rows  (maxvit.py:234,254-257,347)
   {

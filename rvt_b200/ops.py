@@ -66,7 +66,8 @@ def partition_attention_(x: torch.Tensor, blk: dict, scratch_qkv: torch.Tensor, 
     b, h, w, c = x.shape
     ph, pw = blk['part']
     rows = attention_scratch_rows(b, h, w, (ph, pw))
-    assert scratch_qkv.numel() >= rows * 3 * c and scratch_o.numel() >= rows * c
+    if not _lib.lib().rvt_attention_is_fused(c, blk['dh']):
+        assert scratch_qkv.numel() >= rows * 3 * c and scratch_o.numel() >= rows * c
     L = _lib.lib()
     _lib.check(L.rvt_partition_attention(
         _lib.ptr(x), b, h, w, c, ph, pw, blk['grid'], blk['dh'], _lib.ptr(blk['n1_w']), _lib.ptr(blk['n1_b']),

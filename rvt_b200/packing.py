@@ -80,3 +80,20 @@ def pack_stem_weight_s2d(w: torch.Tensor, factor: int) -> torch.Tensor:
     else:
         raise ValueError('unsupported stem geometry')
     return _swizzle_tiles(w2.reshape(co, -1), co)
+
+
+def pack_qkv_weight(w: torch.Tensor, b, dim_head: int, dhp: int = 32):
+    """qkv Linear weight [3C, C] (+ bias [3C] or None) for the fused attention kernel
+    (csrc/attn_fused.cuh): one N-tile of 3*dhp rows per head, [q_h | k_h | v_h] each zero-padded
+    from dim_head to dhp rows (the reference's per-head interleaved layout, maxvit.py:347).
+    Returns (tile images [nh][KC][3*dhp x 64], padded bias [nh * 3*dhp] fp32)."""
+    c3, c = w.shape
+    nh = c // dim_head
+    assert c3 == 3 * c and dim_head <= dhp
+    wf = w.detach().float().view(nh, 3, dim_head, c)
+    wpad = torch.zeros(nh, 3, dhp, c, device=w.device)
+    wpad[:, :, :dim_head] = wf
+    bpad = torch.zeros(nh, 3, dhp, device=w.device)
+    if b is not None:
+        bpad[:, :, :dim_head] = b.detach().float().view(nh, 3, dim_head)
+    return _swizzle_tiles(wpad.reshape(nh * 3 * dhp, c), 3 * dhp), bpad.reshape(-1).contiguous()
