@@ -2,7 +2,9 @@
 // no synchronisation, no torch types.
 #include "../../include/rvt_b200.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
+#include <string.h>
 
 #include "attention_core.cuh"
 #include "gemm_fused.cuh"
@@ -20,8 +22,40 @@ constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
 
 inline int cdiv(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
 
+// ---- TMA tensor maps (driver entry point resolved at run time: no link-time libcuda dependency) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// fp16 row-major [rows, cols] (leading dimension ld elements) -> box of 64 columns x 128 rows, SWIZZLE_128B
+bool make_tmap_f16_rows(const void* base, int64_t rows, int64_t cols, int64_t ld, CUtensorMap* out) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn || (reinterpret_cast<uintptr_t>(base) & 15) || (ld % 8) != 0) return false;
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  const cuuint32_t box[2] = {64, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int LOADER, int EPI>
-int launch_gemm(GemmArgs a, int n_mtiles, int n_ntiles, cudaStream_t st) {
+int launch_gemm(GemmArgs a, int n_mtiles, int n_ntiles, cudaStream_t st, const CUtensorMap* tmap = nullptr) {
   a.KC = cdiv(a.K, 64);
   a.tmem_cols = static_cast<int>(tmem_cols_pow2(static_cast<uint32_t>(a.BN)));
   a.ab_fmt = 0;  // fp16 operands
@@ -40,8 +74,19 @@ int launch_gemm(GemmArgs a, int n_mtiles, int n_ntiles, cudaStream_t st) {
     attr_set = true;
   }
   if (n_mtiles <= 0 || n_ntiles <= 0) return 0;
-  gemm_fused_kernel<LOADER, EPI><<<dim3(n_mtiles, n_ntiles), kGemmThreads, smem, st>>>(a);
+  alignas(64) CUtensorMap tm;
+  if (tmap) tm = *tmap; else memset(&tm, 0, sizeof(tm));
+  gemm_fused_kernel<LOADER, EPI><<<dim3(n_mtiles, n_ntiles), kGemmThreads, smem, st>>>(a, tm);
   return static_cast<int>(cudaGetLastError());
+}
+
+// A = fp16 row-major scratch [a_rows, K]: TMA-fed mainloop when a tensor map can be built, else the
+// register-copy loader (same results).
+template <int EPI>
+int launch_gemm_f16(GemmArgs a, int n_mtiles, int n_ntiles, cudaStream_t st) {
+  alignas(64) CUtensorMap tm;
+  if (make_tmap_f16_rows(a.a16, a.a_rows, a.K, a.lda, &tm)) return launch_gemm<LD_TMA, EPI>(a, n_mtiles, n_ntiles, st, &tm);
+  return launch_gemm<LD_F16, EPI>(a, n_mtiles, n_ntiles, st);
 }
 
 // Stages at least this wide normalise / cast their GEMM A operands once (ln_rows_kernel) instead
@@ -82,8 +127,8 @@ const char* rvt_error_string(int code) {
 int rvt_tile_n(int n_total, int k) {
   // Narrow stages (dim <= 128) have many 128-row tiles: one wide N-tile per CTA.  Wide stages
   // (dim >= 256) have few row tiles: cut N finer so the grid still covers the 148 SMs.
-  const int dim = n_total < k ? n_total : k;
-  const int cap = dim <= 128 ? 128 : (n_total >= 1024 ? 128 : 64);   // <=128 TMEM columns -> 4 CTAs / SM
+  (void)k;
+  const int cap = 128;   // <=128 TMEM columns -> up to 4 CTAs / SM
   for (int bn = cap; bn >= 16; bn -= 16)
     if (n_total % bn == 0) return bn;
   return -1;
@@ -165,7 +210,8 @@ int rvt_downsample_cf2cl(const void* in, int in_dtype, int in_nchw, int batch, i
     const bool patch = ksize == stride && pad == 0;
     if (!in_nchw || !(overlap || patch) || 64 % stride != 0 || (stride * cin) % 8 != 0) return kErrUnsupported;
     const int wg = wout;
-    const size_t smem = static_cast<size_t>(cin) * (kS2dStrip + 2) * sizeof(__half);
+    const size_t smem = static_cast<size_t>(cin) * (kS2dStrip + 2) * sizeof(__half) + static_cast<size_t>(stride) * cin * 2;
+    if (stride * cin > 256) return kErrUnsupported;
     if (smem > 48 * 1024) return kErrUnsupported;
     stem_s2d_kernel<<<dim3((wg * stride + kS2dStrip - 1) / kS2dStrip, hin, batch), 256, smem, st>>>(in, in_dtype, cin, hin, win, wg, stride,
                                                                            static_cast<__half*>(s2d_scratch));
@@ -242,7 +288,7 @@ int rvt_partition_attention(float* x, int batch, int height, int width, int dim,
       rc = launch_ln_rows<true>(x, m, rows, dim, n1_w != nullptr, n1_w, n1_b, eps, scratch_xn, nullptr, nullptr, st);
       if (rc) return rc;
       a.a16 = static_cast<const __half*>(scratch_xn); a.lda = dim; a.a_rows = static_cast<int>(rows);
-      rc = launch_gemm<LD_F16, EP_F16>(a, n_mtiles, 3 * dim / a.BN, st);
+      rc = launch_gemm_f16<EP_F16>(a, n_mtiles, 3 * dim / a.BN, st);
     } else {
       a.x = x; a.C = dim; a.ln_w = n1_w; a.ln_b = n1_b; a.eps = eps; a.do_ln = n1_w != nullptr;
       rc = launch_gemm<LD_LN, EP_F16>(a, n_mtiles, 3 * dim / a.BN, st);
@@ -275,7 +321,7 @@ int rvt_partition_attention(float* x, int batch, int height, int width, int dim,
     a.Wp = static_cast<const __half*>(wproj_packed); a.bias = bproj; a.map = m;
     a.a16 = static_cast<const __half*>(scratch_o); a.lda = dim; a.a_rows = static_cast<int>(rows);
     a.C = dim; a.res = x; a.xout = x; a.gamma = gamma1;
-    return launch_gemm<LD_F16, EP_RES>(a, n_mtiles, dim / a.BN, st);
+    return launch_gemm_f16<EP_RES>(a, n_mtiles, dim / a.BN, st);
   }
 }
 
@@ -322,7 +368,7 @@ int rvt_mlp_block(float* x, int64_t n_tokens, int dim, int hidden, const float* 
       rc = launch_ln_rows<true>(x, m, static_cast<int64_t>(n_mtiles) * 128, dim, 1, n2_w, n2_b, eps, scratch_xn, nullptr, nullptr, st);
       if (rc) return rc;
       a.a16 = static_cast<const __half*>(scratch_xn); a.lda = dim; a.a_rows = n_mtiles * 128;
-      rc = launch_gemm<LD_F16, EP_F16>(a, n_mtiles, hidden / a.BN, st);
+      rc = launch_gemm_f16<EP_F16>(a, n_mtiles, hidden / a.BN, st);
     } else {
       a.x = x; a.C = dim; a.ln_w = n2_w; a.ln_b = n2_b; a.eps = eps; a.do_ln = 1;
       rc = launch_gemm<LD_LN, EP_F16>(a, n_mtiles, hidden / a.BN, st);
@@ -335,7 +381,7 @@ int rvt_mlp_block(float* x, int64_t n_tokens, int dim, int hidden, const float* 
     a.Wp = static_cast<const __half*>(w2_packed); a.bias = b2; a.map = m;
     a.a16 = static_cast<const __half*>(scratch_hidden); a.lda = hidden; a.a_rows = n_mtiles * 128;
     a.C = dim; a.res = x; a.xout = x; a.gamma = gamma2;
-    return launch_gemm<LD_F16, EP_RES>(a, n_mtiles, dim / a.BN, st);
+    return launch_gemm_f16<EP_RES>(a, n_mtiles, dim / a.BN, st);
   }
 }
 
@@ -366,7 +412,7 @@ int rvt_linear_f16(const void* av, int64_t m, int k, int n, const void* w_packed
   a.Wp = static_cast<const __half*>(w_packed); a.bias = bias;
   a.a16 = static_cast<const __half*>(av); a.lda = k; a.a_rows = static_cast<int>(m);
   a.o16 = static_cast<__half*>(out); a.ldo = n; a.act = act;
-  return launch_gemm<LD_F16, EP_F16>(a, cdiv(m, 128), n / a.BN, static_cast<cudaStream_t>(stream));
+  return launch_gemm_f16<EP_F16>(a, cdiv(m, 128), n / a.BN, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

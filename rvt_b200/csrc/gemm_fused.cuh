@@ -4,7 +4,9 @@
 //
 //   D[128 x BN] (fp32, TMEM) = A[128 x K] (fp16, built in smem by the loader) * W[BN x K]^T
 //
-//   loader LD_F16   : A rows are fp16 rows of a scratch matrix
+//   loader LD_F16   : A rows are fp16 rows of a scratch matrix (register copy)
+//          LD_TMA   : same operand, but whole [128 x 64] tiles are fetched by the TMA engine through
+//                     a tensor map (one elected thread, `stages` tiles in flight, no register cost)
 //          LD_LN    : A = LayerNorm(x[token(row)]) (or x itself), tokens gathered through the
 //                     window / grid partition map  (maxvit.py:234,241,252-265,273-304)
 //          LD_CONV  : A = im2col of the strided downsample conv input (maxvit.py:166-175)
@@ -24,7 +26,7 @@
 
 namespace rvt {
 
-enum { LD_F16 = 0, LD_LN = 1, LD_CONV = 2, LD_XH = 3 };
+enum { LD_F16 = 0, LD_LN = 1, LD_CONV = 2, LD_XH = 3, LD_TMA = 4 };
 enum { EP_F16 = 0, EP_RES = 1, EP_LN = 2, EP_LSTM = 3, EP_RAW = 4 };
 enum { MAP_IDENTITY = 0, MAP_WINDOW = 1, MAP_GRID = 2 };
 
@@ -84,7 +86,7 @@ constexpr int kMaxStages = 6;
 constexpr uint32_t kATileBytes = 128 * 128;   // 128 rows x 64 fp16
 
 constexpr int kWorkers = 256;                 // 8 producer / epilogue warps
-constexpr int kGemmThreads = kWorkers + 32;   // + the MMA-issuing warp
+constexpr int kGemmThreads = kWorkers + 64;   // + the MMA-issuing warp + the TMA producer warp (LD_TMA)
 
 __host__ __device__ inline size_t gemm_smem_bytes(int stages, int BN) {
   return 1024 /*align slack*/ + static_cast<size_t>(stages) * (kATileBytes + static_cast<size_t>(BN) * 128) +
@@ -171,7 +173,8 @@ __device__ __forceinline__ float red8(float s) {   // sum over the 8 lanes that 
 }
 
 template <int LOADER, int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 3) gemm_fused_kernel(const __grid_constant__ GemmArgs a) {
+__global__ void __launch_bounds__(kGemmThreads, 2) gemm_fused_kernel(const __grid_constant__ GemmArgs a,
+                                                                     const __grid_constant__ CUtensorMap tmap_a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(kGemmThreads, 3) gemm_fused_kernel(const __gri
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
 
   if (tid == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], kWorkers); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], LOADER == LD_TMA ? 1 : kWorkers); mbar_init(&empty[s], 1); }
     mbar_init(accum, 1);
     fence_mbar_init();
   }
@@ -203,6 +206,7 @@ __global__ void __launch_bounds__(kGemmThreads, 3) gemm_fused_kernel(const __gri
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 8) {
+   if (LOADER != LD_TMA) {
     // =========================== A-tile producers ===========================
     const int j = tid & 7;          // 16-byte chunk (8 fp16) inside the 64-wide K chunk
     const int r0 = tid >> 3;        // rows r0 + 32*i, i = 0..3
@@ -273,47 +277,29 @@ __global__ void __launch_bounds__(kGemmThreads, 3) gemm_fused_kernel(const __gri
       }
     }
 
-    for (int kc = 0; kc < KC; ++kc) {
-      const int s = kc % stages;
-      const uint32_t ph = (kc / stages) & 1;
-      mbar_wait(&empty[s], ph ^ 1);
-      if (tid == 0) {
-        mbar_expect_tx(&full[s], b_bytes);
-        bulk_g2s(sB + static_cast<size_t>(s) * b_bytes,
-                 a.Wp + (static_cast<size_t>(nt) * KC + kc) * static_cast<size_t>(BN) * 64, b_bytes, &full[s]);
-      }
-      const uint32_t tile = sA_addr + s * kATileBytes;
+    // Register double-buffering: the global loads of chunk kc+1 are issued before chunk kc is
+    // converted and stored to shared memory, so a producer thread always has one chunk in flight
+    // (the loaders were long_scoreboard-bound without it, profiles/ncu_r01.md).
+    // raw[i][0..7]: eight fp32 of row i, or (packed) eight fp16 in raw[i][0..3].
+    auto fetch = [&](int kc, uint32_t (&raw)[4][8]) {
       const int k0 = kc * 64 + j * 8;
-
       if (LOADER == LD_F16) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint4 v = make_uint4(0, 0, 0, 0);
           if (tok[i] >= 0 && k0 < a.K)
             v = __ldg(reinterpret_cast<const uint4*>(a.a16 + static_cast<size_t>(tok[i]) * a.lda + k0));
-          st_smem_16B(tile + sw128_offset(r0 + 32 * i, j), v.x, v.y, v.z, v.w);
+          raw[i][0] = v.x; raw[i][1] = v.y; raw[i][2] = v.z; raw[i][3] = v.w;
         }
       } else if (LOADER == LD_LN) {
-        const bool kv = k0 < a.C;
-        float g[8], bb[8];
-        if (a.do_ln && kv) { load8(a.ln_w + k0, g); load8(a.ln_b + k0, bb); }
+        if (!(a.do_ln && KC == 1)) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (tok[i] >= 0 && kv) {
-            if (a.do_ln && KC == 1) {
+          for (int i = 0; i < 4; ++i) {
+            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (tok[i] >= 0 && k0 < a.C) load8(a.x + static_cast<size_t>(tok[i]) * a.C + k0, v);
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = keep[i][e];
-            } else {
-              load8(a.x + static_cast<size_t>(tok[i]) * a.C + k0, v);
-            }
-            if (a.do_ln) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = (v[e] - mean[i]) * rstd[i] * g[e] + bb[e];
-            }
+            for (int e = 0; e < 8; ++e) raw[i][e] = __float_as_uint(v[e]);
           }
-          st_smem_16B(tile + sw128_offset(r0 + 32 * i, j), pack_h2(v[0], v[1]), pack_h2(v[2], v[3]),
-                      pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
         }
       } else if (LOADER == LD_XH) {
         const int C = a.C;
@@ -334,8 +320,8 @@ __global__ void __launch_bounds__(kGemmThreads, 3) gemm_fused_kernel(const __gri
               load8(src + static_cast<size_t>(tok[i]) * C + ch, v);
             }
           }
-          st_smem_16B(tile + sw128_offset(r0 + 32 * i, j), pack_h2(v[0], v[1]), pack_h2(v[2], v[3]),
-                      pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+#pragma unroll
+          for (int e = 0; e < 8; ++e) raw[i][e] = __float_as_uint(v[e]);
         }
       } else {  // LD_CONV
         const int KSy = a.KSy, KSx = a.KSx, Cin = a.Cin, Hin = a.Hin, Win = a.Win;
@@ -367,7 +353,7 @@ __global__ void __launch_bounds__(kGemmThreads, 3) gemm_fused_kernel(const __gri
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const uint32_t* u = reinterpret_cast<const uint32_t*>(&hv[i][0]);
-            st_smem_16B(tile + sw128_offset(r0 + 32 * i, j), u[0], u[1], u[2], u[3]);
+            raw[i][0] = u[0]; raw[i][1] = u[1]; raw[i][2] = u[2]; raw[i][3] = u[3];
           }
         } else {
           // channels-last input (f32 or f16), k = (ky*KSx + kx)*Cin + ci, Cin % 8 == 0
@@ -377,24 +363,75 @@ __global__ void __launch_bounds__(kGemmThreads, 3) gemm_fused_kernel(const __gri
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int iy = ciy[i] + ky, ix = cix[i] + kx;
-            uint4 o = make_uint4(0, 0, 0, 0);
-            if (kv && tok[i] >= 0 && iy >= 0 && iy < Hin && ix >= 0 && ix < Win) {
-              const size_t off = (static_cast<size_t>(cb[i] * Hin + iy) * Win + ix) * Cin + ci;
-              if (a.in_dtype == 2) {
-                o = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.cin) + off));
-              } else {
-                float v[8];
-                load8(reinterpret_cast<const float*>(a.cin) + off, v);
-                o = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-              }
+            const bool ok = kv && tok[i] >= 0 && iy >= 0 && iy < Hin && ix >= 0 && ix < Win;
+            const size_t off = ok ? (static_cast<size_t>(cb[i] * Hin + iy) * Win + ix) * Cin + ci : 0;
+            if (a.in_dtype == 2) {
+              uint4 o = make_uint4(0, 0, 0, 0);
+              if (ok) o = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.cin) + off));
+              raw[i][0] = o.x; raw[i][1] = o.y; raw[i][2] = o.z; raw[i][3] = o.w;
+            } else {
+              float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+              if (ok) load8(reinterpret_cast<const float*>(a.cin) + off, v);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) raw[i][e] = __float_as_uint(v[e]);
             }
-            st_smem_16B(tile + sw128_offset(r0 + 32 * i, j), o.x, o.y, o.z, o.w);
           }
         }
       }
+    };
+    auto commit = [&](int kc, const uint32_t (&raw)[4][8], uint32_t tile) {
+      const int k0 = kc * 64 + j * 8;
+      const bool packed = LOADER == LD_F16 || (LOADER == LD_CONV && (a.in_nchw || a.in_dtype == 2));
+      float g[8], bb[8];
+      const bool ln_here = LOADER == LD_LN && a.do_ln && k0 < a.C;
+      if (ln_here) { load8(a.ln_w + k0, g); load8(a.ln_b + k0, bb); }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t o0, o1, o2, o3;
+        if (packed) {
+          o0 = raw[i][0]; o1 = raw[i][1]; o2 = raw[i][2]; o3 = raw[i][3];
+        } else {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(raw[i][e]);
+          if (LOADER == LD_LN && a.do_ln) {
+            if (KC == 1) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = keep[i][e];
+            }
+            if (tok[i] >= 0 && ln_here) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = (v[e] - mean[i]) * rstd[i] * g[e] + bb[e];
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = 0.f;
+            }
+          }
+          o0 = pack_h2(v[0], v[1]); o1 = pack_h2(v[2], v[3]); o2 = pack_h2(v[4], v[5]); o3 = pack_h2(v[6], v[7]);
+        }
+        st_smem_16B(tile + sw128_offset(r0 + 32 * i, j), o0, o1, o2, o3);
+      }
+    };
+
+    uint32_t raw_a[4][8], raw_b[4][8];
+    fetch(0, raw_a);
+    for (int kc = 0; kc < KC; ++kc) {
+      const int s = kc % stages;
+      const uint32_t ph = (kc / stages) & 1;
+      const bool even = (kc & 1) == 0;
+      if (kc + 1 < KC) { if (even) fetch(kc + 1, raw_b); else fetch(kc + 1, raw_a); }
+      mbar_wait(&empty[s], ph ^ 1);
+      if (tid == 0) {
+        mbar_expect_tx(&full[s], b_bytes);
+        bulk_g2s(sB + static_cast<size_t>(s) * b_bytes,
+                 a.Wp + (static_cast<size_t>(nt) * KC + kc) * static_cast<size_t>(BN) * 64, b_bytes, &full[s]);
+      }
+      const uint32_t tile = sA_addr + s * kATileBytes;
+      if (even) commit(kc, raw_a, tile); else commit(kc, raw_b, tile);
       fence_proxy_async_smem();
       mbar_arrive(&full[s]);
     }
+   }  // LOADER != LD_TMA
 
     // =========================== epilogue ===========================
     mbar_wait(accum, 0);
@@ -563,6 +600,20 @@ __global__ void __launch_bounds__(kGemmThreads, 3) gemm_fused_kernel(const __gri
         }
       }
     }
+  } else if (warp == 9) {
+    // =========================== TMA producer (LD_TMA only) ===========================
+    if (LOADER == LD_TMA && lane == 0) {
+      tma_prefetch_desc(&tmap_a);
+      for (int kc = 0; kc < KC; ++kc) {
+        const int s = kc % stages;
+        mbar_wait(&empty[s], ((kc / stages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full[s], kATileBytes + b_bytes);
+        tma_load_2d(sA_addr + s * kATileBytes, &tmap_a, kc * 64, mt * 128, &full[s]);
+        bulk_g2s(sB + static_cast<size_t>(s) * b_bytes,
+                 a.Wp + (static_cast<size_t>(nt) * KC + kc) * static_cast<size_t>(BN) * 64, b_bytes, &full[s]);
+      }
+    }
+    __syncwarp();
   } else {
     // =========================== MMA issuer (warp 8, one lane) ===========================
     if (lane == 0) {
@@ -688,35 +739,44 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* x, RowMap map
 constexpr int kS2dStrip = 256;   // pixels per CTA strip
 __global__ void __launch_bounds__(256) stem_s2d_kernel(const void* __restrict__ in, int in_dtype, int Cin, int H, int W,
                                                        int Wg, int f, __half* __restrict__ out) {
-  extern __shared__ __half s_tile[];            // [Cin][kS2dStrip + 2]
+  extern __shared__ __half s_tile[];            // [Cin][kS2dStrip + 2], then lut[f*Cin] (u16)
   const int strip = blockIdx.x, y = blockIdx.y, b = blockIdx.z;
   const int x0 = strip * kS2dStrip;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int pitch = kS2dStrip + 2;
-  for (int ci = 0; ci < Cin; ++ci) {             // one coalesced 256-pixel row segment per channel
+  const int cg = f * Cin;                        // channels per group (even)
+  unsigned short* lut = reinterpret_cast<unsigned short*>(s_tile + Cin * pitch);
+  if (tid < cg) {                                // output channel c -> tile offset (ci*pitch + sub), once per CTA
+    const int sub = tid / Cin, ci = tid - sub * Cin;
+    lut[tid] = static_cast<unsigned short>(ci * pitch + sub);
+  }
+  {
     const int x = x0 + tid;
-    float v = 0.f;
-    if (x < W) {
-      const size_t off = ((static_cast<size_t>(b) * Cin + ci) * H + y) * W + x;
-      if (in_dtype == 1) v = static_cast<float>(__ldg(reinterpret_cast<const uint8_t*>(in) + off));
-      else if (in_dtype == 2) v = __half2float(__ldg(reinterpret_cast<const __half*>(in) + off));
-      else v = __ldg(reinterpret_cast<const float*>(in) + off);
+    const bool ok = x < W;
+    const size_t row0 = (static_cast<size_t>(b) * Cin * H + y) * W + x;
+    const size_t cstride = static_cast<size_t>(H) * W;
+#pragma unroll 4
+    for (int ci = 0; ci < Cin; ++ci) {           // one coalesced 256-pixel row segment per channel
+      float v = 0.f;
+      if (ok) {
+        const size_t off = row0 + ci * cstride;
+        if (in_dtype == 1) v = static_cast<float>(__ldg(reinterpret_cast<const uint8_t*>(in) + off));
+        else if (in_dtype == 2) v = __half2float(__ldg(reinterpret_cast<const __half*>(in) + off));
+        else v = __ldg(reinterpret_cast<const float*>(in) + off);
+      }
+      s_tile[ci * pitch + tid] = __float2half_rn(v);
     }
-    s_tile[ci * pitch + tid] = __float2half_rn(v);
   }
   __syncthreads();
-  const int gpc = kS2dStrip / f;                 // groups per strip (f divides 64)
-  const int cg = f * Cin;                        // channels per group (even: 16-byte aligned groups)
+  const int gpc = kS2dStrip / f;                 // groups per strip
   const int g0 = strip * gpc;
   const int ngrp = min(gpc, Wg - g0);
+  const int pairs = cg >> 1;
   __half2* out2 = reinterpret_cast<__half2*>(out + ((static_cast<size_t>(b) * H + y) * Wg + g0) * cg);
-  for (int idx = tid; idx < ngrp * (cg >> 1); idx += 256) {
-    const int e = idx * 2;
-    const int gl = e / cg, c = e - gl * cg;
-    const int c1 = c + 1;
-    const int sub0 = c / Cin, ci0 = c - sub0 * Cin;
-    const int sub1 = c1 / Cin, ci1 = c1 - sub1 * Cin;
-    out2[idx] = __halves2half2(s_tile[ci0 * pitch + gl * f + sub0], s_tile[ci1 * pitch + gl * f + sub1]);
+  for (int gl = warp; gl < ngrp; gl += 8) {      // a warp writes one group's cg halves contiguously
+    const int goff = gl * f;
+    for (int p2 = lane; p2 < pairs; p2 += 32)
+      out2[gl * pairs + p2] = __halves2half2(s_tile[lut[2 * p2] + goff], s_tile[lut[2 * p2 + 1] + goff]);
   }
 }
 

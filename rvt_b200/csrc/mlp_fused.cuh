@@ -40,10 +40,6 @@ __host__ __device__ inline size_t mlp_smem_bytes(int C, int stages) {
   return 1024 + static_cast<size_t>(mlp_kc1(C)) * kATileBytes + stages * mlp_stage_bytes(C) + 2 * kATileBytes + 256;
 }
 
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-
 __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fused_kernel(const __grid_constant__ MlpArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);

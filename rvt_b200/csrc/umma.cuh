@@ -3,6 +3,7 @@
 // Raw PTX only — no CUTLASS.  Bit layouts follow the PTX ISA "tcgen05 matrix descriptor" and
 // "instruction descriptor" tables.
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -63,6 +64,23 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
           smem_u32(smem_dst)),
       "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
+}
+
+// 2-D tiled TMA load (tensor map built on the host with cuTensorMapEncodeTiled, SWIZZLE_128B,
+// box = 64 x 128 fp16): lands a [128 rows x 64 k] operand tile in exactly the SW128 K-major
+// layout the UMMA descriptor expects; out-of-bounds rows / columns are zero filled.
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
 // ----------------------------------------------------------------------------------------
