@@ -27,7 +27,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = 'RVT-B 1Mpx seq_len=21 backbone frames/sec'
 B_PER_GPU, SEQ_LEN, IN_C, IN_H, IN_W, PAD_H, PAD_W = 8, 21, 20, 360, 640, 384, 640
-LAUNCHES_PER_TIMESTEP = 4 * (1 + 2 * (3 + 2) + 1)     # per stage: conv+LN, 2 x (qkv, core, proj, fc1, fc2), lstm
+# per timestep: S1 s2d+conv, 4 fused attn/mlp, lstm; S2 conv, 4 fused, lstm; S3/S4 conv+ln, 2 x (ln,qkv,core,proj,ln,fc1,fc2), lstm
+LAUNCHES_PER_TIMESTEP = (2 + 4 + 1) + (1 + 4 + 1) + 2 * (2 + 2 * 7 + 1)
 GFLOP_PER_FRAME = 20.62                                 # BASELINE.md §3 (algorithmic, MAC = 2 FLOP)
 
 
@@ -133,6 +134,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-wavefront', action='store_true', help='run the four stages strictly one after the other')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', 0))
@@ -164,38 +166,38 @@ def main():
                 (torch.rand((SEQ_LEN, B_PER_GPU, IN_C, IN_H, IN_W), generator=g) < 0.1)).pin_memory()
     seq_dev = seq_host.to(dev)
 
+    wavefront = not args.no_wavefront
+
     def run_sequence_resident():
-        st = None
-        for tstep in range(SEQ_LEN):
-            _, st = model(seq_dev[tstep], st)
+        _, st = model.forward_sequence(seq_dev, None, wavefront=wavefront)
         return st
 
-    stage_buf = [torch.empty((B_PER_GPU, IN_C, IN_H, IN_W), dtype=torch.uint8, device=dev) for _ in range(2)]
     feat_host = torch.empty((B_PER_GPU, 512, PAD_H // 32, PAD_W // 32), dtype=torch.float32).pin_memory()
     copy_stream = torch.cuda.Stream(dev)
 
+    seq_stage = torch.empty_like(seq_dev)        # device landing buffers of the per-timestep H2D copies
+    d2h_stream = torch.cuda.Stream(dev)
+
     def run_sequence_e2e():
-        """Public API with host buffers: H2D of each timestep's uint8 tensor (double-buffered on a
-        copy stream), forward, D2H of the stage-4 feature map every timestep."""
-        st = None
+        """Public API with HOST buffers: every timestep's uint8 event tensor is copied H2D from pinned
+        memory (copy stream, overlapping compute), the sequence runs through
+        RNNDetector.forward_sequence, and every timestep's stage-4 feature map is read back D2H."""
         main_s = torch.cuda.current_stream(dev)
-        ev_ready = [torch.cuda.Event() for _ in range(2)]
-        ev_free = [torch.cuda.Event() for _ in range(2)]
+        copy_stream.wait_stream(main_s)
+        ready = []
         with torch.cuda.stream(copy_stream):
-            stage_buf[0].copy_(seq_host[0], non_blocking=True)
-            ev_ready[0].record(copy_stream)
-        for tstep in range(SEQ_LEN):
-            cur, nxt = tstep & 1, (tstep + 1) & 1
-            if tstep + 1 < SEQ_LEN:
-                with torch.cuda.stream(copy_stream):
-                    if tstep >= 1:
-                        copy_stream.wait_event(ev_free[nxt])
-                    stage_buf[nxt].copy_(seq_host[tstep + 1], non_blocking=True)
-                    ev_ready[nxt].record(copy_stream)
-            main_s.wait_event(ev_ready[cur])
-            out, st = model(stage_buf[cur], st)
-            ev_free[cur].record(main_s)
-            feat_host.copy_(out[4], non_blocking=True)
+            for tstep in range(SEQ_LEN):
+                seq_stage[tstep].copy_(seq_host[tstep], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                ready.append(ev)
+        outs, st = model.forward_sequence(seq_stage, None, wavefront=wavefront, input_ready=ready)
+        with torch.cuda.stream(d2h_stream):
+            for tstep in range(SEQ_LEN):
+                d2h_stream.wait_event(model.last_step_events[tstep])
+                feat_host.copy_(outs[tstep][4], non_blocking=True)
+        main_s.wait_stream(d2h_stream)
+        main_s.wait_stream(copy_stream)
         return st
 
     def barrier():
@@ -250,7 +252,8 @@ def main():
             'config': {'workload': 'RVT-Base 1Mpx 8x20x360x640 uint8 (model res 384x640) seq_len=21 bs=8/GPU '
                                    'inference, states carried', 'frames_per_step': B_PER_GPU * SEQ_LEN,
                        'l2_policy': 'inputs larger than L2 (774 MB of uint8 sequences per GPU)',
-                       'parallelism': f'batch-sharded x{world}, no collective'},
+                       'parallelism': f'batch-sharded x{world}, no collective',
+                       'schedule': 'wavefront over 4 streams' if wavefront else 'sequential'},
             'e2e': {'value': e2e, 'unit': 'frames/s',
                     'h2d_bytes_per_step': SEQ_LEN * B_PER_GPU * IN_C * IN_H * IN_W,
                     'd2h_bytes_per_step': SEQ_LEN * feat_host.numel() * 4},

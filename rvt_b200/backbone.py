@@ -337,59 +337,142 @@ class RNNDetector(nn.Module):
             prev_states = [None] * self.num_stages
         assert len(prev_states) == self.num_stages
         assert x.dim() == 4
-        dev = x.device
-        packed = self._ensure_packed(dev)
-        if x.dtype not in (torch.uint8, torch.float16, torch.float32):
-            x = x.to(torch.float32)
-        x = x.contiguous()
-        b = x.shape[0]
-        assert x.shape[1] == self.stages[0].dim_in
+        packed = self._ensure_packed(x.device)
+        x = self._prep_input(x)
         states: LstmStates = []
         output: Dict[int, torch.Tensor] = {}
-        taps = self.debug_taps
         cur, cur_nchw = x, True
-        for s, (st, pk) in enumerate(zip(self.stages, packed)):
-            d = st.downsample_cf2cl
-            c = st.dim
-            conv_w, s2d = pk['conv_w'], None
-            if s == 0 and pk['conv_w_s2d'] is not None:
-                vw = self.pad_to_hw[1] if self.pad_to_hw is not None else cur.shape[3]
-                if ops.stem_uses_s2d(st.dim_in, d.factor, d.kernel_size, d.padding, vw):
-                    conv_w = pk['conv_w_s2d']
-                    s2d = self._scratch_buf('s2d', b * cur.shape[2] * vw * st.dim_in, torch.float16, dev)
-            xs = ops.downsample_cf2cl(
-                cur, cur_nchw, conv_w, c, d.kernel_size, d.factor, d.padding, pk['ds_ln_w'], pk['ds_ln_b'],
-                virtual_hw=self.pad_to_hw if s == 0 else None,
-                token_mask=token_mask if s == 0 else None, mask_token=pk['mask_token'], s2d_scratch=s2d)
-            if s == 0 and token_mask is not None:
-                assert st.mask_token is not None, 'No mask token present in this stage'
-            _, hh, ww, _ = xs.shape
-            n_tok = b * hh * ww
-            if taps is not None:
-                taps[f'stages.{s}.downsample'] = xs.clone()
-            for bi, blk in enumerate(pk['blocks']):
-                tap_prefix = f"stages.{s}.att_blocks.{bi // 2}.{'att_grid' if blk['grid'] else 'att_window'}."
-                rows = ops.attention_scratch_rows(b, hh, ww, blk['part'])
-                sq = self._scratch_buf('qkv', rows * 3 * c, torch.float16, dev)
-                so = self._scratch_buf('o', rows * c, torch.float16, dev)
-                sx = self._scratch_buf('xn', max(rows, ((n_tok + 127) // 128) * 128) * c, torch.float16, dev)
-                ops.partition_attention_(xs, blk, sq, so, sx)
-                if taps is not None:
-                    taps[tap_prefix + 'x_attn'] = xs.clone()
-                sh = self._scratch_buf('hidden', ((n_tok + 127) // 128) * 128 * blk['hidden'], torch.float16, dev)
-                ops.mlp_block_(xs, blk, sh, sx)
-                if taps is not None:
-                    taps[tap_prefix + 'x_mlp'] = xs.clone()
-            hp = cp = None
-            if prev_states[s] is not None:
-                hp, cp = (self._as_nhwc_f32(t) for t in prev_states[s])
-                assert hp.shape == xs.shape and cp.shape == xs.shape
-            h_new, c_new = ops.dws_conv_lstm(xs, hp, cp, pk, st.lstm.ks)
+        for s in range(self.num_stages):
+            h_new, c_new = self._stage_step(s, packed[s], cur, cur_nchw, prev_states[s],
+                                            token_mask if s == 0 else None)
             h_nchw, c_nchw = h_new.permute(0, 3, 1, 2), c_new.permute(0, 3, 1, 2)
             states.append((h_nchw, c_nchw))
             output[s + 1] = h_nchw
             cur, cur_nchw = h_new, False
         return output, states
+
+    def _prep_input(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise RuntimeError('rvt_b200.RNNDetector runs on CUDA (sm_100a) only; there is no CPU fallback')
+        assert x.dim() == 4 and x.shape[1] == self.stages[0].dim_in
+        if x.dtype not in (torch.uint8, torch.float16, torch.float32):
+            x = x.to(torch.float32)
+        return x.contiguous()
+
+    def _stage_step(self, s: int, pk: dict, cur: torch.Tensor, cur_nchw: bool, prev_state: LstmState,
+                    token_mask: Optional[torch.Tensor]):
+        """One RNNDetectorStage.forward (maxvit_rnn.py:169-182) enqueued on the CURRENT stream:
+        downsample(+LN) -> [window block, grid block] x num_blocks -> Conv-LSTM.  Scratch buffers are
+        per stage, so different stages may run concurrently on different streams."""
+        st = self.stages[s]
+        d = st.downsample_cf2cl
+        c = st.dim
+        dev = cur.device
+        b = cur.shape[0]
+        taps = self.debug_taps
+        conv_w, s2d = pk['conv_w'], None
+        if s == 0 and pk['conv_w_s2d'] is not None:
+            vw = self.pad_to_hw[1] if self.pad_to_hw is not None else cur.shape[3]
+            if ops.stem_uses_s2d(st.dim_in, d.factor, d.kernel_size, d.padding, vw):
+                conv_w = pk['conv_w_s2d']
+                s2d = self._scratch_buf('s2d', b * cur.shape[2] * vw * st.dim_in, torch.float16, dev)
+        if s == 0 and token_mask is not None:
+            assert st.mask_token is not None, 'No mask token present in this stage'
+        xs = ops.downsample_cf2cl(
+            cur, cur_nchw, conv_w, c, d.kernel_size, d.factor, d.padding, pk['ds_ln_w'], pk['ds_ln_b'],
+            virtual_hw=self.pad_to_hw if s == 0 else None,
+            token_mask=token_mask if s == 0 else None, mask_token=pk['mask_token'], s2d_scratch=s2d)
+        _, hh, ww, _ = xs.shape
+        n_tok = b * hh * ww
+        if taps is not None:
+            taps[f'stages.{s}.downsample'] = xs.clone()
+        for bi, blk in enumerate(pk['blocks']):
+            tap_prefix = f"stages.{s}.att_blocks.{bi // 2}.{'att_grid' if blk['grid'] else 'att_window'}."
+            rows = ops.attention_scratch_rows(b, hh, ww, blk['part'])
+            sq = self._scratch_buf(f'qkv{s}', rows * 3 * c, torch.float16, dev)
+            so = self._scratch_buf(f'o{s}', rows * c, torch.float16, dev)
+            sx = self._scratch_buf(f'xn{s}', max(rows, ((n_tok + 127) // 128) * 128) * c, torch.float16, dev)
+            ops.partition_attention_(xs, blk, sq, so, sx)
+            if taps is not None:
+                taps[tap_prefix + 'x_attn'] = xs.clone()
+            sh = self._scratch_buf(f'hidden{s}', ((n_tok + 127) // 128) * 128 * blk['hidden'], torch.float16, dev)
+            ops.mlp_block_(xs, blk, sh, sx)
+            if taps is not None:
+                taps[tap_prefix + 'x_mlp'] = xs.clone()
+        hp = cp = None
+        if prev_state is not None:
+            hp, cp = (self._as_nhwc_f32(t) for t in prev_state)
+            assert hp.shape == xs.shape and cp.shape == xs.shape
+        return ops.dws_conv_lstm(xs, hp, cp, pk, st.lstm.ks)
+
+    @torch.no_grad()
+    def forward_sequence(self, xs, prev_states: Optional[LstmStates] = None, token_masks=None,
+                         wavefront: bool = True, input_ready=None):
+        """Run consecutive timesteps (extension of the reference API; the reference's time loop lives
+        in the harness, modules/detection.py:131-148 / :231-243).
+
+        xs: sequence (list or [L, B, C, H, W] tensor) of event tensors.  Returns
+        ([{1..4: feat} per step], final states) exactly as L chained ``forward`` calls would.
+
+        wavefront=True exploits the recurrence structure: stage s at step t depends only on
+        (s-1, t) and (s, t-1), so the four stages run on four CUDA streams, stage s working on step
+        t while stage s-1 already works on t+1.  The small-grid kernels of the wide late stages then
+        overlap the big grids of the early stages instead of leaving SMs idle.
+
+        input_ready: optional per-step CUDA events (e.g. of host->device copies on a copy stream) the
+        first stage waits on.  After the call ``self.last_step_events[t]`` is the event recorded when
+        step t's last stage finished (lets a caller overlap device->host reads of step t).
+        """
+        L = len(xs)
+        if prev_states is None:
+            prev_states = [None] * self.num_stages
+        assert len(prev_states) == self.num_stages
+        if L == 0:
+            return [], list(prev_states)
+        dev = xs[0].device
+        packed = self._ensure_packed(dev)
+        main = torch.cuda.current_stream(dev)
+        n = self.num_stages
+        if wavefront:
+            if getattr(self, '_streams', None) is None or self._streams[0].device != dev:
+                self._streams = [torch.cuda.Stream(dev) for _ in range(n)]
+            streams = self._streams
+            for st_ in streams:
+                st_.wait_stream(main)
+        else:
+            streams = [main] * n
+        state = list(prev_states)
+        outs = [dict() for _ in range(L)]
+        feats_prev = [None] * L              # output of stage s-1 per step (channels-last)
+        done = [[None] * L for _ in range(n)]
+        for t in range(L):
+            x_t = self._prep_input(xs[t])
+            for s in range(n):
+                with torch.cuda.stream(streams[s]):
+                    if s == 0 and input_ready is not None:
+                        streams[0].wait_event(input_ready[t])
+                    if wavefront and s > 0:
+                        streams[s].wait_event(done[s - 1][t])
+                    cur, nchw = (x_t, True) if s == 0 else (feats_prev[t], False)
+                    tm = token_masks[t] if (token_masks is not None and s == 0) else None
+                    h_new, c_new = self._stage_step(s, packed[s], cur, nchw, state[s], tm)
+                    if wavefront or s == n - 1:
+                        ev = torch.cuda.Event()
+                        ev.record(streams[s])
+                        done[s][t] = ev
+                    if wavefront:
+                        if s + 1 < n:
+                            h_new.record_stream(streams[s + 1])
+                        h_new.record_stream(main)
+                        c_new.record_stream(main)
+                    feats_prev[t] = h_new
+                    state[s] = (h_new.permute(0, 3, 1, 2), c_new.permute(0, 3, 1, 2))
+                    outs[t][s + 1] = state[s][0]
+        self.last_step_events = done[n - 1]
+        if wavefront:
+            for st_ in streams:
+                main.wait_stream(st_)
+        return outs, state
 
 
 def build_recurrent_backbone(backbone_cfg):

@@ -213,8 +213,12 @@ int rvt_downsample_cf2cl(const void* in, int in_dtype, int in_nchw, int batch, i
     const size_t smem = static_cast<size_t>(cin) * (kS2dStrip + 2) * sizeof(__half) + static_cast<size_t>(stride) * cin * 2;
     if (stride * cin > 256) return kErrUnsupported;
     if (smem > 48 * 1024) return kErrUnsupported;
-    stem_s2d_kernel<<<dim3((wg * stride + kS2dStrip - 1) / kS2dStrip, hin, batch), 256, smem, st>>>(in, in_dtype, cin, hin, win, wg, stride,
-                                                                           static_cast<__half*>(s2d_scratch));
+    if (in_dtype == 1 && stride == 4 && win % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 3) == 0 && cin <= 64)
+      stem_s2d_u8x4_kernel<<<dim3((wg + 63) / 64, hin, batch), 256, static_cast<size_t>(64) * 4 * cin * sizeof(__half), st>>>(
+          static_cast<const uint8_t*>(in), cin, hin, win, wg, static_cast<__half*>(s2d_scratch));
+    else
+      stem_s2d_kernel<<<dim3((wg * stride + kS2dStrip - 1) / kS2dStrip, hin, batch), 256, smem, st>>>(
+          in, in_dtype, cin, hin, win, wg, stride, static_cast<__half*>(s2d_scratch));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return static_cast<int>(e);
     a.cin = s2d_scratch; a.in_dtype = 2; a.in_nchw = 0;

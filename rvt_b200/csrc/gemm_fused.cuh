@@ -780,4 +780,33 @@ __global__ void __launch_bounds__(256) stem_s2d_kernel(const void* __restrict__ 
   }
 }
 
+// Fast path of the above for the common case uint8 events, f == 4, W % 4 == 0: one aligned 32-bit
+// load brings the 4 pixels of a (channel, group); the [64 groups x 4*Cin] fp16 strip is assembled in
+// shared memory and written out as 16-byte vectors (the strip is one contiguous global range).
+__global__ void __launch_bounds__(256) stem_s2d_u8x4_kernel(const uint8_t* __restrict__ in, int Cin, int H, int W, int Wg,
+                                                            __half* __restrict__ out) {
+  extern __shared__ __half s_out[];              // [64 groups][4*Cin]
+  const int strip = blockIdx.x, y = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x;
+  const int g = tid & 63, cq = tid >> 6;         // 64 groups x 4 channel lanes
+  const int cg = 4 * Cin;
+  const int x = strip * 256 + g * 4;
+  for (int ci = cq; ci < Cin; ci += 4) {
+    uint32_t w = 0;
+    if (x < W) w = __ldg(reinterpret_cast<const uint32_t*>(in + ((static_cast<size_t>(b) * Cin + ci) * H + y) * W + x));
+    __half* o = s_out + g * cg + ci;
+    o[0] = __ushort2half_rn(static_cast<unsigned short>(w & 0xFF));
+    o[Cin] = __ushort2half_rn(static_cast<unsigned short>((w >> 8) & 0xFF));
+    o[2 * Cin] = __ushort2half_rn(static_cast<unsigned short>((w >> 16) & 0xFF));
+    o[3 * Cin] = __ushort2half_rn(static_cast<unsigned short>(w >> 24));
+  }
+  __syncthreads();
+  const int g0 = strip * 64;
+  const int ngrp = min(64, Wg - g0);
+  const int n16 = ngrp * cg / 8;                 // cg % 8 == 0 -> whole uint4s
+  uint4* dst = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * H + y) * Wg + g0) * cg);
+  const uint4* src = reinterpret_cast<const uint4*>(s_out);
+  for (int i = tid; i < n16; i += 256) dst[i] = src[i];
+}
+
 }  // namespace rvt

@@ -135,3 +135,27 @@ def test_states_are_harness_compatible():
     assert set(out2) == {1, 2, 3, 4}
     with pytest.raises(NotImplementedError):
         m(x)        # grad mode: backward kernels not built -> loud failure, not a silent fallback
+
+
+@pytest.mark.parametrize('name', ['tiny_p6', 'dws_hidden', 'rvt_t_gen1'])
+def test_forward_sequence_equals_chained_forward(name):
+    """forward_sequence (sequential and 4-stream wavefront schedule) is bit-identical to chaining
+    the reference-API forward() over the timesteps, including a non-None initial state."""
+    case = BACKBONE_CASES[name]
+    m, _, spec = build_module(case)
+    L = 4
+    xs = [bo.synth_events_tensor(900 + t, case['batch'], 20, case['height'], case['width']).cuda() for t in range(L)]
+    with torch.no_grad():
+        _, st0 = m(xs[0].float())
+        ref_out, st = [], st0
+        for t in range(L):
+            o, st = m(xs[t], st)
+            ref_out.append(o)
+        for wf in (False, True):
+            outs, st2 = m.forward_sequence(xs, st0, wavefront=wf)
+            torch.cuda.synchronize()
+            for t in range(L):
+                for k in (1, 2, 3, 4):
+                    assert torch.equal(outs[t][k], ref_out[t][k]), (wf, t, k)
+            for (h, c), (h2, c2) in zip(st, st2):
+                assert torch.equal(h, h2) and torch.equal(c, c2)
