@@ -3,5 +3,6 @@ backbone forward (``RNNDetector``) and the event -> ``StackedHistogram`` voxeliz
 reference's own module API.  See DESIGN.md / INTEGRATION.md."""
 from .backbone import RNNDetector, RNNDetectorStage, build_recurrent_backbone  # noqa: F401
 from .representations import StackedHistogram  # noqa: F401
+from .graph import GraphedCallable, capture_sequence  # noqa: F401
 
 MaxViTRNNDetector = RNNDetector

@@ -445,6 +445,7 @@ class RNNDetector(nn.Module):
         outs = [dict() for _ in range(L)]
         feats_prev = [None] * L              # output of stage s-1 per step (channels-last)
         done = [[None] * L for _ in range(n)]
+        capturing = torch.cuda.is_current_stream_capturing()
         for t in range(L):
             x_t = self._prep_input(xs[t])
             for s in range(n):
@@ -460,7 +461,8 @@ class RNNDetector(nn.Module):
                         ev = torch.cuda.Event()
                         ev.record(streams[s])
                         done[s][t] = ev
-                    if wavefront:
+                    if wavefront and not capturing:
+                        # eager mode: tell the caching allocator about the cross-stream consumers
                         if s + 1 < n:
                             h_new.record_stream(streams[s + 1])
                         h_new.record_stream(main)

@@ -172,12 +172,15 @@ int rvt_stacked_histogram(const int64_t* x, const int64_t* y, const int64_t* pol
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t n_out = 2 * static_cast<int64_t>(bins) * height * width;
   const int cutoff = count_cutoff <= 0 ? 255 : (count_cutoff > 255 ? 255 : count_cutoff);
+  if (n_out >= (static_cast<int64_t>(1) << 32) - 1) return kErrUnsupported;
   if (n > 0) {
     if (!x || !y || !pol || !t) return kErrBadArg;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(pol) |
+         reinterpret_cast<uintptr_t>(t)) & 15) return kErrBadArg;   // 16-byte aligned event arrays
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int64_t blocks = (n + 255) / 256;
+    int64_t blocks = (n / 2 + 255) / 256 + 1;
     const int64_t cap = static_cast<int64_t>(sms) * 8;  // 8 resident CTAs of 256 threads per SM
     if (blocks > cap) blocks = cap;
     voxel_accumulate_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, y, pol, t, n, bins, height, width, counts, err_flag);

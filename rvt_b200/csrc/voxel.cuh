@@ -12,6 +12,32 @@
 
 namespace rvt {
 
+// One event -> bin index (0xFFFFFFFF if rejected).  n_out < 2^32 is checked on the host.
+__device__ __forceinline__ uint32_t voxel_bin(int64_t xi, int64_t yi, int64_t pi, int64_t ti, int64_t t0, float denom, float fb,
+                                              int bins, int H, int W, int64_t hw, int* err) {
+  const float q = __fdiv_rn(__ll2float_rn(ti - t0), denom);
+  float f = floorf(__fmul_rn(q, fb));
+  f = fminf(f, fb - 1.0f);
+  if (pi < 0 || pi > 1) { atomicOr(err, 2); return 0xFFFFFFFFu; }
+  if (xi < 0 || xi >= W || yi < 0 || yi >= H) { atomicOr(err, 4); return 0xFFFFFFFFu; }
+  return static_cast<uint32_t>(xi + W * yi + hw * static_cast<int64_t>(f) + bins * hw * pi);
+}
+
+// Adaptive warp aggregation: events are time sorted, so a hot pixel shows up as equal bin indices in
+// neighbouring lanes.  One shuffle + vote decides per warp whether to pay for match_any (one atomic
+// per distinct bin) or to issue plain reductions (the spatially-random common case, where match_any's
+// MIO cost dominated: profiles/ncu_r01.md).
+__device__ __forceinline__ void voxel_commit(uint32_t idx, uint32_t* __restrict__ counts) {
+  const uint32_t nb = __shfl_down_sync(0xffffffffu, idx, 1);
+  const bool dup = idx != 0xFFFFFFFFu && idx == nb && (threadIdx.x & 31) != 31;
+  if (__any_sync(0xffffffffu, dup)) {
+    const unsigned peers = __match_any_sync(0xffffffffu, idx);
+    if (idx != 0xFFFFFFFFu && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(counts + idx, static_cast<uint32_t>(__popc(peers)));
+  } else if (idx != 0xFFFFFFFFu) {
+    atomicAdd(counts + idx, 1u);
+  }
+}
+
 __global__ void __launch_bounds__(256) voxel_accumulate_kernel(const int64_t* __restrict__ x, const int64_t* __restrict__ y,
                                                                const int64_t* __restrict__ pol,
                                                                const int64_t* __restrict__ t, int64_t n, int bins,
@@ -22,28 +48,29 @@ __global__ void __launch_bounds__(256) voxel_accumulate_kernel(const int64_t* __
   const float denom = __ll2float_rn(dt > 1 ? dt : 1);
   const float fb = static_cast<float>(bins);
   const int64_t hw = static_cast<int64_t>(H) * W;
-  const int64_t n_out = 2 * static_cast<int64_t>(bins) * hw;
   if (blockIdx.x == 0 && threadIdx.x == 0 && dt < 0) atomicOr(err, 1);  // time not sorted
 
+  // two consecutive events per thread per iteration: 16-byte loads from each of the four arrays
+  const int64_t npairs = n >> 1;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  const int64_t n_round = (n + 31) & ~static_cast<int64_t>(31);       // keep warps converged
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-    int64_t idx = -1;
-    if (i < n) {
-      const int64_t xi = __ldcs(x + i), yi = __ldcs(y + i), pi = __ldcs(pol + i), ti = __ldcs(t + i);
-      const float q = __fdiv_rn(__ll2float_rn(ti - t0), denom);
-      float f = floorf(__fmul_rn(q, fb));
-      f = fminf(f, fb - 1.0f);
-      idx = xi + W * yi + hw * static_cast<int64_t>(f) + bins * hw * pi;
-      if (pi < 0 || pi > 1) { atomicOr(err, 2); idx = -1; }
-      else if (xi < 0 || xi >= W || yi < 0 || yi >= H || idx < 0 || idx >= n_out) { atomicOr(err, 4); idx = -1; }
+  const int64_t pairs_round = (npairs + 31) & ~static_cast<int64_t>(31);     // keep warps converged
+  const longlong2* x2 = reinterpret_cast<const longlong2*>(x);
+  const longlong2* y2 = reinterpret_cast<const longlong2*>(y);
+  const longlong2* p2 = reinterpret_cast<const longlong2*>(pol);
+  const longlong2* t2 = reinterpret_cast<const longlong2*>(t);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < pairs_round; i += stride) {
+    uint32_t ia = 0xFFFFFFFFu, ib = 0xFFFFFFFFu;
+    if (i < npairs) {
+      const longlong2 xv = __ldcs(x2 + i), yv = __ldcs(y2 + i), pv = __ldcs(p2 + i), tv = __ldcs(t2 + i);
+      ia = voxel_bin(xv.x, yv.x, pv.x, tv.x, t0, denom, fb, bins, H, W, hw, err);
+      ib = voxel_bin(xv.y, yv.y, pv.y, tv.y, t0, denom, fb, bins, H, W, hw, err);
     }
-    // warp-aggregate events that hit the same bin (hot pixels): one atomic per distinct bin
-    const unsigned peers = __match_any_sync(0xffffffffu, idx);
-    if (idx >= 0) {
-      const int leader = __ffs(peers) - 1;
-      if ((threadIdx.x & 31) == leader) atomicAdd(counts + idx, static_cast<uint32_t>(__popc(peers)));
-    }
+    voxel_commit(ia, counts);
+    voxel_commit(ib, counts);
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {   // odd tail event
+    const uint32_t il = voxel_bin(x[n - 1], y[n - 1], pol[n - 1], t[n - 1], t0, denom, fb, bins, H, W, hw, err);
+    if (il != 0xFFFFFFFFu) atomicAdd(counts + il, 1u);
   }
 }
 

@@ -159,3 +159,26 @@ def test_forward_sequence_equals_chained_forward(name):
                     assert torch.equal(outs[t][k], ref_out[t][k]), (wf, t, k)
             for (h, c), (h2, c2) in zip(st, st2):
                 assert torch.equal(h, h2) and torch.equal(c, c2)
+
+
+def test_graphed_sequence_matches_eager():
+    """rvt_b200.capture_sequence: replaying the captured multi-stream graph (twice, with refilled static
+    inputs) reproduces the eager forward_sequence bit for bit."""
+    import rvt_b200
+    case = BACKBONE_CASES['tiny_p6']
+    m, _, _ = build_module(case)
+    L = 3
+    xs = torch.stack([bo.synth_events_tensor(700 + t, 2, 20, 64, 96) for t in range(L)]).cuda()
+    g = rvt_b200.capture_sequence(m, xs)
+    for rep in range(2):
+        fresh = torch.stack([bo.synth_events_tensor(800 + 10 * rep + t, 2, 20, 64, 96) for t in range(L)]).cuda()
+        xs.copy_(fresh)
+        outs, st = g()
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            ref_outs, ref_st = m.forward_sequence(fresh, None, wavefront=False)
+        for t in range(L):
+            for k in (1, 2, 3, 4):
+                assert torch.equal(outs[t][k], ref_outs[t][k]), (rep, t, k)
+        for (h, c), (h2, c2) in zip(st, ref_st):
+            assert torch.equal(h, h2) and torch.equal(c, c2)
