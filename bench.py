@@ -107,16 +107,30 @@ def cpu_reference_fps(n_timesteps, batch, threads):
     return batch * n_timesteps / dt
 
 
+def best_cpu_threads():
+    """torch's intra-op pool at os.cpu_count() threads is far slower than a moderate pool on big hosts
+    (measured 0.56 frames/s at 128 threads vs ~10 at 8-32): calibrate on one bs=1 timestep."""
+    cores = os.cpu_count() or 1
+    cands = sorted({c for c in (8, 16, 32, 64, cores) if c <= cores})
+    best, best_fps = cands[0], 0.0
+    for c in cands:
+        fps = cpu_reference_fps(1, 1, c)
+        if fps > best_fps:
+            best, best_fps = c, fps
+    return best
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    cores = os.cpu_count()
+    cores = best_cpu_threads()
     n_ts = 2                     # bounded sample: 2 timesteps x 8 samples per "step"
     vals = []
     for _ in range(max(1, min(args.steps, 3))):
         vals.append(cpu_reference_fps(n_ts, B_PER_GPU, cores))
     v = sum(vals) / len(vals)
-    sample = f'{n_ts} timesteps x batch {B_PER_GPU} of the 21-timestep sequence per step (states carried), fp32'
+    sample = (f'{n_ts} timesteps x batch {B_PER_GPU} of the 21-timestep sequence per step (states carried), fp32; '
+              f'{cores} torch threads (best of a sweep up to os.cpu_count()={os.cpu_count()})')
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'frames/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * B_PER_GPU * SEQ_LEN / v,
@@ -148,6 +162,7 @@ def main():
 
     import torch.distributed as dist
     import rvt_b200
+    from rvt_b200 import sharding
     from oracle import backbone_oracle as bo     # synthetic parameter / input generators only
 
     torch.cuda.set_device(local_rank)
@@ -161,8 +176,11 @@ def main():
     model = model.to(dev).eval()
     model.pad_to_hw = (PAD_H, PAD_W)
 
+    # weak scaling: the global batch is 8*N samples; this rank owns [lo, hi) and its states (no exchange)
+    lo, hi = sharding.batch_slice(B_PER_GPU * world, rank, world)
+    assert hi - lo == B_PER_GPU
     # synthetic uint8 event tensors: SEQ_LEN timesteps, resident on the device (37 MB each)
-    g = torch.Generator(device='cpu').manual_seed(1234 + rank)
+    g = torch.Generator(device='cpu').manual_seed(1234 + lo)
     seq_host = (torch.randint(1, 11, (SEQ_LEN, B_PER_GPU, IN_C, IN_H, IN_W), generator=g, dtype=torch.uint8) *
                 (torch.rand((SEQ_LEN, B_PER_GPU, IN_C, IN_H, IN_W), generator=g) < 0.1)).pin_memory()
     seq_dev = seq_host.to(dev)
@@ -215,11 +233,7 @@ def main():
             fn()
         e1.record()
         torch.cuda.synchronize(dev)
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            tt = torch.tensor([ms], device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            ms = float(tt.item())
+        ms = sharding.max_over_ranks(e0.elapsed_time(e1), dev)     # device time, max over ranks
         barrier()
         return ms
 
@@ -241,6 +255,36 @@ def main():
             step_e2e()
         ms_e2e = timed(step_e2e, args.steps)
 
+    # ---- roofline of the dominant kernel, timed live with CUDA events on its launch stream ----
+    # attn_fused_kernel, stage-1 instance (largest share of the step in profiles/launches_r01.txt): one
+    # launch = the attention half of one PartitionAttentionCl block over 8 x 96 x 160 tokens, C = 64.
+    roof = None
+    if rank == 0:
+        from rvt_b200 import ops
+        with torch.inference_mode():
+            pk = model._ensure_packed(dev)[0]
+            blk = pk['blocks'][0]
+            n_tok, c, P = B_PER_GPU * 96 * 160, 64, 60
+            bufs = [torch.randn(B_PER_GPU, 96, 160, c, device=dev) for _ in range(10)]   # 315 MB > L2: cold x every launch
+            dummy = torch.empty(1, dtype=torch.float16, device=dev)
+            for xb in bufs[:3]:
+                ops.partition_attention_(xb, blk, dummy, dummy, dummy)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 3
+            e0.record()
+            for _ in range(reps):
+                for xb in bufs:
+                    ops.partition_attention_(xb, blk, dummy, dummy, dummy)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            us = e0.elapsed_time(e1) * 1e3 / (reps * len(bufs))
+            del bufs
+        algo_bytes = 2 * n_tok * c * 4                               # x read + x written, fp32
+        algo_flops = 8 * n_tok * c * c + 4 * n_tok * P * c           # qkv + proj + QK^T + PV
+        roof = {'kernel': 'attn_fused_kernel (stage 1, C=64, 122880 tokens)', 'us_per_launch': us,
+                'algorithmic_bytes': algo_bytes, 'algorithmic_flops': algo_flops}
+
     frames = B_PER_GPU * SEQ_LEN * args.steps * world
     value = frames / (ms * 1e-3)
     e2e = frames / (ms_e2e * 1e-3)
@@ -251,7 +295,15 @@ def main():
         except Exception:
             pass
         peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
+        peak_gbs = peaks.get('hbm_gbs', 6650.0)
+        peak_src = 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback (B200_PROFILING.md)'
         ach_tf = value / world * GFLOP_PER_FRAME / 1e3
+        ach_gbs = roof['algorithmic_bytes'] / roof['us_per_launch'] / 1e3
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic_r01.json'))).get('attn_fused_s1_dram_bytes')
+        except Exception:
+            pass
         line = {
             'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
@@ -267,16 +319,21 @@ def main():
                     'd2h_bytes_per_step': SEQ_LEN * feat_host.numel() * 4},
             'gpu_launches': LAUNCHES_PER_TIMESTEP * SEQ_LEN * args.steps,
             'clocks': clocks,
-            'roofline': {'bound': 'tensor', 'achieved': ach_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                         'frac': ach_tf / peak_tf, 'traffic': None,
-                         'note': 'whole-step algorithmic FLOPs (20.62 GFLOP/frame) / step time vs measured '
-                                 'sustained bf16 peak; per-kernel table in profiles/'},
+            # C = 64: 94 FLOP/B algorithmic intensity, below the 263 FLOP/B ridge -> HBM is the bounding roof
+            'roofline': {'bound': 'hbm', 'achieved': ach_gbs, 'peak': peak_gbs, 'unit': 'GB/s',
+                         'frac': ach_gbs / peak_gbs, 'traffic': traffic, 'kernel': roof['kernel'],
+                         'us_per_launch': roof['us_per_launch'], 'peak_source': peak_src,
+                         'tensor_tflops': roof['algorithmic_flops'] / roof['us_per_launch'] / 1e6,
+                         'note': 'algorithmic bytes = x read + written (fp32) = 62.9 MB per launch; see DESIGN.md §6'},
+            'whole_step': {'algorithmic_tflops': ach_tf, 'frac_of_sustained_bf16_peak': ach_tf / peak_tf,
+                           'gflop_per_frame': GFLOP_PER_FRAME},
         }
         if not args.no_cpu_baseline:
-            cores = os.cpu_count()
+            cores = best_cpu_threads()
             v = cpu_reference_fps(2, B_PER_GPU, cores)
             line['cpu_baseline'] = {'value': v, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
-                                    'sample': '2 timesteps x batch 8 (after 1 warm-up timestep), fp32 torch CPU'}
+                                    'sample': '2 timesteps x batch 8 (after 1 warm-up timestep), fp32 torch CPU ops; '
+                                              f'{cores} threads = best of a sweep up to os.cpu_count()={os.cpu_count()}'}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

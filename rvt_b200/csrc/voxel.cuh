@@ -18,6 +18,7 @@ __device__ __forceinline__ uint32_t voxel_bin(int64_t xi, int64_t yi, int64_t pi
   const float q = __fdiv_rn(__ll2float_rn(ti - t0), denom);
   float f = floorf(__fmul_rn(q, fb));
   f = fminf(f, fb - 1.0f);
+  if (!(f >= 0.0f)) { atomicOr(err, 1); return 0xFFFFFFFFu; }   // t < t[0]: time not sorted
   if (pi < 0 || pi > 1) { atomicOr(err, 2); return 0xFFFFFFFFu; }
   if (xi < 0 || xi >= W || yi < 0 || yi >= H) { atomicOr(err, 4); return 0xFFFFFFFFu; }
   return static_cast<uint32_t>(xi + W * yi + hw * static_cast<int64_t>(f) + bins * hw * pi);
