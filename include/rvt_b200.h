@@ -62,12 +62,16 @@ int rvt_stacked_histogram(const int64_t* x, const int64_t* y, const int64_t* pol
  * token_mask: u8 [B,Hout,Wout] or NULL; mask_token: f32 [Cout].
  * s2d_scratch (stem fast path, in_nchw only): f16 [B, Hin, Wout, stride*Cin] workspace; when given
  * the input is first re-laid out space-to-depth so every conv tap is a 16-byte vector load, and
- * w_packed must come from packing.pack_stem_weight_s2d().  NULL selects the generic gather path. */
+ * w_packed must come from packing.pack_stem_weight_s2d().  NULL selects the generic gather path.
+ * stem_mode: 0/1 = paths above; 2 = uint8 NCHW 7x7/s4 stem with the input patch staged in shared memory
+ * (needs rvt_stem_u8_ok(); w_packed from packing.pack_stem_weight_u8(); no scratch). */
 int rvt_downsample_cf2cl(const void* in, int in_dtype, int in_nchw, int batch, int cin, int hin, int win,
                          int ksize, int stride, int pad, int hout, int wout, int cout,
                          const void* w_packed, const float* ln_w, const float* ln_b, float eps,
                          const uint8_t* token_mask, const float* mask_token, float* out,
-                         void* s2d_scratch, void* stream);
+                         void* s2d_scratch, int stem_mode, void* stream);
+/* 1 if the uint8 smem-patch stem (stem_mode 2) supports this geometry. */
+int rvt_stem_u8_ok(int cin, int ksize, int stride, int pad, int win, int hout, int wout, int cout);
 
 /* ---- a4-a7: attention half of PartitionAttentionCl.forward  (maxvit.py:252-268, 273-354) -
  * x <- x + gamma1 * proj(attn(partition(norm1(x))))   in place, x: f32 [B,H,W,C].
@@ -93,10 +97,12 @@ int rvt_mlp_block(float* x, int64_t n_tokens, int dim, int hidden, const float* 
  * x, h_prev, c_prev, h_out, c_out: f32 [B,H,W,C]; h_prev/c_prev NULL => zero state.
  * dws_mode 0: no depthwise conv; 1: depthwise ks x ks (+bias) on h_prev only; 2: on cat(x,h).
  * dw_w: f32 [ks*ks][D] (tap-major), dw_b: f32 [D], D = C (mode 1) or 2C (mode 2).
- * w_packed / bias_tiled: rvt_b200.packing.pack_lstm_weight() (gate-interleaved tiles). */
+ * w_packed / bias_tiled: rvt_b200.packing.pack_lstm_weight() (gate-interleaved tiles).
+ * scratch_xh: optional f16 [round_up(B*H*W,128), 2C] workspace (used when dim >= 256 and dws_mode == 0). */
 int rvt_dws_conv_lstm(const float* x, const float* h_prev, const float* c_prev, int batch, int height,
                       int width, int dim, const void* w_packed, const float* bias_tiled, const float* dw_w,
-                      const float* dw_b, int dws_mode, int dws_ks, float* h_out, float* c_out, void* stream);
+                      const float* dw_b, int dws_mode, int dws_ks, float* h_out, float* c_out, void* scratch_xh,
+                      void* stream);
 
 /* ---- building block exposed for tests: D = A W^T + b, f16 in / f16 out ------------------
  * a: f16 [m, k] row-major (k % 8 == 0), w_packed: pack_linear_weight(W[n,k]), out: f16

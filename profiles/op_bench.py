@@ -89,7 +89,8 @@ def main():
             timeit('attn', s, lambda: ops.partition_attention_(xs, blk, sq, so, sxn), 8 * n * c * c + 4 * n * P * c, 2 * n * c * 4)
             timeit('mlp', s, lambda: ops.mlp_block_(xs, blk, sh, sxn), 16 * n * c * c, 2 * n * c * 4)
             hp, cp = torch.randn_like(xs), torch.randn_like(xs)
-            timeit('lstm', s, lambda: ops.dws_conv_lstm(xs, hp, cp, pk, 3), 16 * n * c * c, 5 * n * c * 4)
+            sxh = torch.empty(((n + 127) // 128) * 128 * 2 * c, dtype=torch.float16, device=dev)
+            timeit('lstm', s, lambda: ops.dws_conv_lstm(xs, hp, cp, pk, 3, sxh), 16 * n * c * c, 5 * n * c * 4)
             h, w, cin = ho, wo, c
     if rows:
         tot = sum(r['us'] for r in rows)

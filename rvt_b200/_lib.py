@@ -22,11 +22,13 @@ SIGNATURES = {
     'rvt_attention_scratch_rows': (_i64, [_i, _i, _i, _i, _i]),
     'rvt_stacked_histogram': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     'rvt_downsample_cf2cl': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f,
-                                   _vp, _vp, _vp, _vp, _vp]),
+                                   _vp, _vp, _vp, _vp, _i, _vp]),
+    'rvt_stem_u8_ok': (_i, [_i, _i, _i, _i, _i, _i, _i, _i]),
     'rvt_partition_attention': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp,
-                                      _vp, _vp, _vp, _vp, _vp]),
+                                      _vp, _vp, _vp, _vp, _i, _vp]),
+    'rvt_stem_u8_ok': (_i, [_i, _i, _i, _i, _i, _i, _i, _i]),
     'rvt_mlp_block': (_i, [_vp, _i64, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    'rvt_dws_conv_lstm': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    'rvt_dws_conv_lstm': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     'rvt_linear_f16': (_i, [_vp, _i64, _i, _i, _vp, _vp, _i, _vp, _vp]),
 }
 

@@ -264,6 +264,8 @@ class RNNDetector(nn.Module):
                                                     bn=L.rvt_conv_tile_n(c)),
                  'conv_w_s2d': (packing.pack_stem_weight_s2d(d.conv.weight.to(device), d.factor)
                                 if s == 0 and (d.factor * st.dim_in) % 8 == 0 else None),
+                 'conv_w_u8': (packing.pack_stem_weight_u8(d.conv.weight.to(device))
+                               if s == 0 and d.kernel_size == 7 and d.factor == 4 else None),
                  'ds_ln_w': f32(getattr(d.norm, 'weight', None)), 'ds_ln_b': f32(getattr(d.norm, 'bias', None)),
                  'mask_token': f32(st.mask_token.reshape(-1)) if st.mask_token is not None else None,
                  'blocks': []}
@@ -370,8 +372,11 @@ class RNNDetector(nn.Module):
         dev = cur.device
         b = cur.shape[0]
         taps = self.debug_taps
-        conv_w, s2d = pk['conv_w'], None
-        if s == 0 and pk['conv_w_s2d'] is not None:
+        conv_w, s2d, stem_mode = pk['conv_w'], None, 0
+        vhw = self.pad_to_hw if (s == 0 and self.pad_to_hw is not None) else (cur.shape[2], cur.shape[3])
+        if s == 0 and pk['conv_w_u8'] is not None and ops.stem_u8_ok(cur, st.dim_in, d.kernel_size, d.factor, d.padding, vhw, c):
+            conv_w, stem_mode = pk['conv_w_u8'], 2
+        elif s == 0 and pk['conv_w_s2d'] is not None:
             vw = self.pad_to_hw[1] if self.pad_to_hw is not None else cur.shape[3]
             if ops.stem_uses_s2d(st.dim_in, d.factor, d.kernel_size, d.padding, vw):
                 conv_w = pk['conv_w_s2d']
@@ -381,7 +386,8 @@ class RNNDetector(nn.Module):
         xs = ops.downsample_cf2cl(
             cur, cur_nchw, conv_w, c, d.kernel_size, d.factor, d.padding, pk['ds_ln_w'], pk['ds_ln_b'],
             virtual_hw=self.pad_to_hw if s == 0 else None,
-            token_mask=token_mask if s == 0 else None, mask_token=pk['mask_token'], s2d_scratch=s2d)
+            token_mask=token_mask if s == 0 else None, mask_token=pk['mask_token'], s2d_scratch=s2d,
+            stem_mode=stem_mode)
         _, hh, ww, _ = xs.shape
         n_tok = b * hh * ww
         if taps is not None:
@@ -403,7 +409,10 @@ class RNNDetector(nn.Module):
         if prev_state is not None:
             hp, cp = (self._as_nhwc_f32(t) for t in prev_state)
             assert hp.shape == xs.shape and cp.shape == xs.shape
-        return ops.dws_conv_lstm(xs, hp, cp, pk, st.lstm.ks)
+        sxh = None
+        if c >= 256 and pk['dws_mode'] == 0:
+            sxh = self._scratch_buf(f'xh{s}', ((n_tok + 127) // 128) * 128 * 2 * c, torch.float16, dev)
+        return ops.dws_conv_lstm(xs, hp, cp, pk, st.lstm.ks, sxh)
 
     @torch.no_grad()
     def forward_sequence(self, xs, prev_states: Optional[LstmStates] = None, token_masks=None,

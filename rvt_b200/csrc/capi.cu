@@ -4,6 +4,7 @@
 
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "attention_core.cuh"
@@ -55,15 +56,16 @@ bool make_tmap_f16_rows(const void* base, int64_t rows, int64_t cols, int64_t ld
 }
 
 template <int LOADER, int EPI>
-int launch_gemm(GemmArgs a, int n_mtiles, int n_ntiles, cudaStream_t st, const CUtensorMap* tmap = nullptr) {
+int launch_gemm(GemmArgs a, int n_mtiles, int n_ntiles, cudaStream_t st, const CUtensorMap* tmap = nullptr,
+                size_t extra_smem = 0) {
   a.KC = cdiv(a.K, 64);
   a.tmem_cols = static_cast<int>(tmem_cols_pow2(static_cast<uint32_t>(a.BN)));
   a.ab_fmt = 0;  // fp16 operands
   int stages = a.KC < 4 ? a.KC : 4;
-  while (stages > 2 && gemm_smem_bytes(stages, a.BN) > 100 * 1024) --stages;
-  while (stages > 1 && gemm_smem_bytes(stages, a.BN) > static_cast<size_t>(kMaxSmem)) --stages;
+  while (stages > 2 && gemm_smem_bytes(stages, a.BN, extra_smem) > 110 * 1024) --stages;
+  while (stages > 1 && gemm_smem_bytes(stages, a.BN, extra_smem) > static_cast<size_t>(kMaxSmem)) --stages;
   a.stages = stages;
-  const size_t smem = gemm_smem_bytes(stages, a.BN);
+  const size_t smem = gemm_smem_bytes(stages, a.BN, extra_smem);
   if (smem > static_cast<size_t>(kMaxSmem) || a.BN > 512 || a.BN % 16 != 0) return kErrUnsupported;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
@@ -124,11 +126,19 @@ const char* rvt_error_string(int code) {
   return cudaGetErrorString(static_cast<cudaError_t>(code));
 }
 
+static int rvt_wide_bn() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("RVT_WIDE_BN"); v = e ? atoi(e) : 128; }
+  return v;
+}
+
 int rvt_tile_n(int n_total, int k) {
   // Narrow stages (dim <= 128) have many 128-row tiles: one wide N-tile per CTA.  Wide stages
   // (dim >= 256) have few row tiles: cut N finer so the grid still covers the 148 SMs.
-  (void)k;
-  const int cap = 128;   // <=128 TMEM columns -> up to 4 CTAs / SM
+  // narrow stages: <=128 TMEM columns -> up to 4 CTAs / SM.  Wide stages are L2->SM bandwidth bound: wider
+  // N tiles re-read the A operand fewer times (profiles/ncu_r01.md).
+  const int dim = n_total < k ? n_total : k;
+  const int cap = (dim >= kWideDim && rvt_wide_bn() > 0) ? rvt_wide_bn() : 128;
   for (int bn = cap; bn >= 16; bn -= 16)
     if (n_total % bn == 0) return bn;
   return -1;
@@ -146,6 +156,11 @@ int rvt_mlp_tiles(int dim, int hidden, int* bn_fc1, int* bn_fc2) {
   if (bn_fc1) *bn_fc1 = fused ? kMlpHC : rvt_tile_n(hidden, dim);
   if (bn_fc2) *bn_fc2 = fused ? dim : rvt_tile_n(dim, hidden);
   return fused ? 1 : 0;
+}
+
+int rvt_stem_u8_ok(int cin, int ksize, int stride, int pad, int win, int hout, int wout, int cout) {
+  return (ksize == 7 && stride == 4 && pad == 3 && win % 16 == 0 && wout % kStemTileW == 0 && hout % kStemTileH == 0 &&
+          cout <= 128 && cin >= 1) ? 1 : 0;
 }
 
 int rvt_conv_tile_n(int cout) { return (cout >= kWideDim && cout % 128 == 0) ? 64 : cout; }
@@ -195,7 +210,7 @@ int rvt_stacked_histogram(const int64_t* x, const int64_t* y, const int64_t* pol
 int rvt_downsample_cf2cl(const void* in, int in_dtype, int in_nchw, int batch, int cin, int hin, int win, int ksize,
                          int stride, int pad, int hout, int wout, int cout, const void* w_packed, const float* ln_w,
                          const float* ln_b, float eps, const uint8_t* token_mask, const float* mask_token,
-                         float* out, void* s2d_scratch, void* stream) {
+                         float* out, void* s2d_scratch, int stem_mode, void* stream) {
   if (!in || !w_packed || !out || batch < 1 || cout % 16 != 0 || cout > 512) return kErrBadArg;
   if (!in_nchw && (in_dtype == 1 || cin % 8 != 0)) return kErrUnsupported;
   if ((ln_w == nullptr) != (ln_b == nullptr)) return kErrBadArg;
@@ -207,6 +222,20 @@ int rvt_downsample_cf2cl(const void* in, int in_dtype, int in_nchw, int batch, i
   const int64_t n_tok = static_cast<int64_t>(batch) * hout * wout;
   a.map = identity_map(n_tok, hout, wout);
   a.Hout = hout; a.Wout = wout;
+  const bool stem_u8 = in_nchw && in_dtype == 1 && ksize == 7 && stride == 4 && pad == 3 && win % 16 == 0 &&
+                       wout % kStemTileW == 0 && hout % kStemTileH == 0 && cout <= 128 &&
+                       (reinterpret_cast<uintptr_t>(in) & 15) == 0 && stem_mode == 2;
+  if (stem_u8) {
+    // uint8 events, 7x7/s4: input patch staged in smem, A tiles built smem -> smem (no scratch tensor)
+    RowMap bm{};
+    bm.mode = MAP_BLOCK; bm.H = hout; bm.W = wout; bm.ny = hout / kStemTileH; bm.nx = wout / kStemTileW;
+    bm.n_groups = batch * bm.ny * bm.nx; bm.n_tokens = static_cast<int>(n_tok);
+    a.map = bm;
+    a.cin = in; a.in_dtype = 1; a.in_nchw = 1; a.Cin = cin; a.Hin = hin; a.Win = win;
+    a.K = 7 * cin * 8;
+    a.yout = out; a.eln_w = ln_w; a.eln_b = ln_b; a.eeps = eps; a.token_mask = token_mask; a.mask_token = mask_token;
+    return launch_gemm<LD_STEM, EP_LN>(a, bm.n_groups, 1, st, nullptr, stem_patch_bytes(cin) + 128);
+  }
   if (s2d_scratch) {
     // space-to-depth stem: [B,Cin,H,W] -> f16 [B,H,Wg,f*Cin], then a (ks x 2)-tap vectorised conv
     const bool overlap = ksize == 2 * stride - 1 && pad == stride - 1;
@@ -394,7 +423,7 @@ int rvt_mlp_block(float* x, int64_t n_tokens, int dim, int hidden, const float* 
 
 int rvt_dws_conv_lstm(const float* x, const float* h_prev, const float* c_prev, int batch, int height, int width,
                       int dim, const void* w_packed, const float* bias_tiled, const float* dw_w, const float* dw_b,
-                      int dws_mode, int dws_ks, float* h_out, float* c_out, void* stream) {
+                      int dws_mode, int dws_ks, float* h_out, float* c_out, void* scratch_xh, void* stream) {
   if (!x || !w_packed || !bias_tiled || !h_out || !c_out) return kErrBadArg;
   if (dim % 16 != 0 || dws_mode < 0 || dws_mode > 2) return kErrUnsupported;
   if (dws_mode != 0 && (!dw_w || !dw_b || dws_ks % 2 == 0)) return kErrBadArg;
@@ -407,7 +436,20 @@ int rvt_dws_conv_lstm(const float* x, const float* h_prev, const float* c_prev, 
   a.map = identity_map(n_tok, height, width);
   a.x = x; a.C = dim; a.hprev = h_prev; a.dw_w = dw_w; a.dw_b = dw_b; a.dws_mode = dws_mode; a.dws_ks = dws_ks;
   a.cprev = c_prev; a.hout = h_out; a.cout = c_out; a.cw = cw;
-  return launch_gemm<LD_XH, EP_LSTM>(a, cdiv(n_tok, 128), dim / cw, static_cast<cudaStream_t>(stream));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n_mtiles = cdiv(n_tok, 128);
+  if (dws_mode == 0 && dim >= kWideDim && scratch_xh != nullptr) {
+    // wide stage, plain 1x1 cell: cast [x|h] once, then a TMA-fed mainloop (no per-N-tile A rebuild)
+    const int n_rows = n_mtiles * 128;
+    const int64_t items = static_cast<int64_t>(n_rows) * (2 * dim / 8);
+    cast_xh_kernel<<<static_cast<unsigned>((items + 255) / 256), 256, 0, st>>>(x, h_prev, static_cast<int>(n_tok), n_rows, dim,
+                                                                             static_cast<__half*>(scratch_xh));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return static_cast<int>(e);
+    a.a16 = static_cast<const __half*>(scratch_xh); a.lda = 2 * dim; a.a_rows = n_rows;
+    return launch_gemm_f16<EP_LSTM>(a, n_mtiles, dim / cw, st);
+  }
+  return launch_gemm<LD_XH, EP_LSTM>(a, n_mtiles, dim / cw, st);
 }
 
 int rvt_linear_f16(const void* av, int64_t m, int k, int n, const void* w_packed, const float* bias, int act, void* out,

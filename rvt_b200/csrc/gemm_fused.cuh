@@ -10,6 +10,9 @@
 //          LD_LN    : A = LayerNorm(x[token(row)]) (or x itself), tokens gathered through the
 //                     window / grid partition map  (maxvit.py:234,241,252-265,273-304)
 //          LD_CONV  : A = im2col of the strided downsample conv input (maxvit.py:166-175)
+//          LD_STEM  : the 7x7/stride-4 stem on uint8 NCHW events: a [Cin x 35 x 80] input patch of an 8x16-token
+//                     tile is staged in smem with cp.async (zero fill = conv + resolution padding) and the
+//                     A tiles are built smem -> smem (u8 -> fp16 by byte permutes)
 //          LD_XH    : A = cat(x, [dwconv3x3](h_prev)) for the Conv-LSTM 1x1 (rnn.py:50-55)
 //   epilogue EP_F16 : +bias, optional exact-erf GELU, fp16 store
 //            EP_RES : x[token] = res[token] + gamma * (acc + bias)   (LayerScale + residual,
@@ -26,9 +29,9 @@
 
 namespace rvt {
 
-enum { LD_F16 = 0, LD_LN = 1, LD_CONV = 2, LD_XH = 3, LD_TMA = 4 };
+enum { LD_F16 = 0, LD_LN = 1, LD_CONV = 2, LD_XH = 3, LD_TMA = 4, LD_STEM = 5 };
 enum { EP_F16 = 0, EP_RES = 1, EP_LN = 2, EP_LSTM = 3, EP_RAW = 4 };
-enum { MAP_IDENTITY = 0, MAP_WINDOW = 1, MAP_GRID = 2 };
+enum { MAP_IDENTITY = 0, MAP_WINDOW = 1, MAP_GRID = 2, MAP_BLOCK = 3 };
 
 // tile row -> token of a [B, H, W, C] channels-last tensor
 struct RowMap {
@@ -42,8 +45,20 @@ struct RowMap {
   int n_tokens;      // B*H*W
 };
 
+constexpr int kStemTileH = 8, kStemTileW = 16;          // MAP_BLOCK: a tile is 8 x 16 tokens (ny, nx = tiles per image)
+constexpr int kStemPatchRows = kStemTileH * 4 + 3;      // 35 input rows
+constexpr int kStemPatchPitch = 80;                     // bytes per patch row: pixels [4*ox0-16, 4*ox0+64)
+
 __device__ __forceinline__ int row_to_token(const RowMap& m, int row) {
   if (m.mode == MAP_IDENTITY) return row < m.n_tokens ? row : -1;
+  if (m.mode == MAP_BLOCK) {
+    const int tile = row >> 7, r = row & 127;
+    if (tile >= m.n_groups) return -1;
+    const int per_img = m.ny * m.nx;
+    const int b = tile / per_img, t = tile - b * per_img;
+    const int ty = t / m.nx, tx = t - ty * m.nx;
+    return (b * m.H + ty * kStemTileH + (r >> 4)) * m.W + tx * kStemTileW + (r & 15);
+  }
   const int g = row / m.rows_per_win, p = row - g * m.rows_per_win;
   if (p >= m.P || g >= m.n_groups) return -1;
   const int per_img = m.ny * m.nx;
@@ -88,9 +103,12 @@ constexpr uint32_t kATileBytes = 128 * 128;   // 128 rows x 64 fp16
 constexpr int kWorkers = 256;                 // 8 producer / epilogue warps
 constexpr int kGemmThreads = kWorkers + 64;   // + the MMA-issuing warp + the TMA producer warp (LD_TMA)
 
-__host__ __device__ inline size_t gemm_smem_bytes(int stages, int BN) {
+__host__ __device__ inline size_t gemm_smem_bytes(int stages, int BN, size_t extra = 0) {
   return 1024 /*align slack*/ + static_cast<size_t>(stages) * (kATileBytes + static_cast<size_t>(BN) * 128) +
-         2 * 128 * sizeof(float) + (2 * kMaxStages + 1) * sizeof(uint64_t) + 16;
+         2 * 128 * sizeof(float) + (2 * kMaxStages + 1) * sizeof(uint64_t) + 16 + extra;
+}
+__host__ __device__ inline size_t stem_patch_bytes(int cin) {
+  return (static_cast<size_t>(cin) * kStemPatchRows * kStemPatchPitch + 127) & ~static_cast<size_t>(127);
 }
 
 // Exact-erf GELU (F.gelu default, layers/activations.py:138-145) with erf from Abramowitz &
@@ -193,6 +211,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_fused_kernel(const __gri
   uint64_t* empty = full + kMaxStages;
   uint64_t* accum = empty + kMaxStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+  const uint32_t s_patch = (smem_u32(tmem_slot) + 16 + 127u) & ~127u;     // LD_STEM input patch (128-byte aligned)
 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&full[s], LOADER == LD_TMA ? 1 : kWorkers); mbar_init(&empty[s], 1); }
@@ -413,6 +432,70 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_fused_kernel(const __gri
       }
     };
 
+    if (LOADER == LD_STEM) {
+      // ---- stage the uint8 input patch of this 8 x 16-token tile ----
+      const int Cin = a.Cin, Hin = a.Hin, Win = a.Win;
+      const int per_img = a.map.ny * a.map.nx;
+      const int tb = mt / per_img, tt = mt - tb * per_img;
+      const int ty = tt / a.map.nx, tx = tt - ty * a.map.nx;
+      const int iy0 = ty * kStemTileH * 4 - 3;                 // first input row of the patch
+      const int px0 = tx * kStemTileW * 4 - 16;                // first (16-byte aligned) pixel of a patch row
+      const uint8_t* inb = reinterpret_cast<const uint8_t*>(a.cin);
+      const int n16 = Cin * kStemPatchRows * 5;
+      for (int idx = tid; idx < n16; idx += kWorkers) {
+        const int prow = idx / 5, c16 = idx - prow * 5;
+        const int ci = prow / kStemPatchRows, ry = prow - ci * kStemPatchRows;
+        const int iy = iy0 + ry, px = px0 + c16 * 16;
+        const bool ok = mt < a.map.n_groups && iy >= 0 && iy < Hin && px >= 0 && px + 16 <= Win;
+        const uint8_t* src = ok ? inb + ((static_cast<size_t>(tb) * Cin + ci) * Hin + iy) * Win + px : inb;
+        const uint32_t dst = s_patch + prow * kStemPatchPitch + c16 * 16;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      named_bar_sync(1, kWorkers);
+      // ---- K loop: k = (ky*Cin + ci)*8 + kx8, the 8 bytes [4*ox-4, 4*ox+4) of input row 4*oy-3+ky (kx8 = 0 has zero weight)
+      const int npairs = 7 * Cin;
+      for (int kc = 0; kc < KC; ++kc) {
+        const int s = kc % stages;
+        const uint32_t ph = (kc / stages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        if (tid == 0) {
+          mbar_expect_tx(&full[s], b_bytes);
+          bulk_g2s(sB + static_cast<size_t>(s) * b_bytes,
+                   a.Wp + (static_cast<size_t>(nt) * KC + kc) * static_cast<size_t>(BN) * 64, b_bytes, &full[s]);
+        }
+        const uint32_t tile = sA_addr + s * kATileBytes;
+        const int q = kc * 8 + j;                              // (ky, ci) pair of this thread's 16-byte chunk
+        const bool qv = q < npairs;
+        const int ky = qv ? q / Cin : 0, ci = qv ? q - ky * Cin : 0;
+        const uint32_t prow_base = s_patch + (ci * kStemPatchRows + ky) * kStemPatchPitch + 12;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = r0 + 32 * i;
+          uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+          if (qv) {
+            const uint32_t src = prow_base + (r >> 4) * (4 * kStemPatchPitch) + (r & 15) * 4;
+            uint32_t w0, w1;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w0) : "r"(src));
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w1) : "r"(src + 4));
+            // u8 -> fp16 exactly: bytes (b, 0x64) form the half 1024 + b; subtract 1024
+            const __half2 k1024 = __half2half2(__ushort_as_half(static_cast<unsigned short>(0x6400)));
+            uint32_t p0 = __byte_perm(w0, 0x64646464u, 0x4140), p1 = __byte_perm(w0, 0x64646464u, 0x4342);
+            uint32_t p2 = __byte_perm(w1, 0x64646464u, 0x4140), p3 = __byte_perm(w1, 0x64646464u, 0x4342);
+            const __half2 h0 = __hsub2(*reinterpret_cast<__half2*>(&p0), k1024);
+            const __half2 h1 = __hsub2(*reinterpret_cast<__half2*>(&p1), k1024);
+            const __half2 h2 = __hsub2(*reinterpret_cast<__half2*>(&p2), k1024);
+            const __half2 h3 = __hsub2(*reinterpret_cast<__half2*>(&p3), k1024);
+            o0 = *reinterpret_cast<const uint32_t*>(&h0); o1 = *reinterpret_cast<const uint32_t*>(&h1);
+            o2 = *reinterpret_cast<const uint32_t*>(&h2); o3 = *reinterpret_cast<const uint32_t*>(&h3);
+          }
+          st_smem_16B(tile + sw128_offset(r, j), o0, o1, o2, o3);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&full[s]);
+      }
+    } else {
     uint32_t raw_a[4][8], raw_b[4][8];
     fetch(0, raw_a);
     for (int kc = 0; kc < KC; ++kc) {
@@ -430,6 +513,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_fused_kernel(const __gri
       if (even) commit(kc, raw_a, tile); else commit(kc, raw_b, tile);
       fence_proxy_async_smem();
       mbar_arrive(&full[s]);
+    }
     }
    }  // LOADER != LD_TMA
 
@@ -725,6 +809,23 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* x, RowMap map
         *reinterpret_cast<float4*>(o + g * 128 + lane * 4) = t;
       }
   }
+}
+
+// [x | h_prev] fp32 -> fp16 [n_rows, 2C] operand matrix of the wide-stage Conv-LSTM 1x1 (rnn.py:52,55), cast once
+// instead of inside each of the 4C/BN N-tile CTAs.  One thread per 8 elements; rows beyond n_tokens are zero.
+__global__ void __launch_bounds__(256) cast_xh_kernel(const float* __restrict__ x, const float* __restrict__ h, int n_tokens,
+                                                      int n_rows, int C, __half* __restrict__ out) {
+  const int per_row = (2 * C) >> 3;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<int64_t>(n_rows) * per_row) return;
+  const int row = static_cast<int>(idx / per_row), k0 = static_cast<int>(idx - static_cast<int64_t>(row) * per_row) * 8;
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (row < n_tokens) {
+    if (k0 < C) load8(x + static_cast<size_t>(row) * C + k0, v);
+    else if (h != nullptr) load8(h + static_cast<size_t>(row) * C + (k0 - C), v);
+  }
+  *reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * 2 * C + k0) =
+      make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
 }
 
 // ----------------------------------------------------------------------------------------

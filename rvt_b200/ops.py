@@ -18,7 +18,7 @@ def downsample_cf2cl(x: torch.Tensor, x_is_nchw: bool, conv_w_packed: torch.Tens
                      stride: int, pad: int, ln_w: Optional[torch.Tensor], ln_b: Optional[torch.Tensor],
                      virtual_hw: Optional[Tuple[int, int]] = None, token_mask: Optional[torch.Tensor] = None,
                      mask_token: Optional[torch.Tensor] = None, eps: float = 1e-5,
-                     s2d_scratch: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     s2d_scratch: Optional[torch.Tensor] = None, stem_mode: int = 0) -> torch.Tensor:
     """ConvDownsampling_Cf2Cl.forward (maxvit.py:174-178) [+ mask token, maxvit_rnn.py:174-176].
     x: [B,Cin,H,W] (f32/u8/f16) if x_is_nchw else [B,H,W,Cin] f32.  -> f32 [B,Hout,Wout,cout]."""
     assert x.is_cuda and x.is_contiguous() and x.dtype in _IN_DTYPES
@@ -40,8 +40,17 @@ def downsample_cf2cl(x: torch.Tensor, x_is_nchw: bool, conv_w_packed: torch.Tens
     _lib.check(L.rvt_downsample_cf2cl(
         _lib.ptr(x), _IN_DTYPES[x.dtype], int(x_is_nchw), b, cin, hin, win, ksize, stride, pad, hout, wout, cout,
         _lib.ptr(conv_w_packed), _lib.ptr(ln_w), _lib.ptr(ln_b), eps, _lib.ptr(token_mask), _lib.ptr(mask_token),
-        _lib.ptr(out), _lib.ptr(s2d_scratch), _stream(x)), 'downsample_cf2cl')
+        _lib.ptr(out), _lib.ptr(s2d_scratch), stem_mode, _stream(x)), 'downsample_cf2cl')
     return out
+
+
+def stem_u8_ok(x: torch.Tensor, cin: int, ksize: int, stride: int, pad: int, virtual_hw, cout: int) -> bool:
+    """uint8 NCHW input + the default stem geometry -> smem-patch loader (no scratch tensor)."""
+    if x.dtype != torch.uint8 or x.data_ptr() % 16:
+        return False
+    vh, vw = virtual_hw
+    hout, wout = (vh + 2 * pad - ksize) // stride + 1, (vw + 2 * pad - ksize) // stride + 1
+    return bool(_lib.lib().rvt_stem_u8_ok(cin, ksize, stride, pad, x.shape[3], hout, wout, cout))
 
 
 def stem_uses_s2d(cin: int, factor: int, ksize: int, pad: int, virtual_w: int) -> bool:
@@ -92,7 +101,7 @@ def mlp_block_(x: torch.Tensor, blk: dict, scratch_hidden: torch.Tensor,
 
 
 def dws_conv_lstm(x: torch.Tensor, h_prev: Optional[torch.Tensor], c_prev: Optional[torch.Tensor], pk: dict,
-                  dws_ks: int) -> Tuple[torch.Tensor, torch.Tensor]:
+                  dws_ks: int, scratch_xh: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """DWSConvLSTM2d.forward (rnn.py:36-69) on channels-last tensors -> (h_t, c_t)."""
     assert x.is_cuda and x.is_contiguous() and x.dtype == torch.float32
     b, h, w, c = x.shape
@@ -103,5 +112,5 @@ def dws_conv_lstm(x: torch.Tensor, h_prev: Optional[torch.Tensor], c_prev: Optio
     _lib.check(L.rvt_dws_conv_lstm(
         _lib.ptr(x), _lib.ptr(h_prev), _lib.ptr(c_prev), b, h, w, c, _lib.ptr(pk['lstm_w']), _lib.ptr(pk['lstm_b']),
         _lib.ptr(pk['dw_w']), _lib.ptr(pk['dw_b']), pk['dws_mode'], dws_ks, _lib.ptr(h_new), _lib.ptr(c_new),
-        _stream(x)), 'dws_conv_lstm')
+        _lib.ptr(scratch_xh), _stream(x)), 'dws_conv_lstm')
     return h_new, c_new

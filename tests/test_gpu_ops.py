@@ -67,6 +67,12 @@ def test_each_operator_with_oracle_inputs(name):
                                             d.padding, pk['ds_ln_w'], pk['ds_ln_b'], token_mask=tm,
                                             mask_token=pk['mask_token'], s2d_scratch=s2d)
                 rec(step, pre + 'downsample(s2d,u8)', got2, taps[pre + 'downsample'])
+                cu8 = cur.to(torch.uint8)
+                if pk['conv_w_u8'] is not None and ops.stem_u8_ok(cu8, 20, d.kernel_size, d.factor, d.padding, cu8.shape[2:], st.dim):
+                    got3 = ops.downsample_cf2cl(cu8, True, pk['conv_w_u8'], st.dim, d.kernel_size, d.factor, d.padding,
+                                                pk['ds_ln_w'], pk['ds_ln_b'], token_mask=tm, mask_token=pk['mask_token'],
+                                                stem_mode=2)
+                    rec(step, pre + 'downsample(u8 smem patch)', got3, taps[pre + 'downsample'])
             xin = taps[pre + 'downsample']
             b, hh, ww, c = xin.shape
             for bi, blk in enumerate(pk['blocks']):
@@ -86,7 +92,8 @@ def test_each_operator_with_oracle_inputs(name):
             hp = cp = None
             if prev is not None and prev[s] is not None:
                 hp, cp = (t.permute(0, 2, 3, 1).contiguous().to(dev) for t in prev[s])
-            hg, cg = ops.dws_conv_lstm(taps[pre + 'pre_lstm'].to(dev).contiguous(), hp, cp, pk, st.lstm.ks)
+            sxh = torch.empty(((b * hh * ww + 127) // 128) * 128 * 2 * c, dtype=torch.float16, device=dev)
+            hg, cg = ops.dws_conv_lstm(taps[pre + 'pre_lstm'].to(dev).contiguous(), hp, cp, pk, st.lstm.ks, sxh)
             rec(step, pre + 'lstm.h', hg, o_states[s][0].permute(0, 2, 3, 1))
             rec(step, pre + 'lstm.c', cg, o_states[s][1].permute(0, 2, 3, 1))
             cur, cur_nchw = o_states[s][0].permute(0, 2, 3, 1).contiguous().to(dev), False
