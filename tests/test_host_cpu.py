@@ -48,6 +48,25 @@ def test_library_exports_every_declared_symbol(built_lib):
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
 
 
+def test_ctypes_signatures_match_header(built_lib):
+    """Arity and scalar/pointer kind of every ctypes binding equal the C prototype in include/rvt_b200.h."""
+    from rvt_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'rvt_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    protos = re.findall(r'\b([a-z_0-9]+\s*\**)\s*\b(rvt_[a-z0-9_]+)\s*\(([^)]*)\)\s*;', hdr)
+    assert len(protos) == len(_lib.SIGNATURES)
+    for _ret, name, args in protos:
+        params = [a.strip() for a in args.split(',')] if args.strip() != 'void' else []
+        _res, argtypes = _lib.SIGNATURES[name]
+        assert len(params) == len(argtypes), (name, len(params), len(argtypes))
+        for prm, at in zip(params, argtypes):
+            is_ptr = '*' in prm
+            assert is_ptr == (at is ctypes.c_void_p), (name, prm, at)
+            if not is_ptr:
+                want = ctypes.c_float if prm.startswith('float') else ctypes.c_int64 if prm.startswith('int64_t') else ctypes.c_int
+                assert at is want, (name, prm, at)
+
+
 def test_tiling_helpers(built_lib):
     from rvt_b200 import _lib
     L = _lib.lib()
