@@ -44,6 +44,7 @@ __host__ __device__ inline size_t attn_fused_smem_bytes(int C) {
          2 * 128 * sizeof(float) + 256;
 }
 
+template <int KC1>   // K atoms of the C-wide operand: 1 (C <= 64) or 2 (C <= 128); sizes the register-resident x rows
 __global__ void __launch_bounds__(kAfThreads, 2) attn_fused_kernel(const __grid_constant__ AttnFusedArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(kAfThreads, 2) attn_fused_kernel(const __grid_
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int mt = blockIdx.x;
-  const int C = a.C, KC1 = (C + 63) / 64, nh = a.nh, dh = a.dh;
+  const int C = a.C, nh = a.nh, dh = a.dh;
   const uint32_t wq_bytes = static_cast<uint32_t>(KC1) * kAfQkvN * 128;
   const uint32_t wp_bytes = static_cast<uint32_t>(KC1) * C * 128;
 
@@ -78,6 +79,25 @@ __global__ void __launch_bounds__(kAfThreads, 2) attn_fused_kernel(const __grid_
   uint64_t* out_full = bars + 10;    // commit
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
+  // x-tile gather issued before barrier init / TMEM allocation / CTA sync (setup overlaps the load latency)
+  const int j8 = tid & 7, r0 = tid >> 3;
+  int tok[4] = {-1, -1, -1, -1};
+  float keep[KC1][4][8];
+  if (warp < 8) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tok[i] = row_to_token(a.map, mt * 128 + r0 + 32 * i);
+#pragma unroll
+    for (int kc = 0; kc < KC1; ++kc) {
+      const int k0 = kc * 64 + j8 * 8;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) keep[kc][i][e] = 0.f;
+        if (tok[i] >= 0 && k0 < C) load8(a.x + static_cast<size_t>(tok[i]) * C + k0, keep[kc][i]);
+      }
+    }
+  }
+
   if (tid == 0) {
     mbar_init(bar_a, kWorkers); mbar_init(wq_full, 1); mbar_init(wq_empty, 1); mbar_init(wp_full, 1);
     mbar_init(qkv_full, 1); mbar_init(qkv_smem, kWorkers); mbar_init(s_full, 1); mbar_init(p_full, kWorkers);
@@ -96,36 +116,24 @@ __global__ void __launch_bounds__(kAfThreads, 2) attn_fused_kernel(const __grid_
   const int nkeys = rpw == 64 ? 128 : nk_w;              // MMA N of S / K of PV
 
   if (warp < 8) {
-    const int j8 = tid & 7, r0 = tid >> 3;
     // zero the P operand once: blocks outside a row's own window stay zero for every head
     for (int i = tid; i < 2 * static_cast<int>(kATileBytes) / 16; i += kWorkers) st_smem_16B(sP + i * 16, 0u, 0u, 0u, 0u);
 
     // ======================= gather + LN1 -> A operand =======================
     {
-      int tok[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) tok[i] = row_to_token(a.map, mt * 128 + r0 + 32 * i);
-      float keep[2][4][8];
       float mean[4] = {0.f, 0.f, 0.f, 0.f}, rstd[4] = {1.f, 1.f, 1.f, 1.f}, s1[4] = {0.f, 0.f, 0.f, 0.f},
             s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int kc = 0; kc < 2; ++kc) {
-        if (kc >= KC1) break;
-        const int k0 = kc * 64 + j8 * 8;
+      for (int kc = 0; kc < KC1; ++kc)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (tok[i] >= 0 && k0 < C) load8(a.x + static_cast<size_t>(tok[i]) * C + k0, v);
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int e = 0; e < 8; ++e) { s1[i] += v[e]; keep[kc][i][e] = v[e]; }
-        }
-      }
+          for (int e = 0; e < 8; ++e) s1[i] += keep[kc][i][e];
       if (a.do_ln) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) mean[i] = red8(s1[i]) / C;
 #pragma unroll
-        for (int kc = 0; kc < 2; ++kc) {
-          if (kc >= KC1) break;
+        for (int kc = 0; kc < KC1; ++kc) {
           if (kc * 64 + j8 * 8 < C) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -137,8 +145,7 @@ __global__ void __launch_bounds__(kAfThreads, 2) attn_fused_kernel(const __grid_
         for (int i = 0; i < 4; ++i) rstd[i] = rsqrtf(red8(s2[i]) / C + a.eps);
       }
 #pragma unroll
-      for (int kc = 0; kc < 2; ++kc) {
-        if (kc >= KC1) break;
+      for (int kc = 0; kc < KC1; ++kc) {
         const int k0 = kc * 64 + j8 * 8;
         const bool kv = k0 < C;
         float g[8], bb[8];
@@ -284,13 +291,23 @@ __global__ void __launch_bounds__(kAfThreads, 2) attn_fused_kernel(const __grid_
     mbar_arrive(so_full);
 
     // ======================= proj epilogue: residual + scatter =======================
-    mbar_wait(out_full, 0);
-    tc_fence_after();
+    // residual rows prefetched before the proj accumulator barrier
     const int etok = row_to_token(a.map, mt * 128 + erow);
     const int ocols = (C + 15) & ~15;
     const int csplit = ((ocols / 16 + 1) / 2) * 16;
     const int cbeg = hsel ? csplit : 0, cend = hsel ? ocols : csplit;
-    for (int c0 = cbeg; c0 < cend; c0 += 16) {
+    float res[64];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int c0 = cbeg + g * 16;
+      if (c0 < cend && etok >= 0) load16(a.x + static_cast<size_t>(etok) * C + c0, res + g * 16);
+    }
+    mbar_wait(out_full, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int c0 = cbeg + g * 16;
+      if (c0 >= cend) break;
       float v[16];
       tmem_ld_x16(t_out + lane_off + c0, v);
       tmem_ld_wait();
@@ -308,11 +325,10 @@ __global__ void __launch_bounds__(kAfThreads, 2) attn_fused_kernel(const __grid_
           for (int e = 0; e < 16; ++e) v[e] *= bv[e];
         }
 #pragma unroll
-        for (int qd = 0; qd < 4; ++qd) {
-          const float4 r = *reinterpret_cast<const float4*>(xp + qd * 4);
+        for (int qd = 0; qd < 4; ++qd)
           *reinterpret_cast<float4*>(xp + qd * 4) =
-              make_float4(r.x + v[qd * 4], r.y + v[qd * 4 + 1], r.z + v[qd * 4 + 2], r.w + v[qd * 4 + 3]);
-        }
+              make_float4(res[g * 16 + qd * 4] + v[qd * 4], res[g * 16 + qd * 4 + 1] + v[qd * 4 + 1],
+                          res[g * 16 + qd * 4 + 2] + v[qd * 4 + 2], res[g * 16 + qd * 4 + 3] + v[qd * 4 + 3]);
       }
     }
   } else if (warp == 8) {

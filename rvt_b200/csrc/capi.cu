@@ -303,12 +303,15 @@ int rvt_partition_attention(float* x, int batch, int height, int width, int dim,
     if (smem > static_cast<size_t>(kMaxSmem)) return kErrUnsupported;
     static bool attr_set = false;
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+      cudaError_t e = cudaFuncSetAttribute(attn_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
       if (e != cudaSuccess) return static_cast<int>(e);
-      cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(attn_fused_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(attn_fused_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       attr_set = true;
     }
-    attn_fused_kernel<<<n_mtiles, kAfThreads, smem, st>>>(fa);
+    if (dim <= 64) attn_fused_kernel<1><<<n_mtiles, kAfThreads, smem, st>>>(fa);
+    else attn_fused_kernel<2><<<n_mtiles, kAfThreads, smem, st>>>(fa);
     return static_cast<int>(cudaGetLastError());
   }
 
@@ -383,13 +386,16 @@ int rvt_mlp_block(float* x, int64_t n_tokens, int dim, int hidden, const float* 
     if (smem > static_cast<size_t>(kMaxSmem)) return kErrUnsupported;
     static bool attr_set = false;
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+      cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
       if (e != cudaSuccess) return static_cast<int>(e);
-      cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(mlp_fused_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(mlp_fused_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       attr_set = true;
     }
     if (n_mtiles <= 0) return 0;
-    mlp_fused_kernel<<<n_mtiles, kMlpThreads, smem, st>>>(ma);
+    if (dim <= 64) mlp_fused_kernel<1><<<n_mtiles, kMlpThreads, smem, st>>>(ma);
+    else mlp_fused_kernel<2><<<n_mtiles, kMlpThreads, smem, st>>>(ma);
     return static_cast<int>(cudaGetLastError());
   }
   RowMap m = identity_map(n_tokens, 1, static_cast<int>(n_tokens));

@@ -518,13 +518,27 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_fused_kernel(const __gri
    }  // LOADER != LD_TMA
 
     // =========================== epilogue ===========================
-    mbar_wait(accum, 0);
-    tc_fence_after();
     const int q = warp & 3, hsel = warp >> 2;
     const int erow = q * 32 + lane;                 // accumulator row == TMEM lane
     const int row = mt * 128 + erow;
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const int etok = (EPI == EP_F16) ? row : row_to_token(a.map, row);
+    // EP_LSTM: this thread's c_{t-1} values are fetched before the accumulator barrier (latency hides behind the MMAs)
+    float cpre[32];
+    if (EPI == EP_LSTM) {
+      const int cw = a.cw;
+      const int jsplit = ((cw / 16 + 1) / 2) * 16;
+      const int jbeg = hsel ? jsplit : 0, jend = hsel ? cw : jsplit;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int j0 = jbeg + g * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) cpre[g * 8 + e] = 0.f;
+        if (j0 < jend && etok >= 0 && a.cprev) load8(a.cprev + static_cast<size_t>(etok) * a.C + nt * cw + j0, cpre + g * 8);
+      }
+    }
+    mbar_wait(accum, 0);
+    tc_fence_after();
     const int csplit = ((BN / 16 + 1) / 2) * 16;
     const int cbeg = hsel ? csplit : 0, cend = hsel ? BN : csplit;
 
@@ -643,7 +657,10 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_fused_kernel(const __gri
       const int cw = a.cw, C = a.C;
       const int jsplit = ((cw / 16 + 1) / 2) * 16;
       const int jbeg = hsel ? jsplit : 0, jend = hsel ? cw : jsplit;
-      for (int j0 = jbeg; j0 < jend; j0 += 8) {
+#pragma unroll
+      for (int gi = 0; gi < 4; ++gi) {
+        const int j0 = jbeg + gi * 8;
+        if (j0 >= jend) break;
         float f[8], ig[8], og[8], g[8];
         tmem_ld_x8(trow + j0, f);
         tmem_ld_x8(trow + cw + j0, ig);
@@ -669,8 +686,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_fused_kernel(const __gri
 #pragma unroll
             for (int e = 0; e < 8; ++e) g[e] += bv[e];
           }
-          float cpv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (a.cprev) load8(a.cprev + off, cpv);
+          const float* cpv = cpre + gi * 8;
           float hn[8], cn[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {

@@ -40,6 +40,7 @@ __host__ __device__ inline size_t mlp_smem_bytes(int C, int stages) {
   return 1024 + static_cast<size_t>(mlp_kc1(C)) * kATileBytes + stages * mlp_stage_bytes(C) + 2 * kATileBytes + 256;
 }
 
+template <int KC1>   // K atoms of the C-wide operand: 1 (C <= 64) or 2 (C <= 128); sizes the register-resident x rows
 __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fused_kernel(const __grid_constant__ MlpArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -48,7 +49,7 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fused_kernel(const __grid_
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int mt = blockIdx.x;
-  const int C = a.C, KC1 = mlp_kc1(C), S = a.stages;
+  const int C = a.C, S = a.stages;
   const int n_chunks = a.hidden / kMlpHC;
   const uint32_t w1_bytes = static_cast<uint32_t>(KC1) * kMlpHC * 128;
   const uint32_t w2_bytes = static_cast<uint32_t>(C) * 128;
@@ -71,6 +72,30 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fused_kernel(const __grid_
   const uint32_t out_cols = static_cast<uint32_t>((C + 15) & ~15);
   const uint32_t tmem_cols = tmem_cols_pow2(out_cols + 2 * kMlpHC);
 
+  // The x-tile loads of the LayerNorm prologue are issued before barrier init / TMEM allocation / the CTA
+  // sync, so the ~1 us of setup overlaps the ~1 us global-load latency.
+  const int j8 = tid & 7, r0 = tid >> 3;
+  int tok[4] = {-1, -1, -1, -1};
+  float keep[KC1][4][8];         // the tile's x rows stay in registers between the LN passes
+  float s1[4] = {0.f, 0.f, 0.f, 0.f};
+  if (warp < 8) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = mt * 128 + r0 + 32 * i;
+      tok[i] = row < a.n_tokens ? row : -1;
+    }
+#pragma unroll
+    for (int kc = 0; kc < KC1; ++kc) {             // loads only: no use of the values before the CTA sync
+      const int k0 = kc * 64 + j8 * 8;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) keep[kc][i][e] = 0.f;
+        if (tok[i] >= 0 && k0 < C) load8(a.x + static_cast<size_t>(tok[i]) * C + k0, keep[kc][i]);
+      }
+    }
+  }
+
   if (tid == 0) {
     mbar_init(bar_a, kWorkers);
     for (int s = 0; s < S; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
@@ -87,56 +112,30 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fused_kernel(const __grid_
 
   if (warp < 8) {
     // ======================= LN2 -> A operand =======================
-    const int j8 = tid & 7, r0 = tid >> 3;
-    int tok[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int row = mt * 128 + r0 + 32 * i;
-      tok[i] = row < a.n_tokens ? row : -1;
-    }
     {
-      float keep[2][4][8];           // KC1 <= 2 rows stay in registers; wider rows are re-read
-      float mean[4], rstd[4], s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+      float mean[4], rstd[4], s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int kc = 0; kc < 4; ++kc) {
-        if (kc >= KC1) break;
-        const int k0 = kc * 64 + j8 * 8;
+      for (int kc = 0; kc < KC1; ++kc)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (tok[i] >= 0 && k0 < C) load8(a.x + static_cast<size_t>(tok[i]) * C + k0, v);
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int e = 0; e < 8; ++e) { s1[i] += v[e]; if (kc < 2) keep[kc & 1][i][e] = v[e]; }
-        }
-      }
+          for (int e = 0; e < 8; ++e) s1[i] += keep[kc][i][e];
 #pragma unroll
       for (int i = 0; i < 4; ++i) mean[i] = red8(s1[i]) / C;
 #pragma unroll
-      for (int kc = 0; kc < 4; ++kc) {
-        if (kc >= KC1) break;
+      for (int kc = 0; kc < KC1; ++kc) {
         const int k0 = kc * 64 + j8 * 8;
+        if (k0 < C) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float v[8];
-          if (kc < 2) {
+          for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = keep[kc & 1][i][e];
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = mean[i];
-            if (tok[i] >= 0 && k0 < C) load8(a.x + static_cast<size_t>(tok[i]) * C + k0, v);
-          }
-          if (k0 < C) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) { const float d = v[e] - mean[i]; s2[i] += d * d; }
-          }
+            for (int e = 0; e < 8; ++e) { const float d = keep[kc][i][e] - mean[i]; s2[i] += d * d; }
         }
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) rstd[i] = rsqrtf(red8(s2[i]) / C + a.eps);
 #pragma unroll
-      for (int kc = 0; kc < 4; ++kc) {
-        if (kc >= KC1) break;
+      for (int kc = 0; kc < KC1; ++kc) {
         const int k0 = kc * 64 + j8 * 8;
         const bool kv = k0 < C;
         float g[8], bb[8];
@@ -145,14 +144,8 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fused_kernel(const __grid_
         for (int i = 0; i < 4; ++i) {
           float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
           if (tok[i] >= 0 && kv) {
-            if (kc < 2) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = keep[kc & 1][i][e];
-            } else {
-              load8(a.x + static_cast<size_t>(tok[i]) * C + k0, v);
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = (v[e] - mean[i]) * rstd[i] * g[e] + bb[e];
+            for (int e = 0; e < 8; ++e) v[e] = (keep[kc][i][e] - mean[i]) * rstd[i] * g[e] + bb[e];
           }
           st_smem_16B(sA + kc * kATileBytes + sw128_offset(r0 + 32 * i, j8), pack_h2(v[0], v[1]), pack_h2(v[2], v[3]),
                       pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
@@ -195,16 +188,27 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fused_kernel(const __grid_
     }
 
     // ======================= output epilogue =======================
-    mbar_wait(out_full, 0);
-    tc_fence_after();
+    // the residual rows are fetched BEFORE waiting on the last fc2, so their latency hides behind the MMAs
     const int row = mt * 128 + erow;
     const int csplit = ((static_cast<int>(out_cols) / 16 + 1) / 2) * 16;
     const int cbeg = hsel ? csplit : 0, cend = hsel ? static_cast<int>(out_cols) : csplit;
-    for (int c0 = cbeg; c0 < cend; c0 += 16) {
+    float res[64];                                   // <= 64 columns per thread (C <= 128)
+    const bool live = row < a.n_tokens;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int c0 = cbeg + g * 16;
+      if (c0 < cend && live) load16(a.x + static_cast<size_t>(row) * C + c0, res + g * 16);
+    }
+    mbar_wait(out_full, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int c0 = cbeg + g * 16;
+      if (c0 >= cend) break;
       float v[16];
       tmem_ld_x16(t_out + lane_off + c0, v);
       tmem_ld_wait();
-      if (row < a.n_tokens) {
+      if (live) {
         float* xp = a.x + static_cast<size_t>(row) * C + c0;
         float bv[16];
         load16(a.b2 + c0, bv);
@@ -216,11 +220,10 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fused_kernel(const __grid_
           for (int e = 0; e < 16; ++e) v[e] *= bv[e];
         }
 #pragma unroll
-        for (int qd = 0; qd < 4; ++qd) {
-          const float4 r = *reinterpret_cast<const float4*>(xp + qd * 4);
+        for (int qd = 0; qd < 4; ++qd)
           *reinterpret_cast<float4*>(xp + qd * 4) =
-              make_float4(r.x + v[qd * 4], r.y + v[qd * 4 + 1], r.z + v[qd * 4 + 2], r.w + v[qd * 4 + 3]);
-        }
+              make_float4(res[g * 16 + qd * 4] + v[qd * 4], res[g * 16 + qd * 4 + 1] + v[qd * 4 + 1],
+                          res[g * 16 + qd * 4 + 2] + v[qd * 4 + 2], res[g * 16 + qd * 4 + 3] + v[qd * 4 + 3]);
       }
     }
   } else if (warp == 8) {
