@@ -55,8 +55,7 @@ int rvt_stacked_histogram(const int64_t* x, const int64_t* y, const int64_t* pol
 
 /* ---- a3: ConvDownsampling_Cf2Cl.forward  (models/layers/maxvit/maxvit.py:143-178) -------
  * Strided conv (no bias) + LayerNorm(C_out) [+ mask token, maxvit_rnn.py:174-176].
- * in: in_nchw ? [B,Cin,Hin,Win] : [B,Hin,Win,Cin]; in_dtype 0=f32 1=u8 2=f16 (u8/f16 only
- * with in_nchw).  Rows/cols of the virtual input beyond (Hin,Win) read as zero, which folds
+ * in: in_nchw ? [B,Cin,Hin,Win] : [B,Hin,Win,Cin]; in_dtype 0=f32 1=u8 2=f16 (u8 only with in_nchw).  Rows/cols of the virtual input beyond (Hin,Win) read as zero, which folds
  * the harness' zero padding (utils/padding.py:29-44) into the conv.  out: f32 [B,Hout,Wout,Cout].
  * w_packed: rvt_b200.packing.pack_conv_weight().  ln_w/ln_b may be NULL (norm_affine=False).
  * token_mask: u8 [B,Hout,Wout] or NULL; mask_token: f32 [Cout].
@@ -98,11 +97,12 @@ int rvt_mlp_block(float* x, int64_t n_tokens, int dim, int hidden, const float* 
  * dws_mode 0: no depthwise conv; 1: depthwise ks x ks (+bias) on h_prev only; 2: on cat(x,h).
  * dw_w: f32 [ks*ks][D] (tap-major), dw_b: f32 [D], D = C (mode 1) or 2C (mode 2).
  * w_packed / bias_tiled: rvt_b200.packing.pack_lstm_weight() (gate-interleaved tiles).
- * scratch_xh: optional f16 [round_up(B*H*W,128), 2C] workspace (used when dim >= 256 and dws_mode == 0). */
+ * scratch_xh: optional f16 [round_up(B*H*W,128), 2C] workspace (used when dim >= 256 and dws_mode == 0).
+ * h_out_f16: optional f16 [B,H,W,C] second copy of h_t (feeds the next stage's rvt_downsample_cf2cl, in_dtype 2). */
 int rvt_dws_conv_lstm(const float* x, const float* h_prev, const float* c_prev, int batch, int height,
                       int width, int dim, const void* w_packed, const float* bias_tiled, const float* dw_w,
                       const float* dw_b, int dws_mode, int dws_ks, float* h_out, float* c_out, void* scratch_xh,
-                      void* stream);
+                      void* h_out_f16, void* stream);
 
 /* ---- building block exposed for tests: D = A W^T + b, f16 in / f16 out ------------------
  * a: f16 [m, k] row-major (k % 8 == 0), w_packed: pack_linear_weight(W[n,k]), out: f16

@@ -27,7 +27,7 @@ SIGNATURES = {
     'rvt_partition_attention': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp,
                                       _vp, _vp, _vp, _vp, _vp]),
     'rvt_mlp_block': (_i, [_vp, _i64, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    'rvt_dws_conv_lstm': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    'rvt_dws_conv_lstm': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     'rvt_linear_f16': (_i, [_vp, _i64, _i, _i, _vp, _vp, _i, _vp, _vp]),
 }
 

@@ -345,12 +345,12 @@ class RNNDetector(nn.Module):
         output: Dict[int, torch.Tensor] = {}
         cur, cur_nchw = x, True
         for s in range(self.num_stages):
-            h_new, c_new = self._stage_step(s, packed[s], cur, cur_nchw, prev_states[s],
-                                            token_mask if s == 0 else None)
+            h_new, c_new, h16 = self._stage_step(s, packed[s], cur, cur_nchw, prev_states[s],
+                                                 token_mask if s == 0 else None)
             h_nchw, c_nchw = h_new.permute(0, 3, 1, 2), c_new.permute(0, 3, 1, 2)
             states.append((h_nchw, c_nchw))
             output[s + 1] = h_nchw
-            cur, cur_nchw = h_new, False
+            cur, cur_nchw = (h16 if h16 is not None else h_new), False
         return output, states
 
     def _prep_input(self, x: torch.Tensor) -> torch.Tensor:
@@ -362,7 +362,7 @@ class RNNDetector(nn.Module):
         return x.contiguous()
 
     def _stage_step(self, s: int, pk: dict, cur: torch.Tensor, cur_nchw: bool, prev_state: LstmState,
-                    token_mask: Optional[torch.Tensor]):
+                    token_mask: Optional[torch.Tensor], want_h16: bool = True):
         """One RNNDetectorStage.forward (maxvit_rnn.py:169-182) enqueued on the CURRENT stream:
         downsample(+LN) -> [window block, grid block] x num_blocks -> Conv-LSTM.  Scratch buffers are
         per stage, so different stages may run concurrently on different streams."""
@@ -412,7 +412,10 @@ class RNNDetector(nn.Module):
         sxh = None
         if c >= 256 and pk['dws_mode'] == 0:
             sxh = self._scratch_buf(f'xh{s}', ((n_tok + 127) // 128) * 128 * 2 * c, torch.float16, dev)
-        return ops.dws_conv_lstm(xs, hp, cp, pk, st.lstm.ks, sxh)
+        # fp16 copy of h_t for the next stage's im2col loader (half the bytes, no conversion)
+        h16 = torch.empty(xs.shape, dtype=torch.float16, device=dev) if (want_h16 and s + 1 < self.num_stages) else None
+        h_new, c_new = ops.dws_conv_lstm(xs, hp, cp, pk, st.lstm.ks, sxh, h16)
+        return h_new, c_new, h16
 
     @torch.no_grad()
     def forward_sequence(self, xs, prev_states: Optional[LstmStates] = None, token_masks=None,
@@ -465,7 +468,7 @@ class RNNDetector(nn.Module):
                         streams[s].wait_event(done[s - 1][t])
                     cur, nchw = (x_t, True) if s == 0 else (feats_prev[t], False)
                     tm = token_masks[t] if (token_masks is not None and s == 0) else None
-                    h_new, c_new = self._stage_step(s, packed[s], cur, nchw, state[s], tm)
+                    h_new, c_new, h16 = self._stage_step(s, packed[s], cur, nchw, state[s], tm)
                     if wavefront or s == n - 1:
                         ev = torch.cuda.Event()
                         ev.record(streams[s])
@@ -473,10 +476,10 @@ class RNNDetector(nn.Module):
                     if wavefront and not capturing:
                         # eager mode: tell the caching allocator about the cross-stream consumers
                         if s + 1 < n:
-                            h_new.record_stream(streams[s + 1])
+                            (h16 if h16 is not None else h_new).record_stream(streams[s + 1])
                         h_new.record_stream(main)
                         c_new.record_stream(main)
-                    feats_prev[t] = h_new
+                    feats_prev[t] = h16 if h16 is not None else h_new
                     state[s] = (h_new.permute(0, 3, 1, 2), c_new.permute(0, 3, 1, 2))
                     outs[t][s + 1] = state[s][0]
         self.last_step_events = done[n - 1]

@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(kAfThreads, 2) attn_fused_kernel(const __grid_
         for (int e = 0; e < 16; ++e) {
           float p = 0.f;
           if (k0 + e < P) p = ex2_approx((v[e] - mx) * a.scale_log2e);
-          sum += __half2float(__float2half_rn(p));     // normalise by what the tensor core will see
+          sum += p;
           v[e] = p;
         }
         const int key = key_lo + k0;

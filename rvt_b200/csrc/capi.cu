@@ -163,7 +163,7 @@ int rvt_stem_u8_ok(int cin, int ksize, int stride, int pad, int win, int hout, i
           cout <= 128 && cin >= 1) ? 1 : 0;
 }
 
-int rvt_conv_tile_n(int cout) { return (cout >= kWideDim && cout % 128 == 0) ? 64 : cout; }
+int rvt_conv_tile_n(int cout) { return (cout >= kWideDim && cout % 128 == 0) ? 128 : cout; }
 
 int rvt_lstm_cw(int dim) {
   for (int cw = 64; cw >= 16; cw -= 16)
@@ -212,7 +212,7 @@ int rvt_downsample_cf2cl(const void* in, int in_dtype, int in_nchw, int batch, i
                          const float* ln_b, float eps, const uint8_t* token_mask, const float* mask_token,
                          float* out, void* s2d_scratch, int stem_mode, void* stream) {
   if (!in || !w_packed || !out || batch < 1 || cout % 16 != 0 || cout > 512) return kErrBadArg;
-  if (!in_nchw && (in_dtype == 1 || cin % 8 != 0)) return kErrUnsupported;
+  if (!in_nchw && (in_dtype == 1 || cin % 8 != 0)) return kErrUnsupported;   // channels-last: f32 or f16
   if ((ln_w == nullptr) != (ln_b == nullptr)) return kErrBadArg;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   GemmArgs a{};
@@ -429,7 +429,7 @@ int rvt_mlp_block(float* x, int64_t n_tokens, int dim, int hidden, const float* 
 
 int rvt_dws_conv_lstm(const float* x, const float* h_prev, const float* c_prev, int batch, int height, int width,
                       int dim, const void* w_packed, const float* bias_tiled, const float* dw_w, const float* dw_b,
-                      int dws_mode, int dws_ks, float* h_out, float* c_out, void* scratch_xh, void* stream) {
+                      int dws_mode, int dws_ks, float* h_out, float* c_out, void* scratch_xh, void* h_out_f16, void* stream) {
   if (!x || !w_packed || !bias_tiled || !h_out || !c_out) return kErrBadArg;
   if (dim % 16 != 0 || dws_mode < 0 || dws_mode > 2) return kErrUnsupported;
   if (dws_mode != 0 && (!dw_w || !dw_b || dws_ks % 2 == 0)) return kErrBadArg;
@@ -441,7 +441,7 @@ int rvt_dws_conv_lstm(const float* x, const float* h_prev, const float* c_prev, 
   a.Wp = static_cast<const __half*>(w_packed); a.bias = bias_tiled;
   a.map = identity_map(n_tok, height, width);
   a.x = x; a.C = dim; a.hprev = h_prev; a.dw_w = dw_w; a.dw_b = dw_b; a.dws_mode = dws_mode; a.dws_ks = dws_ks;
-  a.cprev = c_prev; a.hout = h_out; a.cout = c_out; a.cw = cw;
+  a.cprev = c_prev; a.hout = h_out; a.cout = c_out; a.cw = cw; a.hout16 = static_cast<__half*>(h_out_f16);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int n_mtiles = cdiv(n_tok, 128);
   if (dws_mode == 0 && dim >= kWideDim && scratch_xh != nullptr) {

@@ -95,6 +95,7 @@ struct GemmArgs {
   const uint8_t* token_mask; const float* mask_token;
   // EP_LSTM
   const float* cprev; float* hout; float* cout; int cw;
+  __half* hout16;      // optional fp16 copy of h_t (operand of the next stage's downsample conv)
 };
 
 constexpr int kMaxStages = 6;
@@ -697,6 +698,9 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_fused_kernel(const __gri
           *reinterpret_cast<float4*>(a.cout + off + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
           *reinterpret_cast<float4*>(a.hout + off) = make_float4(hn[0], hn[1], hn[2], hn[3]);
           *reinterpret_cast<float4*>(a.hout + off + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+          if (a.hout16)
+            *reinterpret_cast<uint4*>(a.hout16 + off) =
+                make_uint4(pack_h2(hn[0], hn[1]), pack_h2(hn[2], hn[3]), pack_h2(hn[4], hn[5]), pack_h2(hn[6], hn[7]));
         }
       }
     }

@@ -7,7 +7,7 @@ import torch
 
 from . import _lib
 
-_IN_DTYPES = {torch.float32: 0, torch.uint8: 1, torch.float16: 2}
+_IN_DTYPES = {torch.float32: 0, torch.uint8: 1, torch.float16: 2}   # channels-last inputs: f32 or f16
 
 
 def _stream(t: torch.Tensor):
@@ -101,7 +101,8 @@ def mlp_block_(x: torch.Tensor, blk: dict, scratch_hidden: torch.Tensor,
 
 
 def dws_conv_lstm(x: torch.Tensor, h_prev: Optional[torch.Tensor], c_prev: Optional[torch.Tensor], pk: dict,
-                  dws_ks: int, scratch_xh: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                  dws_ks: int, scratch_xh: Optional[torch.Tensor] = None,
+                  h16_out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """DWSConvLSTM2d.forward (rnn.py:36-69) on channels-last tensors -> (h_t, c_t)."""
     assert x.is_cuda and x.is_contiguous() and x.dtype == torch.float32
     b, h, w, c = x.shape
@@ -112,5 +113,5 @@ def dws_conv_lstm(x: torch.Tensor, h_prev: Optional[torch.Tensor], c_prev: Optio
     _lib.check(L.rvt_dws_conv_lstm(
         _lib.ptr(x), _lib.ptr(h_prev), _lib.ptr(c_prev), b, h, w, c, _lib.ptr(pk['lstm_w']), _lib.ptr(pk['lstm_b']),
         _lib.ptr(pk['dw_w']), _lib.ptr(pk['dw_b']), pk['dws_mode'], dws_ks, _lib.ptr(h_new), _lib.ptr(c_new),
-        _lib.ptr(scratch_xh), _stream(x)), 'dws_conv_lstm')
+        _lib.ptr(scratch_xh), _lib.ptr(h16_out), _stream(x)), 'dws_conv_lstm')
     return h_new, c_new

@@ -61,6 +61,10 @@ def test_each_operator_with_oracle_inputs(name):
             got = ops.downsample_cf2cl(cur, cur_nchw, pk['conv_w'], st.dim, d.kernel_size, d.factor, d.padding,
                                        pk['ds_ln_w'], pk['ds_ln_b'], token_mask=tm, mask_token=pk['mask_token'])
             rec(step, pre + 'downsample', got, taps[pre + 'downsample'])
+            if s > 0:       # fp16 channels-last input (the LSTM's fp16 copy of h feeds the next stage's conv)
+                got16 = ops.downsample_cf2cl(cur.half(), False, pk['conv_w'], st.dim, d.kernel_size, d.factor, d.padding,
+                                             pk['ds_ln_w'], pk['ds_ln_b'])
+                rec(step, pre + 'downsample(f16 in)', got16, taps[pre + 'downsample'])
             if s == 0:      # stem fast path (space-to-depth) and uint8 input must agree with the generic gather path
                 s2d = torch.empty(cur.numel(), dtype=torch.float16, device=dev)
                 got2 = ops.downsample_cf2cl(cur.to(torch.uint8), True, pk['conv_w_s2d'], st.dim, d.kernel_size, d.factor,
