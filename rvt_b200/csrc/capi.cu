@@ -62,7 +62,12 @@ int launch_gemm(GemmArgs a, int n_mtiles, int n_ntiles, cudaStream_t st, const C
   a.tmem_cols = static_cast<int>(tmem_cols_pow2(static_cast<uint32_t>(a.BN)));
   a.ab_fmt = 0;  // fp16 operands
   int stages = a.KC < 4 ? a.KC : 4;
-  while (stages > 2 && gemm_smem_bytes(stages, a.BN, extra_smem) > 110 * 1024) --stages;
+  static int smem_cap_kb = -1, tma_cap_kb = -1;
+  if (smem_cap_kb < 0) { const char* e = getenv("RVT_GEMM_SMEM_KB"); smem_cap_kb = e ? atoi(e) : 110; }
+  if (tma_cap_kb < 0) { const char* e = getenv("RVT_TMA_SMEM_KB"); tma_cap_kb = e ? atoi(e) : 110; }
+  const size_t cap = static_cast<size_t>(LOADER == LD_TMA ? tma_cap_kb : smem_cap_kb) * 1024;
+  if (LOADER == LD_TMA && a.KC > stages) stages = a.KC < kMaxStages ? a.KC : kMaxStages;
+  while (stages > 2 && gemm_smem_bytes(stages, a.BN, extra_smem) > cap) --stages;
   while (stages > 1 && gemm_smem_bytes(stages, a.BN, extra_smem) > static_cast<size_t>(kMaxSmem)) --stages;
   a.stages = stages;
   const size_t smem = gemm_smem_bytes(stages, a.BN, extra_smem);
@@ -166,7 +171,9 @@ int rvt_stem_u8_ok(int cin, int ksize, int stride, int pad, int win, int hout, i
 int rvt_conv_tile_n(int cout) { return (cout >= kWideDim && cout % 128 == 0) ? 128 : cout; }
 
 int rvt_lstm_cw(int dim) {
-  for (int cw = 64; cw >= 16; cw -= 16)
+  static int cw_max = -1;
+  if (cw_max < 0) { const char* e = getenv("RVT_LSTM_CW"); cw_max = e ? atoi(e) : 64; }
+  for (int cw = cw_max; cw >= 16; cw -= 16)
     if (dim % cw == 0) return cw;
   return -1;
 }
