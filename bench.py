@@ -181,8 +181,10 @@ def main():
     assert hi - lo == B_PER_GPU
     # synthetic uint8 event tensors: SEQ_LEN timesteps, resident on the device (37 MB each)
     g = torch.Generator(device='cpu').manual_seed(1234 + lo)
-    seq_host = (torch.randint(1, 11, (SEQ_LEN, B_PER_GPU, IN_C, IN_H, IN_W), generator=g, dtype=torch.uint8) *
-                (torch.rand((SEQ_LEN, B_PER_GPU, IN_C, IN_H, IN_W), generator=g) < 0.1)).pin_memory()
+    shape = (SEQ_LEN, B_PER_GPU, IN_C, IN_H, IN_W)
+    seq_host = torch.randint(1, 11, shape, generator=g, dtype=torch.uint8)         # counts 1..10 ...
+    seq_host.mul_(torch.randint(0, 10, shape, generator=g, dtype=torch.uint8) == 0)  # ... on ~10 % of the bins
+    seq_host = seq_host.pin_memory()
     seq_dev = seq_host.to(dev)
 
     wavefront = not args.no_wavefront
