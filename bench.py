@@ -168,6 +168,10 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
+        # NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION (the image default); stdout must carry
+        # exactly one JSON line, so keep NCCL at WARN unless the user asked for more.
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=dev)
 
     spec = rvt_b_spec()
@@ -336,7 +340,7 @@ def main():
             line['cpu_baseline'] = {'value': v, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
                                     'sample': '2 timesteps x batch 8 (after 1 warm-up timestep), fp32 torch CPU ops; '
                                               f'{cores} threads = best of a sweep up to os.cpu_count()={os.cpu_count()}'}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
