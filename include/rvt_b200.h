@@ -110,6 +110,80 @@ int rvt_dws_conv_lstm(const float* x, const float* h_prev, const float* c_prev, 
 int rvt_linear_f16(const void* a, int64_t m, int k, int n, const void* w_packed, const float* bias, int act,
                    void* out, void* stream);
 
+/* ======================================================================================
+ * Training step (BASELINE configs[2]).  The reference has no backward code of its own: PyTorch
+ * autograd differentiates maxvit.py / rnn.py inside modules/detection.py:150-199 (training_step).
+ * The entries below are (1) the training-mode forward of each operator, which additionally saves
+ * the intermediates its gradient needs, and (2) the building blocks of the analytic backward,
+ * composed per operator in rvt_b200/train.py.  Gradient matrices are fp32 accumulators the
+ * kernels ADD into (zero them once per backward pass; contributions of all unrolled timesteps
+ * accumulate in place).  Gradient signals inside a branch are fp16 (as under the reference's
+ * precision-16 AMP), the residual-stream / state gradients are fp32.
+ * ====================================================================================== */
+
+/* a3 forward, training: also stores the conv output before LayerNorm (raw_out f32 [B,Hout,Wout,Cout]);
+ * s2d_scratch / stem_mode as in rvt_downsample_cf2cl. */
+int rvt_downsample_cf2cl_train(const void* in, int in_dtype, int in_nchw, int batch, int cin, int hin, int win,
+                               int ksize, int stride, int pad, int hout, int wout, int cout, const void* w_packed,
+                               const float* ln_w, const float* ln_b, float eps, float* out, float* raw_out,
+                               void* s2d_scratch, int stem_mode, void* stream);
+/* a4-a7 forward, training: out of place (x_out = x_in + ...), always the three-kernel path; weights packed with
+ * pack_linear_weight(bn = rvt_tile_n(...)); qkv_save f16 [rows,3C] and o_save f16 [rows,C] are kept for the backward. */
+int rvt_partition_attention_train(const float* x_in, float* x_out, int batch, int height, int width, int dim, int ph,
+                                  int pw, int grid, int dim_head, const float* n1_w, const float* n1_b, float eps,
+                                  const void* wqkv_packed, const float* bqkv, const void* wproj_packed,
+                                  const float* bproj, const float* gamma1, void* qkv_save, void* o_save,
+                                  void* scratch_xn, void* stream);
+/* a8 forward, training: out of place, two-GEMM path; pre_save / act_save f16 [round_up(n,128), hidden] = fc1 output
+ * before / after GELU. */
+int rvt_mlp_block_train(const float* x_in, float* x_out, int64_t n_tokens, int dim, int hidden, const float* n2_w,
+                        const float* n2_b, float eps, const void* w1_packed, const float* b1, const void* w2_packed,
+                        const float* b2, const float* gamma2, void* pre_save, void* act_save, void* scratch_xn,
+                        void* stream);
+/* a9 forward, training (dws_mode 0 only): xh_save f16 [round_up(n,128), 2C] = [x | h_prev], gates_save f16 [n, 4C] =
+ * activated gates [f|i|o|g]. */
+int rvt_dws_conv_lstm_train(const float* x, const float* h_prev, const float* c_prev, int batch, int height, int width,
+                            int dim, const void* w_packed, const float* bias_tiled, float* h_out, float* c_out,
+                            void* xh_save, void* gates_save, void* stream);
+
+/* D = A W^T (+bias) with A f16 [m,k], W packed by pack_linear_weight(W[n,k], rvt_tile_n(n,k)).
+ * out_f32 = 0: f16 out [round_up(m,128), n]; act 0 none, 1 GELU, 2 multiply by gelu'(aux[m,n] f16) (MLP backward).
+ * out_f32 = 1: f32 out [m, n] (no bias / act).  Data gradients dX = dY W are this with W := W^T packed. */
+int rvt_linear_ex(const void* a, int64_t m, int k, int n, const void* w_packed, const float* bias, int act,
+                  const void* aux, void* out, int out_f32, void* stream);
+/* Weight gradient: g[i*s_i + j*s_j] += sum_m a1[m,i] * a2[m,j]; a1 f16 [m,n1] (ld1), a2 f16 [m,n2] (ld2).
+ * mode 0: operands consumed in place as MN-major tcgen05 tiles; mode 1: transposed copies in scratch_t
+ * (f16, rvt_gemm_tn_scratch_elems() elements) and K-major tiles. */
+int rvt_gemm_tn(const void* a1, int ld1, int n1, const void* a2, int ld2, int n2, int64_t m, float* g, int64_t s_i,
+                int64_t s_j, int mode, void* scratch_t, void* stream);
+int64_t rvt_gemm_tn_scratch_elems(int64_t m, int n1, int n2);
+/* Row maps: map_mode 0 identity (rows = tokens), 1 window, 2 grid partition order (rvt_attention_scratch_rows rows). */
+/* out16[row] = LayerNorm(x[token(row)]) (x itself if !do_ln), f16 [rows, dim]; rows without a token are zero. */
+int rvt_ln_rows_f16(const float* x, int map_mode, int batch, int height, int width, int dim, int ph, int pw,
+                    const float* ln_w, const float* ln_b, int do_ln, float eps, void* out16, void* stream);
+/* LayerNorm backward.  dy: f16 [rows, dim] in map order (dy_is_f16) or f32 [tokens, dim].  dres (f32 tokens) += dx when
+ * given; dx16 (f16 [rows, dim]) = dx when given; dw_acc / db_acc (f32 [dim]) += parameter gradients. do_ln = 0: dx = dy. */
+int rvt_ln_bwd(const float* x, const void* dy, int dy_is_f16, int map_mode, int batch, int height, int width, int dim,
+               int ph, int pw, const float* ln_w, int do_ln, float eps, float* dres, void* dx16, float* dw_acc,
+               float* db_acc, void* stream);
+/* d0[row] = f16(dres[token(row)]), d1[row] = f16(gamma * dres[token(row)])  (LayerScale backward, maxvit.py:45-53). */
+int rvt_gather_cast(const float* dres, int map_mode, int batch, int height, int width, int dim, int ph, int pw,
+                    const float* gamma, void* d0, void* d1, void* stream);
+/* softmax(QK^T)V backward per (partition group, head) (maxvit.py:349-352): qkv, dqkv f16 [rows,3C]; dout f16 [rows,C]. */
+int rvt_attn_core_bwd(const void* qkv, const void* dout, void* dqkv, int batch, int height, int width, int dim, int ph,
+                      int pw, int dim_head, void* stream);
+/* Conv-LSTM gates backward (rnn.py:57-67): dpre f16 [n,4C] ([f|i|o|g] = rows of conv1x1.weight), dc_prev f32 [n,C]. */
+int rvt_lstm_gates_bwd(const void* gates, const float* c_prev, const float* c_new, const float* dh, const float* dc,
+                       int64_t n_tokens, int dim, void* dpre, float* dc_prev, void* stream);
+/* Downsample conv operand: col f16 [B*Hout*Wout, round_up(k*k*cin, 8)], K order (ky, kx, ci). */
+int rvt_im2col(const void* in, int in_dtype, int in_nchw, int batch, int cin, int hin, int win, int ksize, int stride,
+               int pad, int hout, int wout, void* col, void* stream);
+/* d_in f32 [B,Hin,Win,Cin] = col2im(dcol f16 [B*Hout*Wout, round_up(k*k*cin, 8)]). */
+int rvt_col2im(const void* dcol, int batch, int cin, int hin, int win, int ksize, int stride, int pad, int hout,
+               int wout, float* d_in, void* stream);
+/* acc[n] += sum_m a[m,n]  (a f16, leading dimension ld): bias gradients. */
+int rvt_colsum(const void* a, int64_t m, int n, int ld, float* acc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,7 @@ _refshim.install()
 from oracle import backbone_oracle as bo  # noqa: E402
 from oracle import voxel_oracle as vo  # noqa: E402
 from tests.golden_configs import BACKBONE_CASES, VOXEL_CASES, spec_of, make_voxel_events  # noqa: E402
+from tests.helpers import GRAD_CASES, GRAD_SUB, case_inputs, train_loss  # noqa: E402
 
 from models.detection.recurrent_backbone import build_recurrent_backbone  # noqa: E402
 from data.utils.representations import StackedHistogram  # noqa: E402
@@ -97,6 +98,44 @@ def run_backbone_case(name, case):
           f'{sum(v.size for v in out.values())} values saved')
 
 
+def run_backbone_grad_case(name, steps):
+    """Training-step pin: gradients of tests.helpers.train_loss over `steps` unrolled timesteps (states carried,
+    modules/detection.py:150-199) from the REFERENCE under autograd, fp32 CPU; the oracle must agree."""
+    case = BACKBONE_CASES[name]
+    spec = spec_of(case)
+    torch.manual_seed(0)
+    ref = build_recurrent_backbone(ref_cfg(spec)).train()
+    params = bo.synth_params(spec, case['seed'], case.get('gamma_mode', 'uniform'))
+    ref.load_state_dict(params, strict=True)
+    xs = case_inputs(case, steps)
+    outs, st = [], None
+    for x in xs:
+        o, st = ref(x.float(), st, None)
+        outs.append(o)
+    loss_r = train_loss(outs, st)
+    loss_r.backward()
+    g_ref = {k: p.grad.detach().clone() for k, p in ref.named_parameters()}
+    po = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    outs, st = [], None
+    for x in xs:
+        o, st = bo.backbone_forward(x.float(), st, po, spec)
+        outs.append(o)
+    loss_o = train_loss(outs, st)
+    loss_o.backward()
+    worst = 0.0
+    for k, g in g_ref.items():
+        e = float((po[k].grad - g).norm() / g.norm().clamp_min(1e-12))
+        worst = max(worst, e)
+    assert worst < 1e-4 and abs(float(loss_o.detach()) - float(loss_r.detach())) <= 1e-5 * abs(float(loss_r.detach())), (name, worst)
+    out = {'loss': np.float64(float(loss_r))}
+    for k, g in g_ref.items():
+        out['g.' + k] = sub(g, GRAD_SUB)
+        out['n.' + k] = np.float64(g.double().norm().item())
+    np.savez_compressed(os.path.join(GOLD, f'backbone_grads_{name}.npz'), **out)
+    print(f'backbone grads {name}: oracle-vs-reference worst rel-L2 {worst:.2e}; loss {float(loss_r):.6f}; '
+          f'{sum(v.size for v in out.values())} values saved')
+
+
 def run_voxel_case(name, case):
     x, y, p, t = make_voxel_events(case)
     out = {}
@@ -115,7 +154,11 @@ def run_voxel_case(name, case):
 if __name__ == '__main__':
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    for n, c in VOXEL_CASES.items():
-        run_voxel_case(n, c)
-    for n, c in BACKBONE_CASES.items():
-        run_backbone_case(n, c)
+    if '--grads-only' not in sys.argv:
+        for n, c in VOXEL_CASES.items():
+            run_voxel_case(n, c)
+    if '--grads-only' not in sys.argv:
+        for n, c in BACKBONE_CASES.items():
+            run_backbone_case(n, c)
+    for n, steps in GRAD_CASES.items():
+        run_backbone_grad_case(n, steps)

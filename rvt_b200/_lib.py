@@ -29,6 +29,24 @@ SIGNATURES = {
     'rvt_mlp_block': (_i, [_vp, _i64, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'rvt_dws_conv_lstm': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     'rvt_linear_f16': (_i, [_vp, _i64, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    # ---- training step ----
+    'rvt_downsample_cf2cl_train': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f,
+                                         _vp, _vp, _vp, _i, _vp]),
+    'rvt_partition_attention_train': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp,
+                                            _vp, _vp, _vp, _vp, _vp, _vp]),
+    'rvt_mlp_block_train': (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'rvt_dws_conv_lstm_train': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'rvt_linear_ex': (_i, [_vp, _i64, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp]),
+    'rvt_gemm_tn': (_i, [_vp, _i, _i, _vp, _i, _i, _i64, _vp, _i64, _i64, _i, _vp, _vp]),
+    'rvt_gemm_tn_scratch_elems': (_i64, [_i64, _i, _i]),
+    'rvt_ln_rows_f16': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _f, _vp, _vp]),
+    'rvt_ln_bwd': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp]),
+    'rvt_gather_cast': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    'rvt_attn_core_bwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    'rvt_lstm_gates_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp]),
+    'rvt_im2col': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    'rvt_col2im': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    'rvt_colsum': (_i, [_vp, _i64, _i, _i, _vp, _vp]),
 }
 
 _lib = None

@@ -227,6 +227,7 @@ class RNNDetector(nn.Module):
         self._packed = None
         self._packed_key = None
         self._scratch: Dict[str, torch.Tensor] = {}
+        self._train = None
         # Optional: model input resolution (config `in_res_hw`).  When set, an un-padded event
         # tensor (e.g. 360x640) is accepted and the bottom/right zero padding the harness would
         # add (utils/padding.py:29-44) is folded into the stem conv's bounds checks.
@@ -245,6 +246,12 @@ class RNNDetector(nn.Module):
         idx = [x - 1 for x in stages]
         assert min(idx) >= 0 and max(idx) < len(self.stages), idx
         return tuple(self.strides[i] for i in idx)
+
+    def _train_engine(self):
+        if getattr(self, '_train', None) is None:
+            from . import train
+            self._train = train.TrainEngine(self)
+        return self._train
 
     # ---- packed weights ------------------------------------------------------------------
     def _param_key(self):
@@ -331,14 +338,14 @@ class RNNDetector(nn.Module):
                 token_mask: Optional[torch.Tensor] = None):
         if not x.is_cuda:
             raise RuntimeError('rvt_b200.RNNDetector runs on CUDA (sm_100a) only; there is no CPU fallback')
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError(
-                'rvt_b200.RNNDetector: backward kernels are not built yet (DESIGN.md §7); call under '
-                'torch.no_grad() / torch.inference_mode() as validation.py:82 does')
         if prev_states is None:
             prev_states = [None] * self.num_stages
         assert len(prev_states) == self.num_stages
         assert x.dim() == 4
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # training step (modules/detection.py:150-199): autograd-visible path, rvt_b200/train.py
+            from . import train
+            return train.forward_train(self, x, list(prev_states), token_mask)
         packed = self._ensure_packed(x.device)
         x = self._prep_input(x)
         states: LstmStates = []

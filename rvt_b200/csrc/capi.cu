@@ -12,6 +12,7 @@
 #include "mlp_fused.cuh"
 #include "attn_fused.cuh"
 #include "voxel.cuh"
+#include "train.cuh"
 
 using namespace rvt;
 
@@ -214,10 +215,10 @@ int rvt_stacked_histogram(const int64_t* x, const int64_t* y, const int64_t* pol
   return static_cast<int>(cudaGetLastError());
 }
 
-int rvt_downsample_cf2cl(const void* in, int in_dtype, int in_nchw, int batch, int cin, int hin, int win, int ksize,
+static int downsample_impl(const void* in, int in_dtype, int in_nchw, int batch, int cin, int hin, int win, int ksize,
                          int stride, int pad, int hout, int wout, int cout, const void* w_packed, const float* ln_w,
                          const float* ln_b, float eps, const uint8_t* token_mask, const float* mask_token,
-                         float* out, void* s2d_scratch, int stem_mode, void* stream) {
+                         float* out, void* s2d_scratch, int stem_mode, float* raw_out, void* stream) {
   if (!in || !w_packed || !out || batch < 1 || cout % 16 != 0 || cout > 512) return kErrBadArg;
   if (!in_nchw && (in_dtype == 1 || cin % 8 != 0)) return kErrUnsupported;   // channels-last: f32 or f16
   if ((ln_w == nullptr) != (ln_b == nullptr)) return kErrBadArg;
@@ -241,6 +242,7 @@ int rvt_downsample_cf2cl(const void* in, int in_dtype, int in_nchw, int batch, i
     a.cin = in; a.in_dtype = 1; a.in_nchw = 1; a.Cin = cin; a.Hin = hin; a.Win = win;
     a.K = 7 * cin * 8;
     a.yout = out; a.eln_w = ln_w; a.eln_b = ln_b; a.eeps = eps; a.token_mask = token_mask; a.mask_token = mask_token;
+    a.raw_out = raw_out;
     return launch_gemm<LD_STEM, EP_LN>(a, bm.n_groups, 1, st, nullptr, stem_patch_bytes(cin) + 128);
   }
   if (s2d_scratch) {
@@ -274,19 +276,41 @@ int rvt_downsample_cf2cl(const void* in, int in_dtype, int in_nchw, int batch, i
     // few row tiles: split N across CTAs (raw fp32 conv output), then LayerNorm the rows in place
     a.BN = rvt_conv_tile_n(cout);
     a.ldo = cout;
+    float* raw = raw_out ? raw_out : out;
+    a.yout = raw;
     int rc = launch_gemm<LD_CONV, EP_RAW>(a, cdiv(n_tok, 128), cout / a.BN, st);
     if (rc) return rc;
-    return launch_ln_rows<false>(out, a.map, n_tok, cout, 1, ln_w, ln_b, eps, out, token_mask, mask_token, st);
+    return launch_ln_rows<false>(raw, a.map, n_tok, cout, 1, ln_w, ln_b, eps, out, token_mask, mask_token, st);
   }
+  a.raw_out = raw_out;
   return launch_gemm<LD_CONV, EP_LN>(a, cdiv(n_tok, 128), 1, st);
 }
 
-int rvt_partition_attention(float* x, int batch, int height, int width, int dim, int ph, int pw, int grid,
+int rvt_downsample_cf2cl(const void* in, int in_dtype, int in_nchw, int batch, int cin, int hin, int win, int ksize,
+                         int stride, int pad, int hout, int wout, int cout, const void* w_packed, const float* ln_w,
+                         const float* ln_b, float eps, const uint8_t* token_mask, const float* mask_token,
+                         float* out, void* s2d_scratch, int stem_mode, void* stream) {
+  return downsample_impl(in, in_dtype, in_nchw, batch, cin, hin, win, ksize, stride, pad, hout, wout, cout, w_packed, ln_w,
+                         ln_b, eps, token_mask, mask_token, out, s2d_scratch, stem_mode, nullptr, stream);
+}
+
+int rvt_downsample_cf2cl_train(const void* in, int in_dtype, int in_nchw, int batch, int cin, int hin, int win, int ksize,
+                               int stride, int pad, int hout, int wout, int cout, const void* w_packed, const float* ln_w,
+                               const float* ln_b, float eps, float* out, float* raw_out, void* s2d_scratch, int stem_mode,
+                               void* stream) {
+  if (!raw_out) return kErrBadArg;
+  return downsample_impl(in, in_dtype, in_nchw, batch, cin, hin, win, ksize, stride, pad, hout, wout, cout, w_packed, ln_w,
+                         ln_b, eps, nullptr, nullptr, out, s2d_scratch, stem_mode, raw_out, stream);
+}
+
+static int partition_attention_impl(const float* x, float* x_out, int force_unfused, int batch, int height, int width, int dim,
+                            int ph, int pw, int grid,
                             int dim_head, const float* n1_w, const float* n1_b, float eps, const void* wqkv_packed,
                             const float* bqkv, const void* wproj_packed, const float* bproj, const float* gamma1,
                             void* scratch_qkv, void* scratch_o, void* scratch_xn, void* stream) {
-  if (!x || !wqkv_packed || !wproj_packed) return kErrBadArg;
-  if (!rvt_attention_is_fused(dim, dim_head) && (!scratch_qkv || !scratch_o)) return kErrBadArg;
+  if (!x || !x_out || !wqkv_packed || !wproj_packed) return kErrBadArg;
+  const bool fused = !force_unfused && rvt_attention_is_fused(dim, dim_head);
+  if (!fused && (!scratch_qkv || !scratch_o)) return kErrBadArg;
   if (dim % 8 != 0 || dim > 512 || dim_head % 8 != 0 || dim_head > 64 || dim % dim_head != 0) return kErrUnsupported;
   const int64_t rows = rvt_attention_scratch_rows(batch, height, width, ph, pw);
   if (rows < 0) return kErrUnsupported;
@@ -298,9 +322,10 @@ int rvt_partition_attention(float* x, int batch, int height, int width, int dim,
   m.rows_per_win = rpg; m.n_groups = batch * m.ny * m.nx; m.n_tokens = batch * height * width;
   const int n_mtiles = static_cast<int>(rows / 128);
 
-  if (rvt_attention_is_fused(dim, dim_head)) {
+  if (fused) {
+    if (x != x_out) return kErrBadArg;
     AttnFusedArgs fa{};
-    fa.x = x; fa.map = m; fa.C = dim; fa.dh = dim_head; fa.nh = dim / dim_head;
+    fa.x = x_out; fa.map = m; fa.C = dim; fa.dh = dim_head; fa.nh = dim / dim_head;
     fa.ln_w = n1_w; fa.ln_b = n1_b; fa.eps = eps; fa.do_ln = n1_w != nullptr;
     fa.wqkv = static_cast<const __half*>(wqkv_packed); fa.bqkv = bqkv;
     fa.wproj = static_cast<const __half*>(wproj_packed); fa.bproj = bproj; fa.gamma = gamma1;
@@ -366,22 +391,44 @@ int rvt_partition_attention(float* x, int batch, int height, int width, int dim,
     a.K = dim; a.BN = rvt_tile_n(dim, dim);
     a.Wp = static_cast<const __half*>(wproj_packed); a.bias = bproj; a.map = m;
     a.a16 = static_cast<const __half*>(scratch_o); a.lda = dim; a.a_rows = static_cast<int>(rows);
-    a.C = dim; a.res = x; a.xout = x; a.gamma = gamma1;
+    a.C = dim; a.res = x; a.xout = x_out; a.gamma = gamma1;
     return launch_gemm_f16<EP_RES>(a, n_mtiles, dim / a.BN, st);
   }
 }
 
-int rvt_mlp_block(float* x, int64_t n_tokens, int dim, int hidden, const float* n2_w, const float* n2_b, float eps,
+int rvt_partition_attention(float* x, int batch, int height, int width, int dim, int ph, int pw, int grid,
+                            int dim_head, const float* n1_w, const float* n1_b, float eps, const void* wqkv_packed,
+                            const float* bqkv, const void* wproj_packed, const float* bproj, const float* gamma1,
+                            void* scratch_qkv, void* scratch_o, void* scratch_xn, void* stream) {
+  return partition_attention_impl(x, x, 0, batch, height, width, dim, ph, pw, grid, dim_head, n1_w, n1_b, eps, wqkv_packed,
+                                  bqkv, wproj_packed, bproj, gamma1, scratch_qkv, scratch_o, scratch_xn, stream);
+}
+
+int rvt_partition_attention_train(const float* x_in, float* x_out, int batch, int height, int width, int dim, int ph, int pw,
+                                  int grid, int dim_head, const float* n1_w, const float* n1_b, float eps,
+                                  const void* wqkv_packed, const float* bqkv, const void* wproj_packed, const float* bproj,
+                                  const float* gamma1, void* qkv_save, void* o_save, void* scratch_xn, void* stream) {
+  if (x_in == x_out) return kErrBadArg;
+  return partition_attention_impl(x_in, x_out, 1, batch, height, width, dim, ph, pw, grid, dim_head, n1_w, n1_b, eps,
+                                  wqkv_packed, bqkv, wproj_packed, bproj, gamma1, qkv_save, o_save, scratch_xn, stream);
+}
+
+static int mlp_block_impl(const float* x, float* x_out, int force_unfused, void* pre_out, int64_t n_tokens, int dim, int hidden,
+                  const float* n2_w, const float* n2_b, float eps,
                   const void* w1_packed, const float* b1, const void* w2_packed, const float* b2, const float* gamma2,
                   void* scratch_hidden, void* scratch_xn, void* stream) {
-  if (!x || !w1_packed || !w2_packed || !scratch_hidden || !n2_w || !n2_b) return kErrBadArg;
+  if (!x || !x_out || !w1_packed || !w2_packed || !scratch_hidden || !n2_w || !n2_b) return kErrBadArg;
   if (dim % 8 != 0 || dim > 512 || hidden % 16 != 0) return kErrUnsupported;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int n_mtiles = cdiv(n_tokens, 128);
   int bn1 = 0, bn2 = 0;
-  if (rvt_mlp_tiles(dim, hidden, &bn1, &bn2)) {
+  if (force_unfused) {
+    bn1 = rvt_tile_n(hidden, dim); bn2 = rvt_tile_n(dim, hidden);
+    if (bn1 < 0 || bn2 < 0) return kErrUnsupported;
+  } else if (rvt_mlp_tiles(dim, hidden, &bn1, &bn2)) {
+    if (x != x_out) return kErrBadArg;
     MlpArgs ma{};
-    ma.x = x; ma.n_tokens = static_cast<int>(n_tokens); ma.C = dim; ma.hidden = hidden;
+    ma.x = x_out; ma.n_tokens = static_cast<int>(n_tokens); ma.C = dim; ma.hidden = hidden;
     ma.ln_w = n2_w; ma.ln_b = n2_b; ma.eps = eps;
     ma.w1p = static_cast<const __half*>(w1_packed); ma.b1 = b1;
     ma.w2p = static_cast<const __half*>(w2_packed); ma.b2 = b2; ma.gamma = gamma2;
@@ -411,6 +458,7 @@ int rvt_mlp_block(float* x, int64_t n_tokens, int dim, int hidden, const float* 
     a.K = dim; a.BN = bn1;
     a.Wp = static_cast<const __half*>(w1_packed); a.bias = b1; a.map = m;
     a.o16 = static_cast<__half*>(scratch_hidden); a.ldo = hidden; a.act = 1;
+    a.o16_pre = static_cast<__half*>(pre_out);
     int rc;
     if (dim >= kWideDim && dim % 128 == 0) {
       if (!scratch_xn) return kErrBadArg;
@@ -429,14 +477,30 @@ int rvt_mlp_block(float* x, int64_t n_tokens, int dim, int hidden, const float* 
     a.K = hidden; a.BN = bn2;
     a.Wp = static_cast<const __half*>(w2_packed); a.bias = b2; a.map = m;
     a.a16 = static_cast<const __half*>(scratch_hidden); a.lda = hidden; a.a_rows = n_mtiles * 128;
-    a.C = dim; a.res = x; a.xout = x; a.gamma = gamma2;
+    a.C = dim; a.res = x; a.xout = x_out; a.gamma = gamma2;
     return launch_gemm_f16<EP_RES>(a, n_mtiles, dim / a.BN, st);
   }
 }
 
-int rvt_dws_conv_lstm(const float* x, const float* h_prev, const float* c_prev, int batch, int height, int width,
+int rvt_mlp_block(float* x, int64_t n_tokens, int dim, int hidden, const float* n2_w, const float* n2_b, float eps,
+                  const void* w1_packed, const float* b1, const void* w2_packed, const float* b2, const float* gamma2,
+                  void* scratch_hidden, void* scratch_xn, void* stream) {
+  return mlp_block_impl(x, x, 0, nullptr, n_tokens, dim, hidden, n2_w, n2_b, eps, w1_packed, b1, w2_packed, b2, gamma2,
+                        scratch_hidden, scratch_xn, stream);
+}
+
+int rvt_mlp_block_train(const float* x_in, float* x_out, int64_t n_tokens, int dim, int hidden, const float* n2_w,
+                        const float* n2_b, float eps, const void* w1_packed, const float* b1, const void* w2_packed,
+                        const float* b2, const float* gamma2, void* pre_save, void* act_save, void* scratch_xn, void* stream) {
+  if (x_in == x_out || !pre_save || !act_save) return kErrBadArg;
+  return mlp_block_impl(x_in, x_out, 1, pre_save, n_tokens, dim, hidden, n2_w, n2_b, eps, w1_packed, b1, w2_packed, b2, gamma2,
+                        act_save, scratch_xn, stream);
+}
+
+static int dws_conv_lstm_impl(const float* x, const float* h_prev, const float* c_prev, int batch, int height, int width,
                       int dim, const void* w_packed, const float* bias_tiled, const float* dw_w, const float* dw_b,
-                      int dws_mode, int dws_ks, float* h_out, float* c_out, void* scratch_xh, void* h_out_f16, void* stream) {
+                      int dws_mode, int dws_ks, float* h_out, float* c_out, void* scratch_xh, void* h_out_f16, void* gates16,
+                      void* stream) {
   if (!x || !w_packed || !bias_tiled || !h_out || !c_out) return kErrBadArg;
   if (dim % 16 != 0 || dws_mode < 0 || dws_mode > 2) return kErrUnsupported;
   if (dws_mode != 0 && (!dw_w || !dw_b || dws_ks % 2 == 0)) return kErrBadArg;
@@ -449,6 +513,7 @@ int rvt_dws_conv_lstm(const float* x, const float* h_prev, const float* c_prev, 
   a.map = identity_map(n_tok, height, width);
   a.x = x; a.C = dim; a.hprev = h_prev; a.dw_w = dw_w; a.dw_b = dw_b; a.dws_mode = dws_mode; a.dws_ks = dws_ks;
   a.cprev = c_prev; a.hout = h_out; a.cout = c_out; a.cw = cw; a.hout16 = static_cast<__half*>(h_out_f16);
+  a.gates16 = static_cast<__half*>(gates16);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int n_mtiles = cdiv(n_tok, 128);
   if (dws_mode == 0 && dim >= kWideDim && scratch_xh != nullptr) {
@@ -465,6 +530,39 @@ int rvt_dws_conv_lstm(const float* x, const float* h_prev, const float* c_prev, 
   return launch_gemm<LD_XH, EP_LSTM>(a, n_mtiles, dim / cw, st);
 }
 
+int rvt_dws_conv_lstm(const float* x, const float* h_prev, const float* c_prev, int batch, int height, int width,
+                      int dim, const void* w_packed, const float* bias_tiled, const float* dw_w, const float* dw_b,
+                      int dws_mode, int dws_ks, float* h_out, float* c_out, void* scratch_xh, void* h_out_f16, void* stream) {
+  return dws_conv_lstm_impl(x, h_prev, c_prev, batch, height, width, dim, w_packed, bias_tiled, dw_w, dw_b, dws_mode, dws_ks,
+                            h_out, c_out, scratch_xh, h_out_f16, nullptr, stream);
+}
+
+int rvt_dws_conv_lstm_train(const float* x, const float* h_prev, const float* c_prev, int batch, int height, int width,
+                            int dim, const void* w_packed, const float* bias_tiled, float* h_out, float* c_out,
+                            void* xh_save, void* gates_save, void* stream) {
+  if (!xh_save || !gates_save) return kErrBadArg;
+  // always the cast + TMA path so the fp16 [x | h_prev] operand is materialised for the weight gradient
+  const int cw = rvt_lstm_cw(dim);
+  if (!x || !w_packed || !bias_tiled || !h_out || !c_out || dim % 16 != 0 || cw < 0) return kErrBadArg;
+  const int64_t n_tok = static_cast<int64_t>(batch) * height * width;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n_mtiles = cdiv(n_tok, 128);
+  const int n_rows = n_mtiles * 128;
+  const int64_t items = static_cast<int64_t>(n_rows) * (2 * dim / 8);
+  cast_xh_kernel<<<static_cast<unsigned>((items + 255) / 256), 256, 0, st>>>(x, h_prev, static_cast<int>(n_tok), n_rows, dim,
+                                                                           static_cast<__half*>(xh_save));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return static_cast<int>(e);
+  GemmArgs a{};
+  a.K = 2 * dim; a.BN = 4 * cw;
+  a.Wp = static_cast<const __half*>(w_packed); a.bias = bias_tiled;
+  a.map = identity_map(n_tok, height, width);
+  a.x = x; a.C = dim; a.hprev = h_prev; a.dws_mode = 0; a.dws_ks = 3;
+  a.cprev = c_prev; a.hout = h_out; a.cout = c_out; a.cw = cw; a.gates16 = static_cast<__half*>(gates_save);
+  a.a16 = static_cast<const __half*>(xh_save); a.lda = 2 * dim; a.a_rows = n_rows;
+  return launch_gemm_f16<EP_LSTM>(a, n_mtiles, dim / cw, st);
+}
+
 int rvt_linear_f16(const void* av, int64_t m, int k, int n, const void* w_packed, const float* bias, int act, void* out,
                    void* stream) {
   if (!av || !w_packed || !out || k % 8 != 0) return kErrBadArg;
@@ -475,6 +573,237 @@ int rvt_linear_f16(const void* av, int64_t m, int k, int n, const void* w_packed
   a.a16 = static_cast<const __half*>(av); a.lda = k; a.a_rows = static_cast<int>(m);
   a.o16 = static_cast<__half*>(out); a.ldo = n; a.act = act;
   return launch_gemm_f16<EP_F16>(a, cdiv(m, 128), n / a.BN, static_cast<cudaStream_t>(stream));
+}
+
+
+// ======================================================================================
+// Training building blocks (see train.cuh).  The reference's backward is PyTorch autograd over
+// maxvit.py / rnn.py; each entry restates the analytic gradient of one forward operator.
+// ======================================================================================
+static int make_row_map(int map_mode, int batch, int height, int width, int ph, int pw, RowMap* out, int64_t* rows) {
+  const int64_t n_tok = static_cast<int64_t>(batch) * height * width;
+  if (map_mode == 0) {
+    *out = identity_map(n_tok, height, width);
+    *rows = n_tok;
+    return 0;
+  }
+  const int64_t r = rvt_attention_scratch_rows(batch, height, width, ph, pw);
+  if (r < 0) return kErrUnsupported;
+  RowMap m{};
+  m.mode = map_mode == 2 ? MAP_GRID : MAP_WINDOW;
+  m.H = height; m.W = width; m.ph = ph; m.pw = pw; m.ny = height / ph; m.nx = width / pw; m.P = ph * pw;
+  m.rows_per_win = rvt_rows_per_group(ph * pw); m.n_groups = batch * m.ny * m.nx; m.n_tokens = static_cast<int>(n_tok);
+  *out = m;
+  *rows = r;
+  return 0;
+}
+
+int rvt_linear_ex(const void* av, int64_t m, int k, int n, const void* w_packed, const float* bias, int act, const void* aux,
+                  void* out, int out_f32, void* stream) {
+  if (!av || !w_packed || !out || k % 8 != 0) return kErrBadArg;
+  if (act == 2 && !aux) return kErrBadArg;
+  GemmArgs a{};
+  a.K = k; a.BN = rvt_tile_n(n, k);
+  if (a.BN < 0) return kErrUnsupported;
+  a.Wp = static_cast<const __half*>(w_packed); a.bias = bias;
+  a.a16 = static_cast<const __half*>(av); a.lda = k; a.a_rows = static_cast<int>(m);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (out_f32) {
+    if (bias || act) return kErrUnsupported;
+    a.map = identity_map(m, 1, static_cast<int>(m));
+    a.yout = static_cast<float*>(out); a.ldo = n;
+    return launch_gemm_f16<EP_RAW>(a, cdiv(m, 128), n / a.BN, st);
+  }
+  a.o16 = static_cast<__half*>(out); a.ldo = n; a.act = act;
+  a.aux16 = static_cast<const __half*>(aux); a.ldaux = n;
+  return launch_gemm_f16<EP_F16>(a, cdiv(m, 128), n / a.BN, st);
+}
+
+static bool make_tmap_f16_box(const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows, CUtensorMap* out) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn || (reinterpret_cast<uintptr_t>(base) & 15) || (ld % 8) != 0) return false;
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int64_t rvt_gemm_tn_scratch_elems(int64_t m, int n1, int n2) {
+  const int64_t ldt = (m + 63) / 64 * 64;
+  return (static_cast<int64_t>((n1 + 127) / 128 * 128) + (n2 + 127) / 128 * 128) * ldt;
+}
+
+int rvt_gemm_tn(const void* a1, int ld1, int n1, const void* a2, int ld2, int n2, int64_t m, float* g, int64_t s_i,
+                int64_t s_j, int mode, void* scratch_t, void* stream) {
+  if (!a1 || !a2 || !g || m < 0 || n1 < 1 || n2 < 1 || ld1 % 8 || ld2 % 8) return kErrBadArg;
+  if (m == 0) return 0;
+  if (m > 0x7fffffffLL) return kErrUnsupported;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TnArgs a{};
+  a.M = static_cast<int>(m); a.N1 = n1; a.N2 = n2;
+  a.BN = n2 <= 64 ? 64 : 128;
+  a.kc_total = cdiv(m, 64);
+  a.G = g; a.s_i = s_i; a.s_j = s_j;
+  a.kmajor = mode == 1 ? 1 : 0;
+  a.tmem_cols = static_cast<int>(tmem_cols_pow2(static_cast<uint32_t>(a.BN)));
+  const int tiles = cdiv(n1, 128) * cdiv(n2, a.BN);
+  int sms = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  int splits = (2 * sms + tiles - 1) / tiles;
+  const int max_splits = (a.kc_total + 7) / 8;           // at least 8 chunks (512 tokens) per split
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  a.kc_per_split = (a.kc_total + splits - 1) / splits;
+  splits = (a.kc_total + a.kc_per_split - 1) / a.kc_per_split;
+  a.stages = 4;
+  const size_t smem = tn_smem_bytes(a.stages, a.BN);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set = true;
+  }
+  alignas(64) CUtensorMap tm1, tm2;
+  if (a.kmajor) {
+    if (!scratch_t) return kErrBadArg;
+    const int64_t ldt = (m + 63) / 64 * 64;
+    __half* t1 = static_cast<__half*>(scratch_t);
+    const int n1p = (n1 + 127) / 128 * 128, n2p = (n2 + 127) / 128 * 128;   // rows beyond n1 / n2: never stored
+    __half* t2 = t1 + static_cast<int64_t>(n1p) * ldt;
+    transpose_f16_kernel<<<dim3(static_cast<unsigned>(ldt / 32), cdiv(n1, 32)), 256, 0, st>>>(
+        static_cast<const __half*>(a1), a.M, n1, ld1, t1, static_cast<int>(ldt));
+    transpose_f16_kernel<<<dim3(static_cast<unsigned>(ldt / 32), cdiv(n2, 32)), 256, 0, st>>>(
+        static_cast<const __half*>(a2), a.M, n2, ld2, t2, static_cast<int>(ldt));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return static_cast<int>(e);
+    if (!make_tmap_f16_box(t1, n1p, m, ldt, 64, 128, &tm1) || !make_tmap_f16_box(t2, n2p, m, ldt, 64, a.BN, &tm2))
+      return kErrUnsupported;
+  } else {
+    if (!make_tmap_f16_box(a1, m, n1, ld1, 64, 64, &tm1) || !make_tmap_f16_box(a2, m, n2, ld2, 64, 64, &tm2))
+      return kErrUnsupported;
+  }
+  gemm_tn_kernel<<<dim3(cdiv(n1, 128), cdiv(n2, a.BN), splits), kTnThreads, smem, st>>>(a, tm1, tm2);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int rvt_ln_rows_f16(const float* x, int map_mode, int batch, int height, int width, int dim, int ph, int pw,
+                    const float* ln_w, const float* ln_b, int do_ln, float eps, void* out16, void* stream) {
+  if (!x || !out16 || dim % 8 != 0 || dim > 512) return kErrBadArg;
+  RowMap m; int64_t rows;
+  int rc = make_row_map(map_mode, batch, height, width, ph, pw, &m, &rows);
+  if (rc) return rc;
+  if (rows <= 0) return 0;
+  ln_rows_any_kernel<true><<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, m, static_cast<int>(rows), dim, do_ln, ln_w, ln_b, eps, out16, dim);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int rvt_ln_bwd(const float* x, const void* dy, int dy_is_f16, int map_mode, int batch, int height, int width, int dim, int ph,
+               int pw, const float* ln_w, int do_ln, float eps, float* dres, void* dx16, float* dw_acc, float* db_acc,
+               void* stream) {
+  if (!dy || (do_ln && !x) || dim % 8 != 0 || dim > 512 || (!dres && !dx16)) return kErrBadArg;
+  RowMap m; int64_t rows;
+  int rc = make_row_map(map_mode, batch, height, width, ph, pw, &m, &rows);
+  if (rc) return rc;
+  if (rows <= 0) return 0;
+  int sms = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  int64_t blocks = (rows + 7) / 8;
+  if (blocks > sms * 4) blocks = sms * 4;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dy_is_f16)
+    ln_bwd_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, dy, dim, m, static_cast<int>(rows), dim, do_ln, ln_w, eps,
+                                                                    dres, static_cast<__half*>(dx16), dim, dw_acc, db_acc);
+  else
+    ln_bwd_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, dy, dim, m, static_cast<int>(rows), dim, do_ln, ln_w, eps,
+                                                                     dres, static_cast<__half*>(dx16), dim, dw_acc, db_acc);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int rvt_gather_cast(const float* dres, int map_mode, int batch, int height, int width, int dim, int ph, int pw,
+                    const float* gamma, void* d0, void* d1, void* stream) {
+  if (!dres || (!d0 && !d1) || dim % 8 != 0) return kErrBadArg;
+  RowMap m; int64_t rows;
+  int rc = make_row_map(map_mode, batch, height, width, ph, pw, &m, &rows);
+  if (rc) return rc;
+  if (rows <= 0) return 0;
+  const int64_t items = rows * (dim / 8);
+  gather_cast_kernel<<<static_cast<unsigned>((items + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      dres, m, static_cast<int>(rows), dim, gamma, static_cast<__half*>(d0), static_cast<__half*>(d1));
+  return static_cast<int>(cudaGetLastError());
+}
+
+int rvt_attn_core_bwd(const void* qkv, const void* dout, void* dqkv, int batch, int height, int width, int dim, int ph, int pw,
+                      int dim_head, void* stream) {
+  if (!qkv || !dout || !dqkv) return kErrBadArg;
+  const int P = ph * pw, rpg = rvt_rows_per_group(P);
+  if (rpg < 0 || dim_head > 32 || dim % dim_head != 0 || height % ph || width % pw) return kErrUnsupported;
+  AttnBwdArgs a{};
+  a.qkv = static_cast<const __half*>(qkv); a.dout = static_cast<const __half*>(dout); a.dqkv = static_cast<__half*>(dqkv);
+  a.C = dim; a.dh = dim_head; a.nh = dim / dim_head; a.P = P; a.rows_per_win = rpg;
+  a.n_groups = batch * (height / ph) * (width / pw);
+  a.scale = 1.0f / sqrtf(static_cast<float>(dim_head));
+  const size_t smem = attn_bwd_smem_bytes(P);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_core_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set = true;
+  }
+  if (a.n_groups <= 0) return 0;
+  attn_core_bwd_kernel<<<dim3(a.n_groups, a.nh), 256, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int rvt_lstm_gates_bwd(const void* gates, const float* c_prev, const float* c_new, const float* dh, const float* dc,
+                       int64_t n_tokens, int dim, void* dpre, float* dc_prev, void* stream) {
+  if (!gates || !c_new || !dpre || dim % 8 != 0) return kErrBadArg;
+  if (n_tokens <= 0) return 0;
+  const int64_t items = n_tokens * (dim / 4);
+  lstm_gates_bwd_kernel<<<static_cast<unsigned>((items + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(gates), c_prev, c_new, dh, dc, n_tokens, dim, static_cast<__half*>(dpre), dc_prev);
+  return static_cast<int>(cudaGetLastError());
+}
+
+static int conv_geom(int in_dtype, int in_nchw, int batch, int cin, int hin, int win, int ksize, int stride, int pad, int hout,
+                     int wout, ConvGeom* g) {
+  if (batch < 1 || cin < 1 || ksize < 1 || stride < 1) return kErrBadArg;
+  g->B = batch; g->Cin = cin; g->Hin = hin; g->Win = win; g->KS = ksize; g->stride = stride; g->pad = pad;
+  g->Hout = hout; g->Wout = wout; g->K = ksize * ksize * cin; g->ldc = (g->K + 7) / 8 * 8;
+  g->in_dtype = in_dtype; g->in_nchw = in_nchw;
+  return 0;
+}
+
+int rvt_im2col(const void* in, int in_dtype, int in_nchw, int batch, int cin, int hin, int win, int ksize, int stride, int pad,
+               int hout, int wout, void* col, void* stream) {
+  ConvGeom g;
+  if (!in || !col || conv_geom(in_dtype, in_nchw, batch, cin, hin, win, ksize, stride, pad, hout, wout, &g)) return kErrBadArg;
+  const int64_t items = static_cast<int64_t>(batch) * hout * wout * (g.ldc / 2);
+  im2col_kernel<<<static_cast<unsigned>((items + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, g,
+                                                                                                        static_cast<__half*>(col));
+  return static_cast<int>(cudaGetLastError());
+}
+
+int rvt_col2im(const void* dcol, int batch, int cin, int hin, int win, int ksize, int stride, int pad, int hout, int wout,
+               float* d_in, void* stream) {
+  ConvGeom g;
+  if (!dcol || !d_in || cin % 2 != 0 || conv_geom(0, 0, batch, cin, hin, win, ksize, stride, pad, hout, wout, &g)) return kErrBadArg;
+  const int64_t items = static_cast<int64_t>(batch) * hin * win * (cin / 2);
+  col2im_kernel<<<static_cast<unsigned>((items + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(dcol), g, d_in);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int rvt_colsum(const void* a, int64_t m, int n, int ld, float* acc, void* stream) {
+  if (!a || !acc || n % 2 != 0 || ld % 2 != 0) return kErrBadArg;
+  if (m <= 0) return 0;
+  const int rows_per_block = 512;
+  colsum_kernel<<<dim3(cdiv(n, 64), cdiv(m, rows_per_block)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(a), m, n, ld, acc, rows_per_block);
+  return static_cast<int>(cudaGetLastError());
 }
 
 }  // extern "C"

@@ -88,14 +88,18 @@ struct GemmArgs {
   const void* cin; int in_dtype; int in_nchw; int Cin, Hin, Win, KSy, KSx, sy, sx, pady, padx, Hout, Wout;
   // EP_F16
   __half* o16; int ldo; int act;
+  __half* o16_pre;                     // optional second store: the pre-activation (bias added), same ld (training forward)
+  const __half* aux16; int ldaux;      // act == 2: acc *= gelu'(aux[row, col])  (MLP backward, maxvit.py:110-118)
   // EP_RES
   const float* res; float* xout; const float* gamma;
   // EP_LN
   float* yout; const float* eln_w; const float* eln_b; float eeps;
+  float* raw_out;                      // optional: the conv output before LayerNorm (saved for the LN backward)
   const uint8_t* token_mask; const float* mask_token;
   // EP_LSTM
   const float* cprev; float* hout; float* cout; int cw;
   __half* hout16;      // optional fp16 copy of h_t (operand of the next stage's downsample conv)
+  __half* gates16;     // optional fp16 [n_tokens, 4C] activated gates [f|i|o|g] (saved for the LSTM backward)
 };
 
 constexpr int kMaxStages = 6;
@@ -126,6 +130,19 @@ __device__ __forceinline__ float gelu_erf(float v) {
   const float q = p * t * ex2_approx(u * u * -1.4426950408889634f);
   const float r = v * q;
   return v >= 0.f ? v - r : r;
+}
+// d/dv gelu(v) = Phi(v) + v * phi(v), same A&S erf polynomial as gelu_erf
+__device__ __forceinline__ float gelu_erf_grad(float v) {
+  const float u = fabsf(v) * 0.70710678118654752f;
+  const float t = rcp_approx(fmaf(0.3275911f, u, 1.0f));
+  float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  const float e = ex2_approx(u * u * -1.4426950408889634f);   // exp(-v^2/2)
+  const float q = p * t * e;                                   // 0.5 * erfc(|v|/sqrt2)
+  const float cdf = v >= 0.f ? 1.0f - q : q;
+  return fmaf(v * 0.3989422804014327f, e, cdf);
 }
 __device__ __forceinline__ float sigmoid_acc(float v) { return rcp_approx(1.0f + ex2_approx(v * -1.4426950408889634f)); }
 __device__ __forceinline__ float tanh_acc(float v) { return fmaf(2.0f, sigmoid_acc(2.0f * v), -1.0f); }
@@ -555,9 +572,27 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_fused_kernel(const __gri
 #pragma unroll
           for (int e = 0; e < 16; ++e) v[e] += bv[e];
         }
+        if (a.o16_pre) {
+          __half* pp = a.o16_pre + static_cast<size_t>(row) * a.ldo + nt * BN + c0;
+          *reinterpret_cast<uint4*>(pp) =
+              make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+          *reinterpret_cast<uint4*>(pp + 8) =
+              make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+        }
         if (a.act == 1) {
 #pragma unroll
           for (int e = 0; e < 16; ++e) v[e] = gelu_erf(v[e]);
+        } else if (a.act == 2) {
+          const __half* ap = a.aux16 + static_cast<size_t>(row) * a.ldaux + nt * BN + c0;
+          const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(ap)), a1 = __ldg(reinterpret_cast<const uint4*>(ap + 8));
+          const __half2* h0 = reinterpret_cast<const __half2*>(&a0);
+          const __half2* h1 = reinterpret_cast<const __half2*>(&a1);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f0 = __half22float2(h0[e]), f1 = __half22float2(h1[e]);
+            v[2 * e] *= gelu_erf_grad(f0.x); v[2 * e + 1] *= gelu_erf_grad(f0.y);
+            v[8 + 2 * e] *= gelu_erf_grad(f1.x); v[8 + 2 * e + 1] *= gelu_erf_grad(f1.y);
+          }
         }
         *reinterpret_cast<uint4*>(dst + c0) =
             make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
@@ -639,6 +674,12 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_fused_kernel(const __gri
         tmem_ld_wait();
         if (etok >= 0) {
           float* op = a.yout + static_cast<size_t>(etok) * BN + c0;
+          if (a.raw_out) {
+            float* rp = a.raw_out + static_cast<size_t>(etok) * BN + c0;
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd)
+              *reinterpret_cast<float4*>(rp + qd * 4) = make_float4(v[qd * 4], v[qd * 4 + 1], v[qd * 4 + 2], v[qd * 4 + 3]);
+          }
 #pragma unroll
           for (int e = 0; e < 16; ++e) v[e] = (v[e] - mean_o) * rstd_o;
           if (a.eln_w) {
@@ -691,8 +732,20 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_fused_kernel(const __gri
           float hn[8], cn[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            cn[e] = sigmoid_acc(f[e]) * cpv[e] + sigmoid_acc(ig[e]) * tanh_acc(g[e]);
-            hn[e] = sigmoid_acc(og[e]) * tanh_acc(cn[e]);
+            f[e] = sigmoid_acc(f[e]); ig[e] = sigmoid_acc(ig[e]); og[e] = sigmoid_acc(og[e]); g[e] = tanh_acc(g[e]);
+            cn[e] = f[e] * cpv[e] + ig[e] * g[e];
+            hn[e] = og[e] * tanh_acc(cn[e]);
+          }
+          if (a.gates16) {
+            __half* gp = a.gates16 + static_cast<size_t>(etok) * 4 * C + ch0;
+            *reinterpret_cast<uint4*>(gp) =
+                make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
+            *reinterpret_cast<uint4*>(gp + C) =
+                make_uint4(pack_h2(ig[0], ig[1]), pack_h2(ig[2], ig[3]), pack_h2(ig[4], ig[5]), pack_h2(ig[6], ig[7]));
+            *reinterpret_cast<uint4*>(gp + 2 * C) =
+                make_uint4(pack_h2(og[0], og[1]), pack_h2(og[2], og[3]), pack_h2(og[4], og[5]), pack_h2(og[6], og[7]));
+            *reinterpret_cast<uint4*>(gp + 3 * C) =
+                make_uint4(pack_h2(g[0], g[1]), pack_h2(g[2], g[3]), pack_h2(g[4], g[5]), pack_h2(g[6], g[7]));
           }
           *reinterpret_cast<float4*>(a.cout + off) = make_float4(cn[0], cn[1], cn[2], cn[3]);
           *reinterpret_cast<float4*>(a.cout + off + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);

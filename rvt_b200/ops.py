@@ -115,3 +115,97 @@ def dws_conv_lstm(x: torch.Tensor, h_prev: Optional[torch.Tensor], c_prev: Optio
         _lib.ptr(pk['dw_w']), _lib.ptr(pk['dw_b']), pk['dws_mode'], dws_ks, _lib.ptr(h_new), _lib.ptr(c_new),
         _lib.ptr(scratch_xh), _lib.ptr(h16_out), _stream(x)), 'dws_conv_lstm')
     return h_new, c_new
+
+
+# =============================================================================================
+# Training building blocks (include/rvt_b200.h "Training step"); composed in rvt_b200/train.py.
+# All tensors CUDA + contiguous; f16 matrices are row-major with ld == number of columns.
+# =============================================================================================
+import os as _os
+TN_MODE = int(_os.environ.get('RVT_TN_MODE', '0'))   # rvt_gemm_tn operand form: 0 = MN-major tiles in place, 1 = transposed copies (K-major)
+
+
+def round_up(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+def linear_ex(a: torch.Tensor, m: int, k: int, n: int, w_packed: torch.Tensor, out: torch.Tensor,
+              bias: Optional[torch.Tensor] = None, act: int = 0, aux: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = a[:m, :k] @ W^T (+bias, act); a f16 [>=m, k]; out f16 [round_up(m,128), n] or f32 [m, n]."""
+    assert a.dtype == torch.float16 and a.numel() >= m * k
+    out_f32 = out.dtype == torch.float32
+    assert out.numel() >= (m if out_f32 else round_up(m, 128)) * n
+    if aux is not None:
+        assert aux.dtype == torch.float16 and aux.numel() >= round_up(m, 128) * n
+    _lib.check(_lib.lib().rvt_linear_ex(_lib.ptr(a), m, k, n, _lib.ptr(w_packed), _lib.ptr(bias), act, _lib.ptr(aux),
+                                        _lib.ptr(out), int(out_f32), _stream(a)), 'linear_ex')
+    return out
+
+
+def gemm_tn(a1: torch.Tensor, n1: int, a2: torch.Tensor, n2: int, m: int, g: torch.Tensor, transpose_out: bool = False,
+            mode: Optional[int] = None) -> None:
+    """g[n1, n2] += a1[:m, :n1]^T @ a2[:m, :n2]  (g f32; transpose_out: g is [n2, n1] and receives the transpose)."""
+    assert a1.dtype == torch.float16 and a2.dtype == torch.float16 and g.dtype == torch.float32
+    assert a1.numel() >= m * n1 and a2.numel() >= m * n2 and g.numel() == n1 * n2 and g.is_contiguous()
+    mode = TN_MODE if mode is None else mode
+    L = _lib.lib()
+    scratch = None
+    if mode == 1:
+        scratch = torch.empty(L.rvt_gemm_tn_scratch_elems(m, n1, n2), dtype=torch.float16, device=a1.device)
+    s_i, s_j = (1, n1) if transpose_out else (n2, 1)
+    _lib.check(L.rvt_gemm_tn(_lib.ptr(a1), n1, n1, _lib.ptr(a2), n2, n2, m, _lib.ptr(g), s_i, s_j, mode,
+                             _lib.ptr(scratch), _stream(a1)), 'gemm_tn')
+
+
+def ln_rows_f16(x: torch.Tensor, map_mode: int, part, ln_w, ln_b, do_ln: bool, eps: float, out16: torch.Tensor) -> None:
+    b, h, w, c = x.shape
+    ph, pw = part if part is not None else (1, 1)
+    _lib.check(_lib.lib().rvt_ln_rows_f16(_lib.ptr(x), map_mode, b, h, w, c, ph, pw, _lib.ptr(ln_w), _lib.ptr(ln_b),
+                                          int(do_ln), eps, _lib.ptr(out16), _stream(x)), 'ln_rows_f16')
+
+
+def ln_bwd(x: Optional[torch.Tensor], dy: torch.Tensor, shape, map_mode: int, part, ln_w, do_ln: bool, eps: float,
+           dres: Optional[torch.Tensor], dx16: Optional[torch.Tensor], dw_acc, db_acc) -> None:
+    b, h, w, c = shape
+    ph, pw = part if part is not None else (1, 1)
+    _lib.check(_lib.lib().rvt_ln_bwd(_lib.ptr(x), _lib.ptr(dy), int(dy.dtype == torch.float16), map_mode, b, h, w, c, ph, pw,
+                                     _lib.ptr(ln_w), int(do_ln), eps, _lib.ptr(dres), _lib.ptr(dx16), _lib.ptr(dw_acc),
+                                     _lib.ptr(db_acc), _stream(dy)), 'ln_bwd')
+
+
+def gather_cast(dres: torch.Tensor, map_mode: int, part, gamma, d0, d1) -> None:
+    b, h, w, c = dres.shape
+    ph, pw = part if part is not None else (1, 1)
+    _lib.check(_lib.lib().rvt_gather_cast(_lib.ptr(dres), map_mode, b, h, w, c, ph, pw, _lib.ptr(gamma), _lib.ptr(d0),
+                                          _lib.ptr(d1), _stream(dres)), 'gather_cast')
+
+
+def attn_core_bwd(qkv, dout, dqkv, shape, part, dim_head: int) -> None:
+    b, h, w, c = shape
+    _lib.check(_lib.lib().rvt_attn_core_bwd(_lib.ptr(qkv), _lib.ptr(dout), _lib.ptr(dqkv), b, h, w, c, part[0], part[1],
+                                            dim_head, _stream(qkv)), 'attn_core_bwd')
+
+
+def lstm_gates_bwd(gates, c_prev, c_new, dh, dc, n_tokens: int, dim: int, dpre, dc_prev) -> None:
+    _lib.check(_lib.lib().rvt_lstm_gates_bwd(_lib.ptr(gates), _lib.ptr(c_prev), _lib.ptr(c_new), _lib.ptr(dh), _lib.ptr(dc),
+                                             n_tokens, dim, _lib.ptr(dpre), _lib.ptr(dc_prev), _stream(gates)),
+               'lstm_gates_bwd')
+
+
+def im2col(x: torch.Tensor, x_is_nchw: bool, ksize: int, stride: int, pad: int, hout: int, wout: int, col: torch.Tensor) -> None:
+    if x_is_nchw:
+        b, cin, hin, win = x.shape
+    else:
+        b, hin, win, cin = x.shape
+    _lib.check(_lib.lib().rvt_im2col(_lib.ptr(x), _IN_DTYPES[x.dtype], int(x_is_nchw), b, cin, hin, win, ksize, stride, pad,
+                                     hout, wout, _lib.ptr(col), _stream(x)), 'im2col')
+
+
+def col2im(dcol: torch.Tensor, b, cin, hin, win, ksize, stride, pad, hout, wout, d_in: torch.Tensor) -> None:
+    _lib.check(_lib.lib().rvt_col2im(_lib.ptr(dcol), b, cin, hin, win, ksize, stride, pad, hout, wout, _lib.ptr(d_in),
+                                     _stream(dcol)), 'col2im')
+
+
+def colsum(a: torch.Tensor, m: int, n: int, acc: torch.Tensor) -> None:
+    assert a.dtype == torch.float16 and acc.dtype == torch.float32 and acc.numel() >= n
+    _lib.check(_lib.lib().rvt_colsum(_lib.ptr(a), m, n, n, _lib.ptr(acc), _stream(a)), 'colsum')

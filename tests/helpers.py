@@ -63,3 +63,33 @@ def check_against_golden(name, case, step_fn, tol, device='cpu', input_dtype=tor
             got_sum = float(hh.detach().double().sum().cpu())
             assert abs(got_sum - ref_sum) <= max(tol, 1e-6) * ref_abs, (name, step, s, got_sum, ref_sum)
     return worst
+
+
+# ---------------------------------------------------------------------------------------------
+# training-step parity: one deterministic scalar loss over an unrolled sequence (features of every
+# step and stage, plus the final cell states), used identically for the reference (golden minting),
+# the oracle and the CUDA path.  Sum-based so gradient magnitudes stay O(0.1-1) (no fp16 underflow).
+# ---------------------------------------------------------------------------------------------
+def train_loss(outs_per_step, final_states) -> torch.Tensor:
+    loss = 0.0
+    for t, feats in enumerate(outs_per_step):
+        for s in range(1, 5):
+            f = feats[s].float()
+            loss = loss + (0.5 + 0.25 * t) / s * 0.5 * ((f - 0.1) ** 2).sum() / f.shape[0]
+    for (_, c) in final_states:
+        loss = loss + 0.1 * (c.float() ** 2).sum() / c.shape[0]
+    return loss
+
+
+GRAD_CASES = {
+    # name -> (backbone case, unrolled steps)
+    'tiny_p6': 3,
+    'small_dh24': 2,
+}
+GRAD_SUB = 29   # stride of the committed gradient subsamples
+
+
+def case_inputs(case, steps):
+    spec = spec_of(case)
+    return [bo.synth_events_tensor(case['seed'] * 1000 + t, case['batch'], spec.input_channels, case['height'], case['width'])
+            for t in range(steps)]

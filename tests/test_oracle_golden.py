@@ -66,3 +66,26 @@ def test_time_bin_fp32_edges():
     t = np.array([0, 4999, 5000, 49999, 50000], np.int64)
     assert vo.time_bin_index(t, 10).tolist() == [0, 0, 1, 9, 9]
     assert vo.time_bin_index(np.array([7, 7, 7], np.int64), 10).tolist() == [0, 0, 0]
+
+
+@pytest.mark.parametrize('name', ['tiny_p6', 'small_dh24'])
+def test_backbone_oracle_gradients_match_reference_golden(name):
+    """Training-step pin: autograd through the oracle reproduces the REFERENCE's gradients
+    (tests/golden/backbone_grads_*.npz, minted by oracle/make_golden.py)."""
+    from tests.helpers import GRAD_CASES, GRAD_SUB, case_inputs, train_loss
+    case = BACKBONE_CASES[name]
+    spec = spec_of(case)
+    gold = np.load(os.path.join(GOLD, f'backbone_grads_{name}.npz'))
+    params = {k: v.clone().requires_grad_(True) for k, v in bo.synth_params(spec, case['seed']).items()}
+    outs, st = [], None
+    for x in case_inputs(case, GRAD_CASES[name]):
+        o, st = bo.backbone_forward(x.float(), st, params, spec)
+        outs.append(o)
+    loss = train_loss(outs, st)
+    loss.backward()
+    assert abs(float(loss.detach()) - float(gold['loss'])) <= 1e-5 * abs(float(gold['loss']))
+    for k, p in params.items():
+        ref = torch.from_numpy(gold['g.' + k])
+        got = p.grad.contiguous().reshape(-1)[::GRAD_SUB]
+        assert float((got - ref).norm()) <= 1e-4 * float(gold['n.' + k]) + 1e-12, k
+        assert abs(float(p.grad.double().norm()) - float(gold['n.' + k])) <= 1e-4 * float(gold['n.' + k]) + 1e-12, k
