@@ -141,12 +141,169 @@ def run_reference(args, rank, world):
     }))
 
 
+def make_uint8_sequence(seed, length, batch):
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    shape = (length, batch, IN_C, IN_H, IN_W)
+    seq = torch.randint(1, 11, shape, generator=g, dtype=torch.uint8)            # counts 1..10 ...
+    seq.mul_(torch.randint(0, 10, shape, generator=g, dtype=torch.uint8) == 0)   # ... on ~10 % of the bins
+    return seq
+
+
+def run_reference_gpu(args, rank, world, local_rank):
+    """Informational arm (the denominator of north_star's '>= 10x PyTorch-eager on one B200'): the reference's
+    op-by-op PyTorch path (oracle port = the same ATen/cuDNN/cuBLAS calls) on the GPU under fp16 autocast and
+    inference_mode, same workload, inputs resident.  Not the driver's reference arm (that is --impl reference, CPU)."""
+    if rank != 0:
+        return
+    from oracle import backbone_oracle as bo
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    spec = rvt_b_spec()
+    params = {k: v.to(dev) for k, v in bo.synth_params(spec, 0).items()}
+    seq = make_uint8_sequence(1234, SEQ_LEN, B_PER_GPU).to(dev)
+
+    def step():
+        st = None
+        for t in range(SEQ_LEN):
+            x = torch.nn.functional.pad(seq[t].float(), (0, PAD_W - IN_W, 0, PAD_H - IN_H))   # modules/detection.py:133-134
+            _, st = bo.backbone_forward(x, st, params, spec)
+        return st
+
+    with torch.inference_mode(), torch.autocast('cuda', dtype=torch.float16):
+        for _ in range(max(args.warmup, 3)):
+            step()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    v = B_PER_GPU * SEQ_LEN * args.steps / (ms * 1e-3)
+    print(json.dumps({
+        'impl': 'reference-gpu', 'metric': METRIC, 'value': v, 'unit': 'frames/s', 'n_gpus': 1, 'steps': args.steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f16 autocast', 'data': 'synthetic',
+        'config': {'workload': 'RVT-Base 1Mpx 360x640 (padded 384x640) seq_len=21 bs=8 inference, PyTorch eager on the GPU '
+                               '(oracle port of the reference op sequence), fp16 autocast, inputs resident'}}))
+
+
+TRAIN_METRIC = 'RVT-B 1Mpx seq_len=21 backbone training frames/sec'
+LOSS_SCALE = 65536.0      # static stand-in for the harness' GradScaler (precision 16, config/general.yaml:6)
+
+
+def run_train(args, rank, world, local_rank):
+    """BASELINE configs[2]: RVT-Base 1Mpx training step, TBPTT over seq_len 21, 3 samples per GPU, batch-sharded,
+    ONE NCCL all-reduce over the flat gradient buffer, fused Adam on the backbone parameters.  A step = forward of
+    21 timesteps (states carried) + synthetic loss on the last step's four feature maps + backward through all 21
+    timesteps + gradient all-reduce + unscale + optimizer step."""
+    import torch.distributed as dist
+    import rvt_b200
+    from rvt_b200 import sharding
+    from oracle import backbone_oracle as bo     # synthetic parameter generator only
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'
+        dist.init_process_group('nccl', device_id=dev)
+    B = args.train_batch
+    spec = rvt_b_spec()
+    model = rvt_b200.RNNDetector(make_cfg(spec))
+    model.load_state_dict(bo.synth_params(spec, 0), strict=True)
+    model = model.to(dev).train()
+    model.pad_to_hw = (PAD_H, PAD_W)
+    lo, hi = sharding.batch_slice(B * world, rank, world)
+    n_seq = 4                                                        # rotate sequences: 4 x 290 MB of uint8 inputs > L2
+    seqs = [make_uint8_sequence(4321 + lo * 10 + i, SEQ_LEN, B).to(dev) for i in range(n_seq)]
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=2e-4, fused=True)
+    ev = {k: [torch.cuda.Event(enable_timing=True) for _ in range(2)] for k in ('fwd', 'bwd', 'ar', 'opt')}
+    acc_ms = {k: 0.0 for k in ev}
+    counter = [0]
+
+    def step(record=False):
+        seq = seqs[counter[0] % n_seq]
+        counter[0] += 1
+        opt.zero_grad(set_to_none=True)
+        if record:
+            ev['fwd'][0].record()
+        st, out = None, None
+        for t in range(SEQ_LEN):
+            out, st = model(seq[t], st)
+        loss = sum((out[s].float() ** 2).mean() for s in (1, 2, 3, 4)) * LOSS_SCALE
+        if record:
+            ev['fwd'][1].record(); ev['bwd'][0].record()
+        loss.backward()
+        if record:
+            ev['bwd'][1].record(); ev['ar'][0].record()
+        n_coll = sharding.allreduce_gradients(params)
+        if record:
+            ev['ar'][1].record(); ev['opt'][0].record()
+        torch._foreach_mul_([p.grad for p in params if p.grad is not None], 1.0 / LOSS_SCALE)
+        opt.step()
+        if record:
+            ev['opt'][1].record()
+        return loss, n_coll
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        loss, n_coll = step()
+    assert torch.isfinite(loss.detach()).item(), 'non-finite training loss'
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss, n_coll = step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):                                               # phase breakdown (separate, event-instrumented steps)
+        step(record=True)
+        torch.cuda.synchronize(dev)
+        for k in ev:
+            acc_ms[k] += ev[k][0].elapsed_time(ev[k][1]) / 2
+    grad_ok = all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in params)
+    frames = B * SEQ_LEN * args.steps * world
+    if rank == 0:
+        n_par = sum(p.numel() for p in params)
+        print(json.dumps({
+            'metric': TRAIN_METRIC, 'value': frames / (ms * 1e-3), 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic',
+            'config': {'workload': f'RVT-Base 1Mpx {B}x20x360x640 uint8 per GPU (model res 384x640) TBPTT seq_len=21 training step: '
+                                   'fwd + bwd through 21 timesteps + grad all-reduce + fused Adam (backbone only)',
+                       'global_batch': B * world, 'frames_per_step': B * SEQ_LEN,
+                       'l2_policy': f'{n_seq} rotating input sequences ({n_seq * seqs[0].numel() >> 20} MB) > L2',
+                       'parallelism': f'batch-sharded x{world}; {n_coll} NCCL all-reduce of {n_par * 4 >> 20} MB fp32 gradients per step',
+                       'loss_scale': LOSS_SCALE},
+            'clocks': clocks, 'phases_ms': acc_ms, 'final_loss': float(loss.detach()) / LOSS_SCALE, 'grads_finite': grad_ok,
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference', 'reference-gpu'])
+    ap.add_argument('--mode', default='infer', choices=['infer', 'train'],
+                    help="infer: BASELINE configs[1] (the headline metric); train: configs[2], the batch-sharded training step")
+    ap.add_argument('--train-batch', type=int, default=3, help='samples per GPU in --mode train (BASELINE configs[2]: 3)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch eagerly instead of replaying CUDA graphs')
     ap.add_argument('--no-wavefront', action='store_true', help='run the four stages strictly one after the other')
@@ -158,6 +315,12 @@ def main():
 
     if args.impl == 'reference':
         run_reference(args, rank, world)
+        return
+    if args.impl == 'reference-gpu':
+        run_reference_gpu(args, rank, world, local_rank)
+        return
+    if args.mode == 'train':
+        run_train(args, rank, world, local_rank)
         return
 
     import torch.distributed as dist

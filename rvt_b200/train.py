@@ -364,10 +364,20 @@ class _GradSink(torch.autograd.Function):
     def backward(ctx, _dtoken):
         eng = ctx.engine
         grads = eng.drain(ctx.device)
-        out = []
-        for i, (name, p) in enumerate(zip(eng.names, eng.params)):
-            g = grads.get(name) if ctx.needs_input_grad[i + 1] else None
-            out.append(None if g is None else g.to(p.dtype).reshape(p.shape))
+        # hand the gradients to autograd as views of ONE flat fp32 buffer (parameter order): AccumulateGrad keeps
+        # them as .grad, so the data-parallel reduction is a single NCCL all-reduce over that buffer with no
+        # flatten / unflatten copies (rvt_b200.sharding.allreduce_gradients).
+        want = [(i, name, p) for i, (name, p) in enumerate(zip(eng.names, eng.params))
+                if ctx.needs_input_grad[i + 1] and name in grads]
+        out = [None] * len(eng.params)
+        if want:
+            flat = torch.empty(sum(p.numel() for _, _, p in want), dtype=torch.float32, device=ctx.device)
+            off = 0
+            for i, name, p in want:
+                seg = flat[off:off + p.numel()].view(p.shape)
+                seg.copy_(grads[name].reshape(p.shape))
+                out[i] = seg if p.dtype == torch.float32 else seg.to(p.dtype)
+                off += p.numel()
         return (None, *out)
 
 

@@ -60,3 +60,78 @@ def test_slices_are_balanced_partitions():
             sizes = [b - a for a, b in parts]
             assert max(sizes) - min(sizes) <= 1
     assert sharding.window_shares(5, 2) == [(0, 3), (3, 5)]
+
+
+# ---- training step: single flat all-reduce of the gradients ----
+def _grad_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(0)
+    res = {}
+    for layout in ('flat', 'separate'):
+        ps = [torch.nn.Parameter(torch.zeros(4, 3)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(2, 2))]
+        if layout == 'flat':
+            flat = torch.arange(21, dtype=torch.float32) * (rank + 1)
+            off = 0
+            for p in ps:
+                p.grad = flat[off:off + p.numel()].view(p.shape)
+                off += p.numel()
+            assert sharding.flat_gradient_view(ps) is not None
+        else:
+            for i, p in enumerate(ps):
+                p.grad = torch.full(p.shape, float((rank + 1) * (i + 1)))
+            assert sharding.flat_gradient_view(ps) is None
+        n = sharding.allreduce_gradients(ps)
+        res[layout] = (n, [p.grad.flatten().tolist() for p in ps])
+    q.put((rank, res))
+    dist.destroy_process_group()
+
+
+def test_allreduce_gradients_two_ranks_gloo():
+    world = 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank in range(world):
+        n, g = res[rank]['flat']
+        assert n == 1                                              # ONE collective
+        assert sum(g, []) == [i * 1.5 for i in range(21)]          # mean of x1 and x2
+        n, g = res[rank]['separate']
+        assert n == 1
+        assert g == [[1.5] * 12, [3.0] * 5, [4.5] * 4]
+
+
+def test_grad_sink_hands_autograd_one_flat_buffer():
+    """rvt_b200.train._GradSink: accumulators -> parameter gradients as views of one allocation that autograd keeps
+    as .grad (so the all-reduce needs no flatten copy); draining zeroes the accumulators; a second backward
+    accumulates into the same buffer."""
+    import rvt_b200
+    from rvt_b200 import train
+    from oracle import backbone_oracle as bo
+    from tests.golden_configs import BACKBONE_CASES, spec_of
+    from tests.test_host_cpu import make_cfg
+    spec = spec_of(BACKBONE_CASES['tiny_p6'])
+    m = rvt_b200.RNNDetector(make_cfg(spec))
+    m.load_state_dict(bo.synth_params(spec, 1), strict=True)
+    eng = m._train_engine()
+    dev = torch.device('cpu')
+    for rep in range(2):
+        acc = eng.acc(dev)
+        for v in acc.values():
+            v.fill_(1.0)
+        eng.dirty = True
+        tok = train._GradSink.apply(eng, *eng.params)
+        tok.sum().backward()
+        assert float(eng._acc_flat.abs().sum()) == 0.0 and not eng.dirty
+        flat = sharding.flat_gradient_view(list(m.parameters()))
+        assert flat is not None and flat.numel() == sum(p.numel() for p in m.parameters())
+        w = m.stages[0].lstm.conv1x1.weight
+        assert torch.equal(w.grad, torch.full_like(w, float(rep + 1)))     # lstm.G passes through unchanged
