@@ -29,6 +29,8 @@ METRIC = 'RVT-B 1Mpx seq_len=21 backbone frames/sec'
 B_PER_GPU, SEQ_LEN, IN_C, IN_H, IN_W, PAD_H, PAD_W = 8, 21, 20, 360, 640, 384, 640
 # per timestep: S1 s2d+conv, 4 fused attn/mlp, lstm; S2 conv, 4 fused, lstm; S3/S4 conv+ln, 2 x (ln,qkv,core,proj,ln,fc1,fc2), lstm
 LAUNCHES_PER_TIMESTEP = (2 + 4 + 1) + (1 + 4 + 1) + 2 * (2 + 2 * 7 + 1)
+TRAIN_METRIC = 'RVT-B 1Mpx seq_len=21 backbone training frames/sec'
+LOSS_SCALE = 65536.0      # static stand-in for the harness' GradScaler (precision 16, config/general.yaml:6)
 GFLOP_PER_FRAME = 20.62                                 # BASELINE.md §3 (algorithmic, MAC = 2 FLOP)
 
 
@@ -160,6 +162,42 @@ def run_reference_gpu(args, rank, world, local_rank):
     torch.cuda.set_device(dev)
     spec = rvt_b_spec()
     params = {k: v.to(dev) for k, v in bo.synth_params(spec, 0).items()}
+    if args.mode == 'train':
+        # the same training step as run_train (fwd 21 timesteps + loss + bwd + unscale + fused Adam), PyTorch eager + autograd
+        B = args.train_batch
+        plist = [v.requires_grad_(True) for v in params.values()]
+        opt = torch.optim.Adam(plist, lr=2e-4, fused=True)
+        seq = make_uint8_sequence(4321, SEQ_LEN, B).to(dev)
+
+        def tstep():
+            opt.zero_grad(set_to_none=True)
+            st, out = None, None
+            with torch.autocast('cuda', dtype=torch.float16):
+                for t in range(SEQ_LEN):
+                    x = torch.nn.functional.pad(seq[t].float(), (0, PAD_W - IN_W, 0, PAD_H - IN_H))
+                    out, st = bo.backbone_forward(x, st, params, spec)
+            loss = sum((out[s].float() ** 2).mean() for s in (1, 2, 3, 4)) * LOSS_SCALE
+            loss.backward()
+            torch._foreach_mul_([p.grad for p in plist], 1.0 / LOSS_SCALE)
+            opt.step()
+
+        for _ in range(max(args.warmup, 3)):
+            tstep()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            tstep()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        print(json.dumps({
+            'impl': 'reference-gpu', 'metric': TRAIN_METRIC, 'value': B * SEQ_LEN * args.steps / (ms * 1e-3), 'unit': 'frames/s',
+            'n_gpus': 1, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
+            'higher_is_better': True, 'dtype': 'f16 autocast', 'data': 'synthetic',
+            'config': {'workload': f'RVT-Base 1Mpx bs={B} TBPTT seq_len=21 training step, PyTorch eager + autograd on the GPU '
+                                   '(oracle port of the reference op sequence), fp16 autocast'}}))
+        return
     seq = make_uint8_sequence(1234, SEQ_LEN, B_PER_GPU).to(dev)
 
     def step():
@@ -189,8 +227,6 @@ def run_reference_gpu(args, rank, world, local_rank):
                                '(oracle port of the reference op sequence), fp16 autocast, inputs resident'}}))
 
 
-TRAIN_METRIC = 'RVT-B 1Mpx seq_len=21 backbone training frames/sec'
-LOSS_SCALE = 65536.0      # static stand-in for the harness' GradScaler (precision 16, config/general.yaml:6)
 
 
 def run_train(args, rank, world, local_rank):

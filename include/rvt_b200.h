@@ -169,9 +169,10 @@ int rvt_ln_bwd(const float* x, const void* dy, int dy_is_f16, int map_mode, int 
 /* d0[row] = f16(dres[token(row)]), d1[row] = f16(gamma * dres[token(row)])  (LayerScale backward, maxvit.py:45-53). */
 int rvt_gather_cast(const float* dres, int map_mode, int batch, int height, int width, int dim, int ph, int pw,
                     const float* gamma, void* d0, void* d1, void* stream);
-/* softmax(QK^T)V backward per (partition group, head) (maxvit.py:349-352): qkv, dqkv f16 [rows,3C]; dout f16 [rows,C]. */
-int rvt_attn_core_bwd(const void* qkv, const void* dout, void* dqkv, int batch, int height, int width, int dim, int ph,
-                      int pw, int dim_head, void* stream);
+/* softmax(QK^T)V backward per (partition group, head) (maxvit.py:349-352): qkv, dqkv f16 [rows,3C]; o (the forward
+ * output of the core) and dout f16 [rows,C]. */
+int rvt_attn_core_bwd(const void* qkv, const void* o, const void* dout, void* dqkv, int batch, int height, int width,
+                      int dim, int ph, int pw, int dim_head, void* stream);
 /* Conv-LSTM gates backward (rnn.py:57-67): dpre f16 [n,4C] ([f|i|o|g] = rows of conv1x1.weight), dc_prev f32 [n,C]. */
 int rvt_lstm_gates_bwd(const void* gates, const float* c_prev, const float* c_new, const float* dh, const float* dc,
                        int64_t n_tokens, int dim, void* dpre, float* dc_prev, void* stream);

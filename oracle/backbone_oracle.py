@@ -138,7 +138,7 @@ def attention_branch(x: Tensor, p, prefix, part, window, dim_head, eps, od=None)
     ng, pp = idx.shape
     yp = self_attention(xp.reshape(b * ng, pp, c), p, prefix + 'self_attn.', dim_head, od)
     out = torch.empty_like(flat)
-    out[:, idx.reshape(-1)] = yp.reshape(b, ng * pp, c)
+    out[:, idx.reshape(-1)] = yp.reshape(b, ng * pp, c).to(out.dtype)   # (dtype cast only matters under autocast)
     return out.reshape(b, h, w, c)
 
 

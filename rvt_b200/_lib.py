@@ -42,7 +42,7 @@ SIGNATURES = {
     'rvt_ln_rows_f16': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _f, _vp, _vp]),
     'rvt_ln_bwd': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp]),
     'rvt_gather_cast': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
-    'rvt_attn_core_bwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    'rvt_attn_core_bwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'rvt_lstm_gates_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp]),
     'rvt_im2col': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     'rvt_col2im': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),

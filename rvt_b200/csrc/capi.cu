@@ -736,13 +736,14 @@ int rvt_gather_cast(const float* dres, int map_mode, int batch, int height, int 
   return static_cast<int>(cudaGetLastError());
 }
 
-int rvt_attn_core_bwd(const void* qkv, const void* dout, void* dqkv, int batch, int height, int width, int dim, int ph, int pw,
-                      int dim_head, void* stream) {
-  if (!qkv || !dout || !dqkv) return kErrBadArg;
+int rvt_attn_core_bwd(const void* qkv, const void* o, const void* dout, void* dqkv, int batch, int height, int width, int dim,
+                      int ph, int pw, int dim_head, void* stream) {
+  if (!qkv || !o || !dout || !dqkv) return kErrBadArg;
   const int P = ph * pw, rpg = rvt_rows_per_group(P);
   if (rpg < 0 || dim_head > 32 || dim % dim_head != 0 || height % ph || width % pw) return kErrUnsupported;
   AttnBwdArgs a{};
-  a.qkv = static_cast<const __half*>(qkv); a.dout = static_cast<const __half*>(dout); a.dqkv = static_cast<__half*>(dqkv);
+  a.qkv = static_cast<const __half*>(qkv); a.o = static_cast<const __half*>(o);
+  a.dout = static_cast<const __half*>(dout); a.dqkv = static_cast<__half*>(dqkv);
   a.C = dim; a.dh = dim_head; a.nh = dim / dim_head; a.P = P; a.rows_per_win = rpg;
   a.n_groups = batch * (height / ph) * (width / pw);
   a.scale = 1.0f / sqrtf(static_cast<float>(dim_head));
@@ -798,11 +799,14 @@ int rvt_col2im(const void* dcol, int batch, int cin, int hin, int win, int ksize
 }
 
 int rvt_colsum(const void* a, int64_t m, int n, int ld, float* acc, void* stream) {
-  if (!a || !acc || n % 2 != 0 || ld % 2 != 0) return kErrBadArg;
+  if (!a || !acc || n % 8 != 0 || ld % 8 != 0 || n > 2048 || n < 8) return kErrBadArg;
   if (m <= 0) return 0;
-  const int rows_per_block = 512;
-  colsum_kernel<<<dim3(cdiv(n, 64), cdiv(m, rows_per_block)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(a), m, n, ld, acc, rows_per_block);
+  int sms = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  int64_t rows_per_block = (m + 2 * sms - 1) / (2 * sms);
+  if (rows_per_block < 32) rows_per_block = 32;
+  colsum_kernel<<<cdiv(m, rows_per_block), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(a), m, n, ld, acc, static_cast<int>(rows_per_block));
   return static_cast<int>(cudaGetLastError());
 }
 

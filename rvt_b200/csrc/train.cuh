@@ -396,13 +396,48 @@ __global__ void __launch_bounds__(256) gather_cast_kernel(const float* __restric
 // fp32 SIMT in shared memory: the tiles are tiny (P <= 128, dh <= 32).
 // ----------------------------------------------------------------------------------------
 struct AttnBwdArgs {
-  const __half* qkv; const __half* dout; __half* dqkv;
+  const __half* qkv; const __half* o; const __half* dout; __half* dqkv;
   int C, dh, nh, P, rows_per_win, n_groups;
   float scale;
 };
 constexpr int kAbPitch = 33;   // dh <= 32
 __host__ __device__ inline size_t attn_bwd_smem_bytes(int P) {
   return (static_cast<size_t>(4) * P * kAbPitch + static_cast<size_t>(P) * (P + 1) + P) * sizeof(float);
+}
+
+// C(i, j) = sum_k A(i, k) * B(j, k) on TM x TN register tiles (operands in shared memory through accessors)
+template <int TM, int TN, class FA, class FB, class FC>
+__device__ __forceinline__ void tile_mm(int M, int N, int K, FA fa, FB fb, FC fc, int tid, int nthreads) {
+  const int tm = (M + TM - 1) / TM, tn = (N + TN - 1) / TN;
+  for (int t = tid; t < tm * tn; t += nthreads) {
+    const int i0 = (t / tn) * TM, j0 = (t - (t / tn) * tn) * TN;
+    int ir[TM], jr[TN];
+#pragma unroll
+    for (int r = 0; r < TM; ++r) ir[r] = min(i0 + r, M - 1);
+#pragma unroll
+    for (int q = 0; q < TN; ++q) jr[q] = min(j0 + q, N - 1);
+    float acc[TM][TN];
+#pragma unroll
+    for (int r = 0; r < TM; ++r)
+#pragma unroll
+      for (int q = 0; q < TN; ++q) acc[r][q] = 0.f;
+    for (int k = 0; k < K; ++k) {
+      float av[TM], bv[TN];
+#pragma unroll
+      for (int r = 0; r < TM; ++r) av[r] = fa(ir[r], k);
+#pragma unroll
+      for (int q = 0; q < TN; ++q) bv[q] = fb(jr[q], k);
+#pragma unroll
+      for (int r = 0; r < TM; ++r)
+#pragma unroll
+        for (int q = 0; q < TN; ++q) acc[r][q] = fmaf(av[r], bv[q], acc[r][q]);
+    }
+#pragma unroll
+    for (int r = 0; r < TM; ++r)
+#pragma unroll
+      for (int q = 0; q < TN; ++q)
+        if (i0 + r < M && j0 + q < N) fc(i0 + r, j0 + q, acc[r][q]);
+  }
 }
 
 __global__ void __launch_bounds__(256) attn_core_bwd_kernel(const __grid_constant__ AttnBwdArgs a) {
@@ -413,10 +448,12 @@ __global__ void __launch_bounds__(256) attn_core_bwd_kernel(const __grid_constan
   float* sV = sK + P * kAbPitch;
   float* sD = sV + P * kAbPitch;      // dO
   float* sS = sD + P * kAbPitch;      // S -> A -> dS
+  float* sDelta = sS + P * SP;        // rowsum(dO * O) = rowsum(dA * A)
   const int g = blockIdx.x, hd = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const size_t row0 = static_cast<size_t>(g) * a.rows_per_win;
   const int C3 = 3 * a.C;
+  const float scale = a.scale;
 
   for (int idx = tid; idx < P * dh; idx += 256) {
     const int i = idx / dh, d = idx - i * dh;
@@ -427,13 +464,15 @@ __global__ void __launch_bounds__(256) attn_core_bwd_kernel(const __grid_constan
     sD[i * kAbPitch + d] = __half2float(a.dout[(row0 + i) * a.C + hd * dh + d]);
   }
   __syncthreads();
-  // S = scale * Q K^T
-  for (int idx = tid; idx < P * P; idx += 256) {
-    const int i = idx / P, j = idx - i * P;
+  for (int i = warp; i < P; i += 8) {
     float s = 0.f;
-    for (int d = 0; d < dh; ++d) s = fmaf(sQ[i * kAbPitch + d], sK[j * kAbPitch + d], s);
-    sS[i * SP + j] = s * a.scale;
+    if (lane < dh) s = sD[i * kAbPitch + lane] * __half2float(a.o[(row0 + i) * a.C + hd * dh + lane]);
+    s = warp_sum(s);
+    if (lane == 0) sDelta[i] = s;
   }
+  // S = scale * Q K^T
+  tile_mm<4, 4>(P, P, dh, [&](int i, int k) { return sQ[i * kAbPitch + k]; }, [&](int j, int k) { return sK[j * kAbPitch + k]; },
+                [&](int i, int j, float v) { sS[i * SP + j] = v * scale; }, tid, 256);
   __syncthreads();
   // row softmax
   for (int i = warp; i < P; i += 8) {
@@ -449,48 +488,18 @@ __global__ void __launch_bounds__(256) attn_core_bwd_kernel(const __grid_constan
   }
   __syncthreads();
   // dV[j][d] = sum_i A[i][j] dO[i][d]
-  for (int idx = tid; idx < P * dh; idx += 256) {
-    const int j = idx / dh, d = idx - j * dh;
-    float s = 0.f;
-    for (int i = 0; i < P; ++i) s = fmaf(sS[i * SP + j], sD[i * kAbPitch + d], s);
-    a.dqkv[(row0 + j) * C3 + hd * 3 * dh + 2 * dh + d] = __float2half_rn(s);
-  }
+  tile_mm<2, 4>(P, dh, P, [&](int j, int i) { return sS[i * SP + j]; }, [&](int d, int i) { return sD[i * kAbPitch + d]; },
+                [&](int j, int d, float v) { a.dqkv[(row0 + j) * C3 + hd * 3 * dh + 2 * dh + d] = __float2half_rn(v); }, tid, 256);
   __syncthreads();
-  // dS[i][j] = A[i][j] * (dA[i][j] - sum_j dA[i][j] A[i][j]) * scale,  dA[i][j] = sum_d dO[i][d] V[j][d]
-  for (int i = warp; i < P; i += 8) {
-    float da[4];
-    float delta = 0.f;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int j = lane + 32 * q;
-      da[q] = 0.f;
-      if (j < P) {
-        float s = 0.f;
-        for (int d = 0; d < dh; ++d) s = fmaf(sD[i * kAbPitch + d], sV[j * kAbPitch + d], s);
-        da[q] = s;
-        delta += s * sS[i * SP + j];
-      }
-    }
-    delta = warp_sum(delta);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int j = lane + 32 * q;
-      if (j < P) sS[i * SP + j] = sS[i * SP + j] * (da[q] - delta) * a.scale;
-    }
-  }
+  // dS[i][j] = A[i][j] * (dA[i][j] - delta_i) * scale,  dA[i][j] = sum_d dO[i][d] V[j][d]   (in place over A)
+  tile_mm<4, 4>(P, P, dh, [&](int i, int k) { return sD[i * kAbPitch + k]; }, [&](int j, int k) { return sV[j * kAbPitch + k]; },
+                [&](int i, int j, float v) { sS[i * SP + j] = sS[i * SP + j] * (v - sDelta[i]) * scale; }, tid, 256);
   __syncthreads();
   // dQ[i][d] = sum_j dS[i][j] K[j][d];  dK[j][d] = sum_i dS[i][j] Q[i][d]
-  for (int idx = tid; idx < P * dh; idx += 256) {
-    const int i = idx / dh, d = idx - i * dh;
-    float sq = 0.f, sk = 0.f;
-    for (int j = 0; j < P; ++j) {
-      sq = fmaf(sS[i * SP + j], sK[j * kAbPitch + d], sq);
-      sk = fmaf(sS[j * SP + i], sQ[j * kAbPitch + d], sk);
-    }
-    __half* op = a.dqkv + (row0 + i) * C3 + hd * 3 * dh + d;
-    op[0] = __float2half_rn(sq);
-    op[dh] = __float2half_rn(sk);
-  }
+  tile_mm<2, 4>(P, dh, P, [&](int i, int j) { return sS[i * SP + j]; }, [&](int d, int j) { return sK[j * kAbPitch + d]; },
+                [&](int i, int d, float v) { a.dqkv[(row0 + i) * C3 + hd * 3 * dh + d] = __float2half_rn(v); }, tid, 256);
+  tile_mm<2, 4>(P, dh, P, [&](int j, int i) { return sS[i * SP + j]; }, [&](int d, int i) { return sQ[i * kAbPitch + d]; },
+                [&](int j, int d, float v) { a.dqkv[(row0 + j) * C3 + hd * 3 * dh + dh + d] = __float2half_rn(v); }, tid, 256);
   // padding rows of this head: zeros
   const int pad = a.rows_per_win - P;
   for (int idx = tid; idx < pad * 3 * dh; idx += 256) {
@@ -616,28 +625,33 @@ __global__ void __launch_bounds__(256) col2im_kernel(const __half* __restrict__ 
   *reinterpret_cast<float2*>(d_in + static_cast<size_t>(pix) * g.Cin + ci) = make_float2(s0, s1);
 }
 
-// acc[n] += sum_m a[m, n]   (bias gradients).  fp16 [M, N] with leading dimension ld; block = 64 columns x row slab.
+// acc[n] += sum_m a[m, n]   (bias gradients).  fp16 [M, N] (ld), N % 8 == 0, N <= 2048.  16-byte loads: thread = 8 columns
+// of one row slot; a CTA sweeps rows [m_lo, m_hi), reduces its row slots through shared memory, one atomicAdd per column.
 __global__ void __launch_bounds__(256) colsum_kernel(const __half* __restrict__ a, long long M, int N, int ld, float* acc,
                                                      int rows_per_block) {
-  __shared__ float s[8][64];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int n0 = blockIdx.x * 64 + tx * 2;
-  const long long m_lo = static_cast<long long>(blockIdx.y) * rows_per_block;
+  __shared__ float s[2048];
+  const int tpr = N >> 3;                    // threads per row
+  const int slots = 256 / tpr;               // rows in flight per sweep
+  const int cg = threadIdx.x % tpr, slot = threadIdx.x / tpr;
+  const long long m_lo = static_cast<long long>(blockIdx.x) * rows_per_block;
   const long long m_hi = min(M, m_lo + rows_per_block);
-  float s0 = 0.f, s1 = 0.f;
-  if (n0 < N)
-    for (long long m = m_lo + ty; m < m_hi; m += 8) {
-      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(a + static_cast<size_t>(m) * ld + n0));
-      s0 += f.x; s1 += f.y;
-    }
-  s[ty][tx * 2] = s0; s[ty][tx * 2 + 1] = s1;
-  __syncthreads();
-  if (threadIdx.x < 64) {
-    float t = 0.f;
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (slot < slots)
+    for (long long m = m_lo + slot; m < m_hi; m += slots) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(a + static_cast<size_t>(m) * ld + cg * 8));
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += s[w][threadIdx.x];
-    const int n = blockIdx.x * 64 + threadIdx.x;
-    if (n < N) atomicAdd(acc + n, t);
+      for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
+    }
+  if (slot < slots) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[slot * N + cg * 8 + e] = v[e];
+  }
+  __syncthreads();
+  for (int n = threadIdx.x; n < N; n += 256) {
+    float t = 0.f;
+    for (int w = 0; w < slots; ++w) t += s[w * N + n];
+    atomicAdd(acc + n, t);
   }
 }
 

@@ -148,6 +148,9 @@ def gemm_tn(a1: torch.Tensor, n1: int, a2: torch.Tensor, n2: int, m: int, g: tor
     assert a1.dtype == torch.float16 and a2.dtype == torch.float16 and g.dtype == torch.float32
     assert a1.numel() >= m * n1 and a2.numel() >= m * n2 and g.numel() == n1 * n2 and g.is_contiguous()
     mode = TN_MODE if mode is None else mode
+    if n1 <= 64 < n2:
+        # the MMA tile is 128 rows of a1^T: put the wider operand there (half the tensor work for C = 64 stages)
+        a1, n1, a2, n2, transpose_out = a2, n2, a1, n1, not transpose_out
     L = _lib.lib()
     scratch = None
     if mode == 1:
@@ -180,10 +183,10 @@ def gather_cast(dres: torch.Tensor, map_mode: int, part, gamma, d0, d1) -> None:
                                           _lib.ptr(d1), _stream(dres)), 'gather_cast')
 
 
-def attn_core_bwd(qkv, dout, dqkv, shape, part, dim_head: int) -> None:
+def attn_core_bwd(qkv, o, dout, dqkv, shape, part, dim_head: int) -> None:
     b, h, w, c = shape
-    _lib.check(_lib.lib().rvt_attn_core_bwd(_lib.ptr(qkv), _lib.ptr(dout), _lib.ptr(dqkv), b, h, w, c, part[0], part[1],
-                                            dim_head, _stream(qkv)), 'attn_core_bwd')
+    _lib.check(_lib.lib().rvt_attn_core_bwd(_lib.ptr(qkv), _lib.ptr(o), _lib.ptr(dout), _lib.ptr(dqkv), b, h, w, c, part[0],
+                                            part[1], dim_head, _stream(qkv)), 'attn_core_bwd')
 
 
 def lstm_gates_bwd(gates, c_prev, c_new, dh, dc, n_tokens: int, dim: int, dpre, dc_prev) -> None:

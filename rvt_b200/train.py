@@ -320,7 +320,7 @@ class TrainEngine:
             ops.linear_ex(d1 if d1 is not None else d0, rows, c, c, blk['wprojT'], do)
             groups_rows = b * (hh // part[0]) * (ww // part[1]) * _lib.lib().rvt_rows_per_group(part[0] * part[1])
             dqkv = f16(rows * 3 * c) if groups_rows == rows else torch.zeros(rows * 3 * c, dtype=torch.float16, device=dev)
-            ops.attn_core_bwd(sv['qkv'], do, dqkv, shape, part, blk['dh'])
+            ops.attn_core_bwd(sv['qkv'], sv['o'], do, dqkv, shape, part, blk['dh'])
             xn = f16(rows * c)
             do_ln = blk['n1_w'] is not None
             ops.ln_rows_f16(sv['x_in'], mm, part, blk['n1_w'], blk['n1_b'], do_ln, eps, xn)

@@ -176,20 +176,22 @@ def test_attn_core_bwd(dev, part, dh, c):
         dout[gi * rpg:gi * rpg + p] = torch.randn(p, c, generator=g)
         qkv[gi * rpg + p:(gi + 1) * rpg] = 0.3           # padding rows hold the qkv bias in the real pipeline
     qkv16, dout16 = qkv.to(dev).half(), dout.to(dev).half()
-    dqkv = torch.full((rows, 3 * c), 9.0, device=dev).half()
-    ops.attn_core_bwd(qkv16, dout16, dqkv, (b, h, w, c), part, dh)
     # reference: autograd over the valid tokens of every group
     q32 = qkv16.float().requires_grad_(True)
     loss = 0.0
+    o_rows = torch.zeros(rows, c, device=dev)
     for gi in range(ng):
         blk = q32[gi * rpg:gi * rpg + p].view(p, nh, 3, dh)
         q, k, v = (blk[:, :, i].transpose(0, 1) for i in range(3))            # [nh, P, dh]
         a = torch.softmax(q @ k.transpose(-1, -2) * dh ** -0.5, -1)
         o = (a @ v).transpose(0, 1).reshape(p, c)
+        o_rows[gi * rpg:gi * rpg + p] = o.detach()
         loss = loss + (o * dout16.float()[gi * rpg:gi * rpg + p]).sum()
     loss.backward()
+    dqkv = torch.full((rows, 3 * c), 9.0, device=dev).half()
+    ops.attn_core_bwd(qkv16, o_rows.half(), dout16, dqkv, (b, h, w, c), part, dh)
     n_valid_rows = ng * rpg
-    assert rel_l2(dqkv.float()[:n_valid_rows], q32.grad[:n_valid_rows]) < 2e-3
+    assert rel_l2(dqkv.float()[:n_valid_rows], q32.grad[:n_valid_rows]) < 3e-3
     for gi in range(ng):
         assert float(dqkv[gi * rpg + p:(gi + 1) * rpg].float().abs().max()) == 0.0
 
