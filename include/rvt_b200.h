@@ -127,18 +127,19 @@ int rvt_downsample_cf2cl_train(const void* in, int in_dtype, int in_nchw, int ba
                                int ksize, int stride, int pad, int hout, int wout, int cout, const void* w_packed,
                                const float* ln_w, const float* ln_b, float eps, float* out, float* raw_out,
                                void* s2d_scratch, int stem_mode, void* stream);
-/* a4-a7 forward, training: out of place (x_out = x_in + ...), always the three-kernel path; weights packed with
- * pack_linear_weight(bn = rvt_tile_n(...)); qkv_save f16 [rows,3C] and o_save f16 [rows,C] are kept for the backward. */
+/* a4-a7 forward, training: out of place (x_out = x_in + ...), always the row-LN + three-kernel path; weights packed with
+ * pack_linear_weight(bn = rvt_tile_n(...)); xn_save f16 [rows,C] (= norm1(x) rows in partition order), qkv_save f16
+ * [rows,3C] and o_save f16 [rows,C] are kept for the backward. */
 int rvt_partition_attention_train(const float* x_in, float* x_out, int batch, int height, int width, int dim, int ph,
                                   int pw, int grid, int dim_head, const float* n1_w, const float* n1_b, float eps,
                                   const void* wqkv_packed, const float* bqkv, const void* wproj_packed,
                                   const float* bproj, const float* gamma1, void* qkv_save, void* o_save,
-                                  void* scratch_xn, void* stream);
-/* a8 forward, training: out of place, two-GEMM path; pre_save / act_save f16 [round_up(n,128), hidden] = fc1 output
- * before / after GELU. */
+                                  void* xn_save, void* stream);
+/* a8 forward, training: out of place, row-LN + two-GEMM path; xn_save f16 [round_up(n,128), C] = norm2(x);
+ * pre_save / act_save f16 [round_up(n,128), hidden] = fc1 output before / after GELU. */
 int rvt_mlp_block_train(const float* x_in, float* x_out, int64_t n_tokens, int dim, int hidden, const float* n2_w,
                         const float* n2_b, float eps, const void* w1_packed, const float* b1, const void* w2_packed,
-                        const float* b2, const float* gamma2, void* pre_save, void* act_save, void* scratch_xn,
+                        const float* b2, const float* gamma2, void* pre_save, void* act_save, void* xn_save,
                         void* stream);
 /* a9 forward, training (dws_mode 0 only): xh_save f16 [round_up(n,128), 2C] = [x | h_prev], gates_save f16 [n, 4C] =
  * activated gates [f|i|o|g]. */

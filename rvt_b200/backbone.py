@@ -20,6 +20,7 @@ keep working.
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -454,7 +455,17 @@ class RNNDetector(nn.Module):
         n = self.num_stages
         if wavefront:
             if getattr(self, '_streams', None) is None or self._streams[0].device != dev:
-                self._streams = [torch.cuda.Stream(dev) for _ in range(n)]
+                # later stages = small grids on the critical recurrence chain: give them scheduling priority so their
+                # CTAs are placed as soon as an SM slot frees instead of queueing behind the big early-stage grids
+                mode = os.environ.get('RVT_STREAM_PRIO', '1')
+                prio = [0] * n
+                if mode == '1':
+                    prio = [-s for s in range(n)]
+                elif mode == '2':
+                    prio = [0, 0] + [-1] * (n - 2)
+                elif mode == '3':
+                    prio = [-(n - 1 - s) for s in range(n)]
+                self._streams = [torch.cuda.Stream(dev, priority=p) for p in prio]
             streams = self._streams
             for st_ in streams:
                 st_.wait_stream(main)

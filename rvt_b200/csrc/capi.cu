@@ -111,12 +111,25 @@ int launch_ln_rows(const float* x, const RowMap& map, int64_t n_rows, int C, int
   return static_cast<int>(cudaGetLastError());
 }
 
+// any C % 8 == 0 (training forward: the normalised fp16 operand is materialised once and kept for the backward)
+int launch_ln_rows_any_f16(const float* x, const RowMap& map, int64_t n_rows, int C, int do_ln, const float* w, const float* b,
+                           float eps, void* out, cudaStream_t st);
+
 RowMap identity_map(int64_t n_tokens, int H, int W) {
   RowMap m{};
   m.mode = MAP_IDENTITY;
   m.H = H; m.W = W; m.ph = m.pw = 1; m.ny = H; m.nx = W; m.P = 1; m.rows_per_win = 1;
   m.n_groups = 0; m.n_tokens = static_cast<int>(n_tokens);
   return m;
+}
+
+int launch_ln_rows_any_f16(const float* x, const RowMap& map, int64_t n_rows, int C, int do_ln, const float* w, const float* b,
+                           float eps, void* out, cudaStream_t st) {
+  if (C % 8 != 0 || C > 512) return kErrUnsupported;
+  if (n_rows <= 0) return 0;
+  ln_rows_any_kernel<true><<<static_cast<unsigned>((n_rows + 7) / 8), 256, 0, st>>>(x, map, static_cast<int>(n_rows), C, do_ln, w, b,
+                                                                                   eps, out, C);
+  return static_cast<int>(cudaGetLastError());
 }
 
 }  // namespace
@@ -354,9 +367,10 @@ static int partition_attention_impl(const float* x, float* x_out, int force_unfu
     a.Wp = static_cast<const __half*>(wqkv_packed); a.bias = bqkv; a.map = m;
     a.o16 = static_cast<__half*>(scratch_qkv); a.ldo = 3 * dim; a.act = 0;
     int rc;
-    if (dim >= kWideDim && dim % 128 == 0) {
+    if (force_unfused || (dim >= kWideDim && dim % 128 == 0)) {
       if (!scratch_xn) return kErrBadArg;
-      rc = launch_ln_rows<true>(x, m, rows, dim, n1_w != nullptr, n1_w, n1_b, eps, scratch_xn, nullptr, nullptr, st);
+      rc = force_unfused ? launch_ln_rows_any_f16(x, m, rows, dim, n1_w != nullptr, n1_w, n1_b, eps, scratch_xn, st)
+                         : launch_ln_rows<true>(x, m, rows, dim, n1_w != nullptr, n1_w, n1_b, eps, scratch_xn, nullptr, nullptr, st);
       if (rc) return rc;
       a.a16 = static_cast<const __half*>(scratch_xn); a.lda = dim; a.a_rows = static_cast<int>(rows);
       rc = launch_gemm_f16<EP_F16>(a, n_mtiles, 3 * dim / a.BN, st);
@@ -407,10 +421,10 @@ int rvt_partition_attention(float* x, int batch, int height, int width, int dim,
 int rvt_partition_attention_train(const float* x_in, float* x_out, int batch, int height, int width, int dim, int ph, int pw,
                                   int grid, int dim_head, const float* n1_w, const float* n1_b, float eps,
                                   const void* wqkv_packed, const float* bqkv, const void* wproj_packed, const float* bproj,
-                                  const float* gamma1, void* qkv_save, void* o_save, void* scratch_xn, void* stream) {
-  if (x_in == x_out) return kErrBadArg;
+                                  const float* gamma1, void* qkv_save, void* o_save, void* xn_save, void* stream) {
+  if (x_in == x_out || !xn_save) return kErrBadArg;
   return partition_attention_impl(x_in, x_out, 1, batch, height, width, dim, ph, pw, grid, dim_head, n1_w, n1_b, eps,
-                                  wqkv_packed, bqkv, wproj_packed, bproj, gamma1, qkv_save, o_save, scratch_xn, stream);
+                                  wqkv_packed, bqkv, wproj_packed, bproj, gamma1, qkv_save, o_save, xn_save, stream);
 }
 
 static int mlp_block_impl(const float* x, float* x_out, int force_unfused, void* pre_out, int64_t n_tokens, int dim, int hidden,
@@ -460,9 +474,11 @@ static int mlp_block_impl(const float* x, float* x_out, int force_unfused, void*
     a.o16 = static_cast<__half*>(scratch_hidden); a.ldo = hidden; a.act = 1;
     a.o16_pre = static_cast<__half*>(pre_out);
     int rc;
-    if (dim >= kWideDim && dim % 128 == 0) {
+    if (force_unfused || (dim >= kWideDim && dim % 128 == 0)) {
       if (!scratch_xn) return kErrBadArg;
-      rc = launch_ln_rows<true>(x, m, static_cast<int64_t>(n_mtiles) * 128, dim, 1, n2_w, n2_b, eps, scratch_xn, nullptr, nullptr, st);
+      rc = force_unfused ? launch_ln_rows_any_f16(x, m, static_cast<int64_t>(n_mtiles) * 128, dim, 1, n2_w, n2_b, eps, scratch_xn, st)
+                         : launch_ln_rows<true>(x, m, static_cast<int64_t>(n_mtiles) * 128, dim, 1, n2_w, n2_b, eps, scratch_xn, nullptr,
+                                                nullptr, st);
       if (rc) return rc;
       a.a16 = static_cast<const __half*>(scratch_xn); a.lda = dim; a.a_rows = n_mtiles * 128;
       rc = launch_gemm_f16<EP_F16>(a, n_mtiles, hidden / a.BN, st);
@@ -491,10 +507,10 @@ int rvt_mlp_block(float* x, int64_t n_tokens, int dim, int hidden, const float* 
 
 int rvt_mlp_block_train(const float* x_in, float* x_out, int64_t n_tokens, int dim, int hidden, const float* n2_w,
                         const float* n2_b, float eps, const void* w1_packed, const float* b1, const void* w2_packed,
-                        const float* b2, const float* gamma2, void* pre_save, void* act_save, void* scratch_xn, void* stream) {
-  if (x_in == x_out || !pre_save || !act_save) return kErrBadArg;
+                        const float* b2, const float* gamma2, void* pre_save, void* act_save, void* xn_save, void* stream) {
+  if (x_in == x_out || !pre_save || !act_save || !xn_save) return kErrBadArg;
   return mlp_block_impl(x_in, x_out, 1, pre_save, n_tokens, dim, hidden, n2_w, n2_b, eps, w1_packed, b1, w2_packed, b2, gamma2,
-                        act_save, scratch_xn, stream);
+                        act_save, xn_save, stream);
 }
 
 static int dws_conv_lstm_impl(const float* x, const float* h_prev, const float* c_prev, int batch, int height, int width,
@@ -648,6 +664,9 @@ int rvt_gemm_tn(const void* a1, int ld1, int n1, const void* a2, int ld2, int n2
   a.kc_total = cdiv(m, 64);
   a.G = g; a.s_i = s_i; a.s_j = s_j;
   a.kmajor = mode == 1 ? 1 : 0;
+  static int epi_env = -1;
+  if (epi_env < 0) { const char* e = getenv("RVT_TN_EPI"); epi_env = e ? atoi(e) : 1; }
+  a.epi_bulk = (epi_env == 1 && s_j == 1 && s_i % 4 == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0) ? 1 : 0;
   a.tmem_cols = static_cast<int>(tmem_cols_pow2(static_cast<uint32_t>(a.BN)));
   const int tiles = cdiv(n1, 128) * cdiv(n2, a.BN);
   int sms = 148;
@@ -712,7 +731,8 @@ int rvt_ln_bwd(const float* x, const void* dy, int dy_is_f16, int map_mode, int 
   int sms = 148;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   int64_t blocks = (rows + 7) / 8;
-  if (blocks > sms * 4) blocks = sms * 4;
+  const int64_t cap = static_cast<int64_t>(sms) * (dim <= 128 ? 16 : 8);   // rows are latency chains: favour parallelism
+  if (blocks > cap) blocks = cap;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dy_is_f16)
     ln_bwd_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, dy, dim, m, static_cast<int>(rows), dim, do_ln, ln_w, eps,
@@ -803,8 +823,9 @@ int rvt_colsum(const void* a, int64_t m, int n, int ld, float* acc, void* stream
   if (m <= 0) return 0;
   int sms = 148;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-  int64_t rows_per_block = (m + 2 * sms - 1) / (2 * sms);
-  if (rows_per_block < 32) rows_per_block = 32;
+  int64_t rows_per_block = (m + 4 * sms - 1) / (4 * sms);
+  const int64_t min_rows = 4 * (256 / (n / 8));            // >= one 4-deep sweep of every row slot
+  if (rows_per_block < min_rows) rows_per_block = min_rows;
   colsum_kernel<<<cdiv(m, rows_per_block), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(a), m, n, ld, acc, static_cast<int>(rows_per_block));
   return static_cast<int>(cudaGetLastError());

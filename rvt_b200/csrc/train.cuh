@@ -32,6 +32,7 @@ struct TnArgs {
   int M, N1, N2, BN;
   int kc_total, kc_per_split;
   int stages, tmem_cols, kmajor;
+  int epi_bulk;        // 1: rows of the accumulator tile are staged in smem and added to G with cp.reduce.async.bulk (s_j == 1)
   float* G;
   long long s_i, s_j;
 };
@@ -132,19 +133,45 @@ __global__ void __launch_bounds__(kTnThreads) gemm_tn_kernel(const __grid_consta
     __syncwarp();
   } else {
     const int q = warp & 3;                                  // TMEM lane quarter this warp may read
-    const int i = i0 + q * 32 + lane;
+    const int r = q * 32 + lane;
+    const int i = i0 + r;
     mbar_wait(accum, 0);
     tc_fence_after();
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      float v[16];
-      tmem_ld_x16(trow + c0, v);
-      tmem_ld_wait();
-      if (i < a.N1) {
+    if (a.epi_bulk) {
+      // all MMAs have completed (accum barrier): the operand stages are free -> stage this thread's accumulator row
+      // (pitch BN*4 + 16 B: conflict-free 16-byte stores) and add it to G with ONE bulk reduction per row.
+      const uint32_t pitch = static_cast<uint32_t>(BN) * 4u + 16u;
+      const uint32_t srow = base + static_cast<uint32_t>(r) * pitch;
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        float v[16];
+        tmem_ld_x16(trow + c0, v);
+        tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int j = j0 + c0 + e;
-          if (j < a.N2) atomicAdd(a.G + static_cast<long long>(i) * a.s_i + static_cast<long long>(j) * a.s_j, v[e]);
+        for (int qd = 0; qd < 4; ++qd)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (c0 + qd * 4) * 4), "f"(v[qd * 4]), "f"(v[qd * 4 + 1]),
+                       "f"(v[qd * 4 + 2]), "f"(v[qd * 4 + 3]) : "memory");
+      }
+      fence_proxy_async_smem();
+      const int ncols = min(BN, a.N2 - j0);
+      if (i < a.N1 && ncols > 0) {
+        float* dst = a.G + static_cast<long long>(i) * a.s_i + j0;
+        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst), "r"(srow),
+                     "r"(static_cast<uint32_t>(ncols) * 4u) : "memory");
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    } else {
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        float v[16];
+        tmem_ld_x16(trow + c0, v);
+        tmem_ld_wait();
+        if (i < a.N1) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int j = j0 + c0 + e;
+            if (j < a.N2) atomicAdd(a.G + static_cast<long long>(i) * a.s_i + static_cast<long long>(j) * a.s_j, v[e]);
+          }
         }
       }
     }
@@ -560,8 +587,9 @@ __global__ void __launch_bounds__(256) lstm_gates_bwd_kernel(const __half* __res
 }
 
 // ----------------------------------------------------------------------------------------
-// Downsample conv (maxvit.py:166-175) operand / input-gradient helpers.  K order (ky, kx, ci); col rows = output
-// tokens, ldc = round_up(K, 8) (pad columns are zeros).
+// Downsample conv (maxvit.py:166-175) operand / input-gradient helpers.  K order: (ky, kx, ci) for channels-last inputs,
+// (ci, ky, kx) — the conv weight's own order — for NCHW inputs (the stem), so consecutive threads read consecutive
+// pixels either way; col rows = output tokens, ldc = round_up(K, 8) (pad columns are zeros).
 // im2col: in NCHW (u8 / f32 / f16) or NHWC (f32 / f16); rows / cols of the virtual input beyond (Hin, Win) are zero.
 // col2im: d_in[b, iy, ix, ci] = sum over the taps that read this pixel of dcol[(b, oy, ox), (ky, kx, ci)]  (gather form,
 // deterministic); d_in fp32 NHWC.
@@ -583,8 +611,9 @@ __global__ void __launch_bounds__(256) im2col_kernel(const void* __restrict__ in
   for (int e = 0; e < 2; ++e) {
     const int k = k0 + e;
     if (k >= g.K) continue;
-    const int tap = k / g.Cin, ci = k - tap * g.Cin;
-    const int ky = tap / g.KS, kx = tap - ky * g.KS;
+    int ci, ky, kx;
+    if (g.in_nchw) { const int kk = g.KS * g.KS; ci = k / kk; const int rem2 = k - ci * kk; ky = rem2 / g.KS; kx = rem2 - ky * g.KS; }
+    else { const int tap = k / g.Cin; ci = k - tap * g.Cin; ky = tap / g.KS; kx = tap - ky * g.KS; }
     const int iy = oy * g.stride - g.pad + ky, ix = ox * g.stride - g.pad + kx;
     if (iy < 0 || iy >= g.Hin || ix < 0 || ix >= g.Win) continue;
     const size_t off = g.in_nchw ? ((static_cast<size_t>(b) * g.Cin + ci) * g.Hin + iy) * g.Win + ix
@@ -636,13 +665,26 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __half* __restrict__ 
   const long long m_lo = static_cast<long long>(blockIdx.x) * rows_per_block;
   const long long m_hi = min(M, m_lo + rows_per_block);
   float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (slot < slots)
-    for (long long m = m_lo + slot; m < m_hi; m += slots) {
+  if (slot < slots) {
+    long long m = m_lo + slot;
+    for (; m + 3LL * slots < m_hi; m += 4LL * slots) {          // four independent 16-byte loads in flight
+      uint4 u[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) u[q] = __ldg(reinterpret_cast<const uint4*>(a + static_cast<size_t>(m + q * slots) * ld + cg * 8));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const __half2* h = reinterpret_cast<const __half2*>(&u[q]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
+      }
+    }
+    for (; m < m_hi; m += slots) {
       const uint4 u = __ldg(reinterpret_cast<const uint4*>(a + static_cast<size_t>(m) * ld + cg * 8));
       const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
       for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
     }
+  }
   if (slot < slots) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) s[slot * N + cg * 8 + e] = v[e];

@@ -144,13 +144,11 @@ def linear_ex(a: torch.Tensor, m: int, k: int, n: int, w_packed: torch.Tensor, o
 
 def gemm_tn(a1: torch.Tensor, n1: int, a2: torch.Tensor, n2: int, m: int, g: torch.Tensor, transpose_out: bool = False,
             mode: Optional[int] = None) -> None:
-    """g[n1, n2] += a1[:m, :n1]^T @ a2[:m, :n2]  (g f32; transpose_out: g is [n2, n1] and receives the transpose)."""
+    """g[n1, n2] += a1[:m, :n1]^T @ a2[:m, :n2]  (g f32; transpose_out: g is [n2, n1] and receives the transpose).
+    The MMA tile is 128 rows of a1^T x up to 128 of a2^T: pass the wider operand as a1."""
     assert a1.dtype == torch.float16 and a2.dtype == torch.float16 and g.dtype == torch.float32
     assert a1.numel() >= m * n1 and a2.numel() >= m * n2 and g.numel() == n1 * n2 and g.is_contiguous()
     mode = TN_MODE if mode is None else mode
-    if n1 <= 64 < n2:
-        # the MMA tile is 128 rows of a1^T: put the wider operand there (half the tensor work for C = 64 stages)
-        a1, n1, a2, n2, transpose_out = a2, n2, a1, n1, not transpose_out
     L = _lib.lib()
     scratch = None
     if mode == 1:

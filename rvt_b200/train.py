@@ -122,14 +122,14 @@ class TrainEngine:
             d = st.downsample_cf2cl
             k = d.kernel_size * d.kernel_size * st.dim_in
             pre = f'stages.{s}.'
-            lay += [(pre + 'conv.G', (c, _ru(k, 8))), (pre + 'conv.ln_w', (c,)), (pre + 'conv.ln_b', (c,))]
+            lay += [(pre + 'conv.GT', (_ru(k, 8), c)), (pre + 'conv.ln_w', (c,)), (pre + 'conv.ln_b', (c,))]
             for bi, pair in enumerate(st.att_blocks):
                 for kind, att in (('att_window', pair.att_window), ('att_grid', pair.att_grid)):
                     bp = f'{pre}att_blocks.{bi}.{kind}.'
                     hid = att.mlp.net[0][0].weight.shape[0]
                     lay += [(bp + 'n1_w', (c,)), (bp + 'n1_b', (c,)), (bp + 'qkv.G', (3 * c, c)), (bp + 'qkv.s', (3 * c,)),
                             (bp + 'proj.G0', (c, c)), (bp + 'proj.s0', (c,)), (bp + 'n2_w', (c,)), (bp + 'n2_b', (c,)),
-                            (bp + 'fc1.G', (hid, c)), (bp + 'fc1.s', (hid,)), (bp + 'fc2.G0', (c, hid)), (bp + 'fc2.s0', (c,))]
+                            (bp + 'fc1.G', (hid, c)), (bp + 'fc1.s', (hid,)), (bp + 'fc2.G0T', (hid, c)), (bp + 'fc2.s0', (c,))]
             lay += [(pre + 'lstm.G', (4 * c, 2 * c)), (pre + 'lstm.s', (4 * c,))]
         return lay
 
@@ -167,7 +167,11 @@ class TrainEngine:
             d = st.downsample_cf2cl
             pre = f'stages.{s}.'
             k = d.kernel_size * d.kernel_size * st.dim_in
-            g = A[pre + 'conv.G'][:, :k].reshape(c, d.kernel_size, d.kernel_size, st.dim_in).permute(0, 3, 1, 2)
+            gt = A[pre + 'conv.GT'][:k].t()                          # [c, K]; K order (ci,ky,kx) for the NCHW stem, else (ky,kx,ci)
+            if s == 0:
+                g = gt.reshape(c, st.dim_in, d.kernel_size, d.kernel_size)
+            else:
+                g = gt.reshape(c, d.kernel_size, d.kernel_size, st.dim_in).permute(0, 3, 1, 2)
             grads[pre + 'downsample_cf2cl.conv.weight'] = g.contiguous()
             if d.norm_affine:
                 grads[pre + 'downsample_cf2cl.norm.weight'] = A[pre + 'conv.ln_w'].clone()
@@ -182,7 +186,8 @@ class TrainEngine:
                 for gname, G0n, s0n, wname, bname, w32, bias in (
                         ('ls1.gamma', 'proj.G0', 'proj.s0', 'self_attn.proj.weight', 'self_attn.proj.bias', blk['wproj_f32'], blk['bproj']),
                         ('ls2.gamma', 'fc2.G0', 'fc2.s0', 'mlp.net.2.weight', 'mlp.net.2.bias', blk['w2_f32'], blk['b2'])):
-                    G0, s0 = A[bp + G0n], A[bp + s0n]
+                    G0 = A[bp + 'fc2.G0T'].t() if G0n == 'fc2.G0' else A[bp + G0n]
+                    s0 = A[bp + s0n]
                     gamma = blk['g1'] if gname == 'ls1.gamma' else blk['g2']
                     if gamma is not None:
                         # out = x + gamma * (a W^T + b):  dW = gamma[:,None] * G0,  db = gamma * s0,
@@ -194,7 +199,7 @@ class TrainEngine:
                         grads[bp + wname] = gamma[:, None] * G0
                         grads[bp + bname] = gamma * s0
                     else:
-                        grads[bp + wname] = G0.clone()
+                        grads[bp + wname] = G0.contiguous().clone()
                         grads[bp + bname] = s0.clone()
                 grads[bp + 'norm2.weight'] = A[bp + 'n2_w'].clone()
                 grads[bp + 'norm2.bias'] = A[bp + 'n2_b'].clone()
@@ -247,18 +252,19 @@ class TrainEngine:
             rows = ops.attention_scratch_rows(b, hh, ww, blk['part'])
             hid = blk['hidden']
             qkv, o = f16(rows * 3 * c), f16(rows * c)
-            sxn = f16(max(rows, n_pad) * c) if c >= 256 else None
+            xn1, xn2 = f16(rows * c), f16(n_pad * c)
             x1 = torch.empty_like(x)
             _lib.check(L.rvt_partition_attention_train(
                 ptr(x), ptr(x1), b, hh, ww, c, blk['part'][0], blk['part'][1], blk['grid'], blk['dh'], ptr(blk['n1_w']),
                 ptr(blk['n1_b']), blk['eps'], ptr(blk['wqkv']), ptr(blk['bqkv']), ptr(blk['wproj']), ptr(blk['bproj']),
-                ptr(blk['g1']), ptr(qkv), ptr(o), ptr(sxn), stream), 'partition_attention_train')
+                ptr(blk['g1']), ptr(qkv), ptr(o), ptr(xn1), stream), 'partition_attention_train')
             pre_, act = f16(n_pad * hid), f16(n_pad * hid)
             x2 = torch.empty_like(x)
             _lib.check(L.rvt_mlp_block_train(
                 ptr(x1), ptr(x2), n_tok, c, hid, ptr(blk['n2_w']), ptr(blk['n2_b']), blk['eps'], ptr(blk['w1']), ptr(blk['b1']),
-                ptr(blk['w2']), ptr(blk['b2']), ptr(blk['g2']), ptr(pre_), ptr(act), ptr(sxn), stream), 'mlp_block_train')
-            saved['blocks'].append({'x_in': x, 'qkv': qkv, 'o': o, 'x_mid': x1, 'pre': pre_, 'act': act, 'rows': rows})
+                ptr(blk['w2']), ptr(blk['b2']), ptr(blk['g2']), ptr(pre_), ptr(act), ptr(xn2), stream), 'mlp_block_train')
+            saved['blocks'].append({'x_in': x, 'qkv': qkv, 'o': o, 'x_mid': x1, 'pre': pre_, 'act': act, 'rows': rows,
+                                    'xn1': xn1, 'xn2': xn2})
             x = x2
         xh, gates = f16(n_pad * 2 * c), f16(n_tok * 4 * c)
         h_new, c_new = torch.empty_like(x), torch.empty_like(x)
@@ -298,18 +304,16 @@ class TrainEngine:
             # MLP half: x2 = x1 + g2 * (fc2(gelu(fc1(norm2(x1)))) )
             d0, d1 = f16(n_pad * c), (f16(n_pad * c) if blk['g2'] is not None else None)
             ops.gather_cast(dres, 0, None, blk['g2'], d0, d1)
-            ops.gemm_tn(d0, c, sv['act'], hid, n_tok, A[bp + 'fc2.G0'])
+            ops.gemm_tn(sv['act'], hid, d0, c, n_tok, A[bp + 'fc2.G0T'])
             ops.colsum(d0, n_tok, c, A[bp + 'fc2.s0'])
             dpre_m = f16(n_pad * hid)
             ops.linear_ex(d1 if d1 is not None else d0, n_tok, c, hid, blk['w2T'], dpre_m, act=2, aux=sv['pre'])
-            xn = f16(n_pad * c)
-            ops.ln_rows_f16(sv['x_mid'], 0, None, blk['n2_w'], blk['n2_b'], True, eps, xn)
-            ops.gemm_tn(dpre_m, hid, xn, c, n_tok, A[bp + 'fc1.G'])
+            ops.gemm_tn(dpre_m, hid, sv['xn2'], c, n_tok, A[bp + 'fc1.G'])
             ops.colsum(dpre_m, n_tok, hid, A[bp + 'fc1.s'])
             dxn = f16(n_pad * c)
             ops.linear_ex(dpre_m, n_tok, hid, c, blk['w1T'], dxn)
             ops.ln_bwd(sv['x_mid'], dxn, shape, 0, None, blk['n2_w'], True, eps, dres, None, A[bp + 'n2_w'], A[bp + 'n2_b'])
-            del dpre_m, dxn, xn, d0, d1
+            del dpre_m, dxn, d0, d1
             # attention half: x1 = x0 + g1 * proj(attn(partition(norm1(x0))))
             rows, mm, part = sv['rows'], blk['map_mode'], blk['part']
             d0, d1 = f16(rows * c), (f16(rows * c) if blk['g1'] is not None else None)
@@ -321,16 +325,14 @@ class TrainEngine:
             groups_rows = b * (hh // part[0]) * (ww // part[1]) * _lib.lib().rvt_rows_per_group(part[0] * part[1])
             dqkv = f16(rows * 3 * c) if groups_rows == rows else torch.zeros(rows * 3 * c, dtype=torch.float16, device=dev)
             ops.attn_core_bwd(sv['qkv'], sv['o'], do, dqkv, shape, part, blk['dh'])
-            xn = f16(rows * c)
             do_ln = blk['n1_w'] is not None
-            ops.ln_rows_f16(sv['x_in'], mm, part, blk['n1_w'], blk['n1_b'], do_ln, eps, xn)
-            ops.gemm_tn(dqkv, 3 * c, xn, c, rows, A[bp + 'qkv.G'])
+            ops.gemm_tn(dqkv, 3 * c, sv['xn1'], c, rows, A[bp + 'qkv.G'])
             ops.colsum(dqkv, rows, 3 * c, A[bp + 'qkv.s'])
             dxn = f16(rows * c)
             ops.linear_ex(dqkv, rows, 3 * c, c, blk['wqkvT'], dxn)
             ops.ln_bwd(sv['x_in'] if do_ln else None, dxn, shape, mm, part, blk['n1_w'], do_ln, eps, dres, None,
                        A[bp + 'n1_w'] if do_ln else None, A[bp + 'n1_b'] if do_ln else None)
-            del d0, d1, do, dqkv, xn, dxn
+            del d0, d1, do, dqkv, dxn
         # ---- downsample conv + LayerNorm (maxvit.py:174-178)
         bq, cin, hin, win, ks, stride, pad, _, _ = saved['geom']
         dy16 = f16(n_pad * c)
@@ -339,7 +341,7 @@ class TrainEngine:
         ldc = pk['ldc']
         col = f16(n_tok * ldc)
         ops.im2col(saved['cur'], saved['cur_nchw'], ks, stride, pad, hh, ww, col)
-        ops.gemm_tn(dy16, c, col, ldc, n_tok, A[pre + 'conv.G'])
+        ops.gemm_tn(col, ldc, dy16, c, n_tok, A[pre + 'conv.GT'])
         d_cur = None
         if need_in:
             if pk['conv_wT'] is None:

@@ -239,7 +239,10 @@ def test_im2col_col2im(dev, nchw, dtype, cin, ks, stride):
     col = torch.full((b * hout * wout, ldc), 5.0, device=dev).half()
     ops.im2col(x, nchw, ks, stride, pad, hout, wout, col)
     unf = F.unfold(xn.to(dtype).float().to(dev), ks, padding=pad, stride=stride)          # [B, cin*ks*ks, L]  (ci, ky, kx)
-    ref = unf.view(b, cin, ks * ks, hout * wout).permute(0, 3, 2, 1).reshape(b * hout * wout, k)   # (ky, kx, ci)
+    if nchw:
+        ref = unf.permute(0, 2, 1).reshape(b * hout * wout, k)                                      # (ci, ky, kx): the stem's order
+    else:
+        ref = unf.view(b, cin, ks * ks, hout * wout).permute(0, 3, 2, 1).reshape(b * hout * wout, k)   # (ky, kx, ci)
     assert rel_l2(col[:, :k].float(), ref.half().float()) == 0.0
     assert float(col[:, k:].float().abs().max() if ldc > k else 0.0) == 0.0
     if not nchw:
