@@ -260,21 +260,51 @@ def run_train(args, rank, world, local_rank):
     acc_ms = {k: 0.0 for k in ev}
     counter = [0]
 
-    def step(record=False):
-        seq = seqs[counter[0] % n_seq]
-        counter[0] += 1
-        opt.zero_grad(set_to_none=True)
+    cpu_ms = {'fwd': 0.0, 'bwd': 0.0}
+    graphed = {}
+
+    def fwd_bwd(seq, record=False):
         if record:
             ev['fwd'][0].record()
+        t0 = time.perf_counter()
         st, out = None, None
         for t in range(SEQ_LEN):
             out, st = model(seq[t], st)
         loss = sum((out[s].float() ** 2).mean() for s in (1, 2, 3, 4)) * LOSS_SCALE
+        t1 = time.perf_counter()
         if record:
             ev['fwd'][1].record(); ev['bwd'][0].record()
         loss.backward()
+        t2 = time.perf_counter()
         if record:
-            ev['bwd'][1].record(); ev['ar'][0].record()
+            ev['bwd'][1].record()
+            cpu_ms['fwd'] += (t1 - t0) * 500; cpu_ms['bwd'] += (t2 - t1) * 500    # mean of the 2 recorded steps, ms
+        return loss
+
+    def capture():
+        # ONE CUDA graph of forward (21 timesteps) + loss + backward (rvt_b200.graph.capture_training_step): the weight
+        # re-packing, every kernel and the gradient hand-over are replayed without Python; the all-reduce and the optimizer
+        # stay outside.  p.grad become static tensors that each replay overwrites.
+        from rvt_b200.graph import capture_training_step
+        static_seq = torch.empty_like(seqs[0])
+        graphed['seq'] = static_seq
+        graphed['run'] = capture_training_step(model, lambda: fwd_bwd(static_seq), params)
+
+    def step(record=False):
+        seq = seqs[counter[0] % n_seq]
+        counter[0] += 1
+        if graphed:
+            graphed['seq'].copy_(seq, non_blocking=True)
+            if record:
+                ev['fwd'][0].record(); ev['fwd'][1].record(); ev['bwd'][0].record()
+            loss = graphed['run']()
+            if record:
+                ev['bwd'][1].record()
+        else:
+            opt.zero_grad(set_to_none=True)
+            loss = fwd_bwd(seq, record)
+        if record:
+            ev['ar'][0].record()
         n_coll = sharding.allreduce_gradients(params)
         if record:
             ev['ar'][1].record(); ev['opt'][0].record()
@@ -290,6 +320,10 @@ def run_train(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    for _ in range(2):
+        loss, n_coll = step()
+    if not args.train_eager:
+        capture()
     for _ in range(max(args.warmup, 3)):
         loss, n_coll = step()
     assert torch.isfinite(loss.detach()).item(), 'non-finite training loss'
@@ -325,7 +359,8 @@ def run_train(args, rank, world, local_rank):
                        'l2_policy': f'{n_seq} rotating input sequences ({n_seq * seqs[0].numel() >> 20} MB) > L2',
                        'parallelism': f'batch-sharded x{world}; {n_coll} NCCL all-reduce of {n_par * 4 >> 20} MB fp32 gradients per step',
                        'loss_scale': LOSS_SCALE},
-            'clocks': clocks, 'phases_ms': acc_ms, 'final_loss': float(loss.detach()) / LOSS_SCALE, 'grads_finite': grad_ok,
+            'schedule': 'eager launches' if args.train_eager else 'fwd+bwd replayed as one CUDA graph; all-reduce + Adam eager',
+            'clocks': clocks, 'phases_ms': acc_ms, 'cpu_issue_ms': cpu_ms if args.train_eager else None, 'final_loss': float(loss.detach()) / LOSS_SCALE, 'grads_finite': grad_ok,
         }), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -340,6 +375,8 @@ def main():
     ap.add_argument('--mode', default='infer', choices=['infer', 'train'],
                     help="infer: BASELINE configs[1] (the headline metric); train: configs[2], the batch-sharded training step")
     ap.add_argument('--train-batch', type=int, default=3, help='samples per GPU in --mode train (BASELINE configs[2]: 3)')
+    ap.add_argument('--train-eager', action='store_true',
+                    help='--mode train: launch forward+backward eagerly instead of replaying one CUDA graph of them')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch eagerly instead of replaying CUDA graphs')
     ap.add_argument('--no-wavefront', action='store_true', help='run the four stages strictly one after the other')

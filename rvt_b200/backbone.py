@@ -457,7 +457,7 @@ class RNNDetector(nn.Module):
             if getattr(self, '_streams', None) is None or self._streams[0].device != dev:
                 # later stages = small grids on the critical recurrence chain: give them scheduling priority so their
                 # CTAs are placed as soon as an SM slot frees instead of queueing behind the big early-stage grids
-                mode = os.environ.get('RVT_STREAM_PRIO', '1')
+                mode = os.environ.get('RVT_STREAM_PRIO', '2')
                 prio = [0] * n
                 if mode == '1':
                     prio = [-s for s in range(n)]

@@ -802,6 +802,12 @@ int rvt_im2col(const void* in, int in_dtype, int in_nchw, int batch, int cin, in
                int hout, int wout, void* col, void* stream) {
   ConvGeom g;
   if (!in || !col || conv_geom(in_dtype, in_nchw, batch, cin, hin, win, ksize, stride, pad, hout, wout, &g)) return kErrBadArg;
+  if (in_nchw) {
+    const int64_t nitems = static_cast<int64_t>(batch) * hout * wout * (cin * ksize + 1);
+    im2col_nchw_kernel<<<static_cast<unsigned>((nitems + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        in, g, static_cast<__half*>(col));
+    return static_cast<int>(cudaGetLastError());
+  }
   const int64_t items = static_cast<int64_t>(batch) * hout * wout * (g.ldc / 2);
   im2col_kernel<<<static_cast<unsigned>((items + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, g,
                                                                                                         static_cast<__half*>(col));

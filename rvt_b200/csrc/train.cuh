@@ -625,6 +625,40 @@ __global__ void __launch_bounds__(256) im2col_kernel(const void* __restrict__ in
   *reinterpret_cast<uint32_t*>(col + static_cast<size_t>(tok) * g.ldc + k0) = pack_h2(v[0], v[1]);
 }
 
+// NCHW input (the stem): one thread per (token, ci, ky) writes the KS consecutive columns (ci, ky, 0..KS-1) from KS
+// consecutive pixels of one input row; the last thread slot of a token zero-fills the pad columns [K, ldc).
+__global__ void __launch_bounds__(256) im2col_nchw_kernel(const void* __restrict__ in, ConvGeom g, __half* __restrict__ col) {
+  const int per_tok = g.Cin * g.KS + 1;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long n_tok = static_cast<long long>(g.B) * g.Hout * g.Wout;
+  if (idx >= n_tok * per_tok) return;
+  const long long tok = idx / per_tok;
+  const int slot = static_cast<int>(idx - tok * per_tok);
+  __half* crow = col + static_cast<size_t>(tok) * g.ldc;
+  if (slot == per_tok - 1) {
+    for (int k = g.K; k < g.ldc; ++k) crow[k] = __float2half(0.f);
+    return;
+  }
+  const int ci = slot / g.KS, ky = slot - ci * g.KS;
+  const int hw = g.Hout * g.Wout;
+  const int b = static_cast<int>(tok / hw), rem = static_cast<int>(tok - static_cast<long long>(b) * hw);
+  const int oy = rem / g.Wout, ox = rem - oy * g.Wout;
+  const int iy = oy * g.stride - g.pad + ky, ix0 = ox * g.stride - g.pad;
+  __half* dst = crow + (ci * g.KS + ky) * g.KS;
+  const bool row_ok = iy >= 0 && iy < g.Hin;
+  const size_t base = ((static_cast<size_t>(b) * g.Cin + ci) * g.Hin + (row_ok ? iy : 0)) * g.Win;
+  for (int kx = 0; kx < g.KS; ++kx) {
+    const int ix = ix0 + kx;
+    float v = 0.f;
+    if (row_ok && ix >= 0 && ix < g.Win) {
+      if (g.in_dtype == 1) v = static_cast<float>(__ldg(reinterpret_cast<const uint8_t*>(in) + base + ix));
+      else if (g.in_dtype == 2) v = __half2float(__ldg(reinterpret_cast<const __half*>(in) + base + ix));
+      else v = __ldg(reinterpret_cast<const float*>(in) + base + ix);
+    }
+    dst[kx] = __float2half_rn(v);
+  }
+}
+
 __global__ void __launch_bounds__(256) col2im_kernel(const __half* __restrict__ dcol, ConvGeom g, float* __restrict__ d_in) {
   const int half_c = g.Cin >> 1;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;

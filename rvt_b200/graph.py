@@ -39,3 +39,33 @@ def capture_sequence(model, xs, prev_states=None, wavefront: bool = True, warmup
         with torch.no_grad():
             return model.forward_sequence(xs, prev_states, wavefront=wavefront)
     return GraphedCallable(run, warmup)
+
+
+def capture_training_step(model, fwd_bwd: Callable[[], torch.Tensor], params, warmup: int = 2):
+    """Capture ``loss = fwd_bwd()`` — forward over the unrolled sequence, loss and ``loss.backward()`` through
+    rvt_b200.train — into ONE CUDA graph.  ``fwd_bwd`` must read its inputs from static tensors.  After the capture every
+    ``p.grad`` is a static tensor (a view of the flat gradient buffer) that each replay OVERWRITES; run the all-reduce and
+    the optimizer eagerly after the replay and do not call ``zero_grad(set_to_none=True)`` any more.  The re-packing of
+    the (optimizer-updated) weights is part of the graph.  Returns a callable giving the static loss tensor."""
+    eng = model._train_engine()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(warmup):
+            for p in params:
+                p.grad = None
+            fwd_bwd()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    for p in params:
+        p.grad = None
+    eng.invalidate()                      # the packed-weight refresh must be recorded in the graph
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        loss = fwd_bwd()
+
+    def replay():
+        g.replay()
+        return loss
+    replay.graph = g
+    return replay

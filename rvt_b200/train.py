@@ -47,6 +47,10 @@ class TrainEngine:
         self.gen = 0
         self._zero_tok = None
 
+    def invalidate(self):
+        """Forget the packed weights (next forward re-packs; used before a CUDA-graph capture so the refresh is recorded)."""
+        self._packed = self._packed_key = None
+
     # ------------------------------------------------------------------ packed weights
     def packed(self, device):
         m = self.model
@@ -160,7 +164,7 @@ class TrainEngine:
         if not self.dirty:
             return grads
         A = self.acc(device)
-        pk = self.packed(device)
+        pk = self._packed if self._packed is not None else self.packed(device)
         m = self.model
         for s, st in enumerate(m.stages):
             c = st.dim
@@ -225,7 +229,7 @@ class TrainEngine:
         d = st.downsample_cf2cl
         c = st.dim
         dev = cur.device
-        pk = self.packed(dev)[s]
+        pk = self._packed[s]                          # refreshed once per forward call (forward_train)
         L = _lib.lib()
         stream = torch.cuda.current_stream(dev).cuda_stream
         ptr = _lib.ptr
@@ -278,7 +282,7 @@ class TrainEngine:
         """Returns (d_cur or None, dh_prev or None, dc_prev or None); parameter gradients go to the accumulators."""
         b, hh, ww, c = saved['shape']
         dev = c_new.device
-        pk = self.packed(dev)[s]
+        pk = self._packed[s]                          # the weights of the forward this backward belongs to
         A = self.acc(dev)
         pre = f'stages.{s}.'
         n_tok, n_pad = b * hh * ww, _ru(b * hh * ww, 128)
@@ -428,6 +432,7 @@ def forward_train(model, x: torch.Tensor, prev_states, token_mask):
     if token is None:
         token = _GradSink.apply(eng, *eng.params)
     x = model._prep_input(x)
+    eng.packed(x.device)                              # re-pack if an optimizer step changed the parameters
     states, output = [], {}
     cur, cur_nchw = x, True
     for s in range(model.num_stages):
