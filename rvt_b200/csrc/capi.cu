@@ -127,8 +127,10 @@ int launch_ln_rows_any_f16(const float* x, const RowMap& map, int64_t n_rows, in
                            float eps, void* out, cudaStream_t st) {
   if (C % 8 != 0 || C > 512) return kErrUnsupported;
   if (n_rows <= 0) return 0;
-  ln_rows_any_kernel<true><<<static_cast<unsigned>((n_rows + 7) / 8), 256, 0, st>>>(x, map, static_cast<int>(n_rows), C, do_ln, w, b,
-                                                                                   eps, out, C);
+  const int rpb = 8 * (32 / ((C >> 2) > 16 ? 32 : ((C >> 2) > 8 ? 16 : 8)));      // rows per CTA (train.cuh ln_lanes_per_row)
+  const unsigned grid = static_cast<unsigned>((n_rows + rpb - 1) / rpb);
+  if (C <= 128) ln_rows_any_kernel<true, 1><<<grid, 256, 0, st>>>(x, map, static_cast<int>(n_rows), C, do_ln, w, b, eps, out, C);
+  else ln_rows_any_kernel<true, 4><<<grid, 256, 0, st>>>(x, map, static_cast<int>(n_rows), C, do_ln, w, b, eps, out, C);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -715,9 +717,7 @@ int rvt_ln_rows_f16(const float* x, int map_mode, int batch, int height, int wid
   int rc = make_row_map(map_mode, batch, height, width, ph, pw, &m, &rows);
   if (rc) return rc;
   if (rows <= 0) return 0;
-  ln_rows_any_kernel<true><<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, m, static_cast<int>(rows), dim, do_ln, ln_w, ln_b, eps, out16, dim);
-  return static_cast<int>(cudaGetLastError());
+  return launch_ln_rows_any_f16(x, m, rows, dim, do_ln, ln_w, ln_b, eps, out16, static_cast<cudaStream_t>(stream));
 }
 
 int rvt_ln_bwd(const float* x, const void* dy, int dy_is_f16, int map_mode, int batch, int height, int width, int dim, int ph,
@@ -730,16 +730,21 @@ int rvt_ln_bwd(const float* x, const void* dy, int dy_is_f16, int map_mode, int 
   if (rows <= 0) return 0;
   int sms = 148;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-  int64_t blocks = (rows + 7) / 8;
+  const int rpb = 8 * (32 / ((dim >> 2) > 16 ? 32 : ((dim >> 2) > 8 ? 16 : 8)));  // rows per CTA sweep (train.cuh ln_lanes_per_row)
+  int64_t blocks = (rows + rpb - 1) / rpb;
   const int64_t cap = static_cast<int64_t>(sms) * (dim <= 128 ? 16 : 8);   // rows are latency chains: favour parallelism
   if (blocks > cap) blocks = cap;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dy_is_f16)
-    ln_bwd_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, dy, dim, m, static_cast<int>(rows), dim, do_ln, ln_w, eps,
-                                                                    dres, static_cast<__half*>(dx16), dim, dw_acc, db_acc);
-  else
-    ln_bwd_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, dy, dim, m, static_cast<int>(rows), dim, do_ln, ln_w, eps,
-                                                                     dres, static_cast<__half*>(dx16), dim, dw_acc, db_acc);
+  const unsigned grid = static_cast<unsigned>(blocks);
+  const int nr = static_cast<int>(rows);
+  __half* dx = static_cast<__half*>(dx16);
+  if (dy_is_f16) {
+    if (dim <= 128) ln_bwd_kernel<true, 1><<<grid, 256, 0, st>>>(x, dy, dim, m, nr, dim, do_ln, ln_w, eps, dres, dx, dim, dw_acc, db_acc);
+    else ln_bwd_kernel<true, 4><<<grid, 256, 0, st>>>(x, dy, dim, m, nr, dim, do_ln, ln_w, eps, dres, dx, dim, dw_acc, db_acc);
+  } else {
+    if (dim <= 128) ln_bwd_kernel<false, 1><<<grid, 256, 0, st>>>(x, dy, dim, m, nr, dim, do_ln, ln_w, eps, dres, dx, dim, dw_acc, db_acc);
+    else ln_bwd_kernel<false, 4><<<grid, 256, 0, st>>>(x, dy, dim, m, nr, dim, do_ln, ln_w, eps, dres, dx, dim, dw_acc, db_acc);
+  }
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -208,37 +208,48 @@ __device__ __forceinline__ float warp_sum(float s) {
   return s;
 }
 
-template <bool OUT_F16>
+// Sub-warp row groups: a row of C channels = nv = C/4 float4s is handled by `lpr` lanes (8, 16 or 32), so narrow stages
+// (C <= 64) process 2-4 rows per warp instead of idling lanes; reductions shuffle inside the group only.
+__device__ __forceinline__ int ln_lanes_per_row(int nv) { return nv > 16 ? 32 : (nv > 8 ? 16 : 8); }
+__device__ __forceinline__ float group_sum(float s, int lpr) {
+  for (int o = lpr >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+
+template <bool OUT_F16, int VPL>   // VPL float4s per lane: 1 for C <= 128, 4 up to C = 512
 __global__ void __launch_bounds__(256) ln_rows_any_kernel(const float* __restrict__ x, RowMap map, int n_rows, int C, int do_ln,
                                                           const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                                                           float eps, void* out, int ldo) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= n_rows) return;
-  const int tok = row_to_token(map, row);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = C >> 2;
-  float4 v[4];
+  const int lpr = ln_lanes_per_row(nv), rpw = 32 / lpr;
+  const int sub = lane / lpr, sl = lane - sub * lpr;
+  const int row = (blockIdx.x * 8 + warp) * rpw + sub;
+  const bool in_range = row < n_rows;
+  const int tok = in_range ? row_to_token(map, row) : -1;
+  float4 v[VPL];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int g = lane + 32 * i;
+  for (int i = 0; i < VPL; ++i) {
+    const int g = sl + lpr * i;
     v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (g < nv && tok >= 0) v[i] = *reinterpret_cast<const float4*>(x + static_cast<size_t>(tok) * C + 4 * g);
   }
   if (do_ln) {
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) s += v[i].x + v[i].y + v[i].z + v[i].w;
-    const float mean = warp_sum(s) / C;
+    for (int i = 0; i < VPL; ++i) s += v[i].x + v[i].y + v[i].z + v[i].w;
+    const float mean = group_sum(s, lpr) / C;
     float ss = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (lane + 32 * i < nv) {
+    for (int i = 0; i < VPL; ++i)
+      if (sl + lpr * i < nv) {
         const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
         ss += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
       }
-    const float rstd = rsqrtf(warp_sum(ss) / C + eps);
+    const float rstd = rsqrtf(group_sum(ss, lpr) / C + eps);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int g = lane + 32 * i;
+    for (int i = 0; i < VPL; ++i) {
+      const int g = sl + lpr * i;
       if (g < nv) {
         float4 w = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ln_w != nullptr) { w = __ldg(reinterpret_cast<const float4*>(ln_w) + g); b = __ldg(reinterpret_cast<const float4*>(ln_b) + g); }
@@ -247,9 +258,10 @@ __global__ void __launch_bounds__(256) ln_rows_any_kernel(const float* __restric
       }
     }
   }
+  if (!in_range) return;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int g = lane + 32 * i;
+  for (int i = 0; i < VPL; ++i) {
+    const int g = sl + lpr * i;
     if (g >= nv) continue;
     if (OUT_F16) {
       const float4 t = tok >= 0 ? v[i] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -272,34 +284,29 @@ __global__ void __launch_bounds__(256) ln_rows_any_kernel(const float* __restric
 // Persistent CTAs (grid-stride over rows) so the per-channel dw/db partials live in registers and are flushed
 // with one atomicAdd per channel per CTA.
 // ----------------------------------------------------------------------------------------
-template <bool DY_F16>
+template <bool DY_F16, int VPL>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ x, const void* __restrict__ dy, int lddy, RowMap map,
                                                      int n_rows, int C, int do_ln, const float* __restrict__ ln_w, float eps,
                                                      float* dres, __half* dx16, int lddx, float* dw_acc, float* db_acc) {
-  __shared__ float s_acc[8][512];
+  __shared__ float s_acc[4096];                 // [8 warps * rows-per-warp][C]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = C >> 2;
-  float4 aw[4], ab[4];
+  const int lpr = ln_lanes_per_row(nv), rpw = 32 / lpr;
+  const int sub = lane / lpr, sl = lane - sub * lpr;
+  float4 aw[VPL], ab[VPL];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { aw[i] = make_float4(0.f, 0.f, 0.f, 0.f); ab[i] = aw[i]; }
-  for (int row = blockIdx.x * 8 + warp; row < n_rows; row += gridDim.x * 8) {
-    const int tok = row_to_token(map, row);
-    if (tok < 0) {
-      if (dx16) {
+  for (int i = 0; i < VPL; ++i) { aw[i] = make_float4(0.f, 0.f, 0.f, 0.f); ab[i] = aw[i]; }
+  for (int base_row = (blockIdx.x * 8 + warp) * rpw; base_row < n_rows; base_row += gridDim.x * 8 * rpw) {
+    const int row = base_row + sub;
+    const bool in_range = row < n_rows;
+    const int tok = in_range ? row_to_token(map, row) : -1;
+    const bool act = tok >= 0;
+    float4 xv[VPL], gv[VPL];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int g = lane + 32 * i;
-          if (g < nv) *reinterpret_cast<uint2*>(dx16 + static_cast<size_t>(row) * lddx + 4 * g) = make_uint2(0u, 0u);
-        }
-      }
-      continue;
-    }
-    float4 xv[4], gv[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int g = lane + 32 * i;
+    for (int i = 0; i < VPL; ++i) {
+      const int g = sl + lpr * i;
       xv[i] = make_float4(0.f, 0.f, 0.f, 0.f); gv[i] = xv[i];
-      if (g < nv) {
+      if (g < nv && act) {
         if (do_ln) xv[i] = *reinterpret_cast<const float4*>(x + static_cast<size_t>(tok) * C + 4 * g);
         if (DY_F16) {
           const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(dy) + static_cast<size_t>(row) * lddy + 4 * g);
@@ -314,24 +321,26 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ x
     if (do_ln) {
       float s = 0.f;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) s += xv[i].x + xv[i].y + xv[i].z + xv[i].w;
-      const float mean = warp_sum(s) / C;
+      for (int i = 0; i < VPL; ++i) s += xv[i].x + xv[i].y + xv[i].z + xv[i].w;
+      const float mean = group_sum(s, lpr) / C;
       float ss = 0.f;
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (lane + 32 * i < nv) {
+      for (int i = 0; i < VPL; ++i)
+        if (sl + lpr * i < nv) {
           xv[i].x -= mean; xv[i].y -= mean; xv[i].z -= mean; xv[i].w -= mean;
           ss += xv[i].x * xv[i].x + xv[i].y * xv[i].y + xv[i].z * xv[i].z + xv[i].w * xv[i].w;
         }
-      const float rstd = rsqrtf(warp_sum(ss) / C + eps);
+      const float rstd = rsqrtf(group_sum(ss, lpr) / C + eps);
       float sg = 0.f, sgx = 0.f;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int g = lane + 32 * i;
+      for (int i = 0; i < VPL; ++i) {
+        const int g = sl + lpr * i;
         if (g < nv) {
           xv[i].x *= rstd; xv[i].y *= rstd; xv[i].z *= rstd; xv[i].w *= rstd;      // xhat
-          aw[i].x += gv[i].x * xv[i].x; aw[i].y += gv[i].y * xv[i].y; aw[i].z += gv[i].z * xv[i].z; aw[i].w += gv[i].w * xv[i].w;
-          ab[i].x += gv[i].x; ab[i].y += gv[i].y; ab[i].z += gv[i].z; ab[i].w += gv[i].w;
+          if (act) {
+            aw[i].x += gv[i].x * xv[i].x; aw[i].y += gv[i].y * xv[i].y; aw[i].z += gv[i].z * xv[i].z; aw[i].w += gv[i].w * xv[i].w;
+            ab[i].x += gv[i].x; ab[i].y += gv[i].y; ab[i].z += gv[i].z; ab[i].w += gv[i].w;
+          }
           if (ln_w != nullptr) {
             const float4 w = __ldg(reinterpret_cast<const float4*>(ln_w) + g);
             gv[i].x *= w.x; gv[i].y *= w.y; gv[i].z *= w.z; gv[i].w *= w.w;
@@ -340,44 +349,46 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ x
           sgx += gv[i].x * xv[i].x + gv[i].y * xv[i].y + gv[i].z * xv[i].z + gv[i].w * xv[i].w;
         }
       }
-      const float mg = warp_sum(sg) / C, mgx = warp_sum(sgx) / C;
+      const float mg = group_sum(sg, lpr) / C, mgx = group_sum(sgx, lpr) / C;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < VPL; ++i) {
         gv[i].x = rstd * (gv[i].x - mg - xv[i].x * mgx); gv[i].y = rstd * (gv[i].y - mg - xv[i].y * mgx);
         gv[i].z = rstd * (gv[i].z - mg - xv[i].z * mgx); gv[i].w = rstd * (gv[i].w - mg - xv[i].w * mgx);
       }
     }
+    if (!in_range) continue;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int g = lane + 32 * i;
+    for (int i = 0; i < VPL; ++i) {
+      const int g = sl + lpr * i;
       if (g >= nv) continue;
-      if (dres) {
+      if (dres && act) {
         float4* p = reinterpret_cast<float4*>(dres + static_cast<size_t>(tok) * C + 4 * g);
         float4 r = *p;
         r.x += gv[i].x; r.y += gv[i].y; r.z += gv[i].z; r.w += gv[i].w;
         *p = r;
       }
-      if (dx16)
-        *reinterpret_cast<uint2*>(dx16 + static_cast<size_t>(row) * lddx + 4 * g) =
-            make_uint2(pack_h2(gv[i].x, gv[i].y), pack_h2(gv[i].z, gv[i].w));
+      if (dx16) {
+        const float4 t = act ? gv[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<uint2*>(dx16 + static_cast<size_t>(row) * lddx + 4 * g) = make_uint2(pack_h2(t.x, t.y), pack_h2(t.z, t.w));
+      }
     }
   }
   if (!do_ln || (dw_acc == nullptr && db_acc == nullptr)) return;
-  // flush dw, then db: 8 warps -> smem -> one atomicAdd per channel
+  // flush dw, then db: (8 warps x rows-per-warp) partial rows -> smem -> one atomicAdd per channel
+  const int nparts = 8 * rpw;
   for (int pass = 0; pass < 2; ++pass) {
     float* acc = pass == 0 ? dw_acc : db_acc;
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int g = lane + 32 * i;
-      if (g < nv) *reinterpret_cast<float4*>(&s_acc[warp][4 * g]) = pass == 0 ? aw[i] : ab[i];
+    for (int i = 0; i < VPL; ++i) {
+      const int g = sl + lpr * i;
+      if (g < nv) *reinterpret_cast<float4*>(&s_acc[(warp * rpw + sub) * C + 4 * g]) = pass == 0 ? aw[i] : ab[i];
     }
     __syncthreads();
     if (acc != nullptr)
       for (int c = threadIdx.x; c < C; c += 256) {
         float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) s += s_acc[w][c];
+        for (int w = 0; w < nparts; ++w) s += s_acc[w * C + c];
         atomicAdd(acc + c, s);
       }
   }

@@ -38,11 +38,12 @@ def pack_conv_weight(w: torch.Tensor, channels_last_input: bool, bn: int = 0) ->
     return _swizzle_tiles(w2, bn or co)
 
 
-def lstm_row_order(dim: int, cw: int) -> torch.Tensor:
-    """Row permutation of the [4C, 2C] gate weight: tile j = [f|i|o|g] x channels [j*cw,(j+1)*cw)."""
-    j = torch.arange(dim // cw).view(-1, 1, 1)
-    g = torch.arange(4).view(1, 4, 1)
-    c = torch.arange(cw).view(1, 1, cw)
+def lstm_row_order(dim: int, cw: int, device=None) -> torch.Tensor:
+    """Row permutation of the [4C, 2C] gate weight: tile j = [f|i|o|g] x channels [j*cw,(j+1)*cw).
+    Built on `device` directly (no host->device copy, so weight re-packing can be captured in a CUDA graph)."""
+    j = torch.arange(dim // cw, device=device).view(-1, 1, 1)
+    g = torch.arange(4, device=device).view(1, 4, 1)
+    c = torch.arange(cw, device=device).view(1, 1, cw)
     return (g * dim + j * cw + c).reshape(-1)
 
 
@@ -50,7 +51,7 @@ def pack_lstm_weight(w: torch.Tensor, b: torch.Tensor, cw: int):
     """conv1x1 weight [4C, 2C, 1, 1] + bias [4C] -> (tile images with BN = 4*cw, tiled bias)."""
     dim = w.shape[0] // 4
     w2 = w.detach().float().reshape(4 * dim, 2 * dim)
-    order = lstm_row_order(dim, cw).to(w.device)
+    order = lstm_row_order(dim, cw, w.device)
     return _swizzle_tiles(w2[order], 4 * cw), b.detach().float()[order].contiguous()
 
 
