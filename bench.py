@@ -320,10 +320,8 @@ def run_train(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(2):
-        loss, n_coll = step()
     if not args.train_eager:
-        capture()
+        capture()            # (no eager step before this: AccumulateGrad nodes must first be created on the capture stream)
     for _ in range(max(args.warmup, 3)):
         loss, n_coll = step()
     assert torch.isfinite(loss.detach()).item(), 'non-finite training loss'

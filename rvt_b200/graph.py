@@ -46,7 +46,9 @@ def capture_training_step(model, fwd_bwd: Callable[[], torch.Tensor], params, wa
     rvt_b200.train — into ONE CUDA graph.  ``fwd_bwd`` must read its inputs from static tensors.  After the capture every
     ``p.grad`` is a static tensor (a view of the flat gradient buffer) that each replay OVERWRITES; run the all-reduce and
     the optimizer eagerly after the replay and do not call ``zero_grad(set_to_none=True)`` any more.  The re-packing of
-    the (optimizer-updated) weights is part of the graph.  Returns a callable giving the static loss tensor."""
+    the (optimizer-updated) weights is part of the graph.  Call this BEFORE any eager training step that is still
+    referenced (a live loss keeps AccumulateGrad nodes bound to the default stream, which cannot join a capture).
+    Returns a callable giving the static loss tensor."""
     eng = model._train_engine()
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
@@ -59,9 +61,11 @@ def capture_training_step(model, fwd_bwd: Callable[[], torch.Tensor], params, wa
     torch.cuda.synchronize()
     for p in params:
         p.grad = None
+    import gc
+    gc.collect()                          # drop dead autograd graphs: their AccumulateGrad nodes pin the stream they were made on
     eng.invalidate()                      # the packed-weight refresh must be recorded in the graph
     g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
+    with torch.cuda.graph(g, stream=side):
         loss = fwd_bwd()
 
     def replay():
