@@ -251,6 +251,7 @@ def run_train(args, rank, world, local_rank):
     model.load_state_dict(bo.synth_params(spec, 0), strict=True)
     model = model.to(dev).train()
     model.pad_to_hw = (PAD_H, PAD_W)
+    model.train_wavefront = not args.no_wavefront     # stage-per-stream schedule, forward and (via autograd) backward
     lo, hi = sharding.batch_slice(B * world, rank, world)
     n_seq = 4                                                        # rotate sequences: 4 x 290 MB of uint8 inputs > L2
     seqs = [make_uint8_sequence(4321 + lo * 10 + i, SEQ_LEN, B).to(dev) for i in range(n_seq)]
@@ -357,7 +358,8 @@ def run_train(args, rank, world, local_rank):
                        'l2_policy': f'{n_seq} rotating input sequences ({n_seq * seqs[0].numel() >> 20} MB) > L2',
                        'parallelism': f'batch-sharded x{world}; {n_coll} NCCL all-reduce of {n_par * 4 >> 20} MB fp32 gradients per step',
                        'loss_scale': LOSS_SCALE},
-            'schedule': 'eager launches' if args.train_eager else 'fwd+bwd replayed as one CUDA graph; all-reduce + Adam eager',
+            'schedule': ('eager launches' if args.train_eager else 'fwd+bwd replayed as one CUDA graph; all-reduce + Adam eager') +
+                        ('' if args.no_wavefront else '; stage-per-stream wavefront (4 streams)'),
             'clocks': clocks, 'phases_ms': acc_ms, 'cpu_issue_ms': cpu_ms if args.train_eager else None, 'final_loss': float(loss.detach()) / LOSS_SCALE, 'grads_finite': grad_ok,
         }), flush=True)
     if world > 1:

@@ -154,9 +154,10 @@ int rvt_linear_ex(const void* a, int64_t m, int k, int n, const void* w_packed, 
                   const void* aux, void* out, int out_f32, void* stream);
 /* Weight gradient: g[i*s_i + j*s_j] += sum_m a1[m,i] * a2[m,j]; a1 f16 [m,n1] (ld1), a2 f16 [m,n2] (ld2).
  * mode 0: operands consumed in place as MN-major tcgen05 tiles; mode 1: transposed copies in scratch_t
- * (f16, rvt_gemm_tn_scratch_elems() elements) and K-major tiles. */
+ * (f16, rvt_gemm_tn_scratch_elems() elements) and K-major tiles.  colsum1 / colsum2 (optional, f32 [n1] / [n2]):
+ * += the column sums of a1 / a2 (bias gradients), accumulated from the operand tiles while they sit in shared memory. */
 int rvt_gemm_tn(const void* a1, int ld1, int n1, const void* a2, int ld2, int n2, int64_t m, float* g, int64_t s_i,
-                int64_t s_j, int mode, void* scratch_t, void* stream);
+                int64_t s_j, int mode, void* scratch_t, float* colsum1, float* colsum2, void* stream);
 int64_t rvt_gemm_tn_scratch_elems(int64_t m, int n1, int n2);
 /* Row maps: map_mode 0 identity (rows = tokens), 1 window, 2 grid partition order (rvt_attention_scratch_rows rows). */
 /* out16[row] = LayerNorm(x[token(row)]) (x itself if !do_ln), f16 [rows, dim]; rows without a token are zero. */
@@ -177,9 +178,13 @@ int rvt_attn_core_bwd(const void* qkv, const void* o, const void* dout, void* dq
 /* Conv-LSTM gates backward (rnn.py:57-67): dpre f16 [n,4C] ([f|i|o|g] = rows of conv1x1.weight), dc_prev f32 [n,C]. */
 int rvt_lstm_gates_bwd(const void* gates, const float* c_prev, const float* c_new, const float* dh, const float* dc,
                        int64_t n_tokens, int dim, void* dpre, float* dc_prev, void* stream);
-/* Downsample conv operand: col f16 [B*Hout*Wout, round_up(k*k*cin, 8)], K order (ky, kx, ci). */
+/* Downsample conv operand: col f16 [B*Hout*Wout, round_up(k*k*cin, 8)]; K order (ky, kx, ci) for channels-last inputs,
+ * (ci, ky, kx) for NCHW inputs. */
 int rvt_im2col(const void* in, int in_dtype, int in_nchw, int batch, int cin, int hin, int win, int ksize, int stride,
                int pad, int hout, int wout, void* col, void* stream);
+/* NCHW (in_dtype 0 f32 / 1 u8 / 2 f16) -> channels-last f16 [B,H,W,channels_padded] (zero padded channels). */
+int rvt_nchw_to_nhwc_f16(const void* in, int in_dtype, int batch, int channels, int height, int width,
+                         int channels_padded, void* out, void* stream);
 /* d_in f32 [B,Hin,Win,Cin] = col2im(dcol f16 [B*Hout*Wout, round_up(k*k*cin, 8)]). */
 int rvt_col2im(const void* dcol, int batch, int cin, int hin, int win, int ksize, int stride, int pad, int hout,
                int wout, float* d_in, void* stream);

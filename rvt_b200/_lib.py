@@ -37,7 +37,8 @@ SIGNATURES = {
     'rvt_mlp_block_train': (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'rvt_dws_conv_lstm_train': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'rvt_linear_ex': (_i, [_vp, _i64, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp]),
-    'rvt_gemm_tn': (_i, [_vp, _i, _i, _vp, _i, _i, _i64, _vp, _i64, _i64, _i, _vp, _vp]),
+    'rvt_gemm_tn': (_i, [_vp, _i, _i, _vp, _i, _i, _i64, _vp, _i64, _i64, _i, _vp, _vp, _vp, _vp]),
+    'rvt_nchw_to_nhwc_f16': (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     'rvt_gemm_tn_scratch_elems': (_i64, [_i64, _i, _i]),
     'rvt_ln_rows_f16': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _f, _vp, _vp]),
     'rvt_ln_bwd': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp]),

@@ -655,7 +655,7 @@ int64_t rvt_gemm_tn_scratch_elems(int64_t m, int n1, int n2) {
 }
 
 int rvt_gemm_tn(const void* a1, int ld1, int n1, const void* a2, int ld2, int n2, int64_t m, float* g, int64_t s_i,
-                int64_t s_j, int mode, void* scratch_t, void* stream) {
+                int64_t s_j, int mode, void* scratch_t, float* colsum1, float* colsum2, void* stream) {
   if (!a1 || !a2 || !g || m < 0 || n1 < 1 || n2 < 1 || ld1 % 8 || ld2 % 8) return kErrBadArg;
   if (m == 0) return 0;
   if (m > 0x7fffffffLL) return kErrUnsupported;
@@ -666,6 +666,14 @@ int rvt_gemm_tn(const void* a1, int ld1, int n1, const void* a2, int ld2, int n2
   a.kc_total = cdiv(m, 64);
   a.G = g; a.s_i = s_i; a.s_j = s_j;
   a.kmajor = mode == 1 ? 1 : 0;
+  if (a.kmajor) {                                           // column sums ride along only in the MN-major form
+    int rc = 0;
+    if (colsum1) rc = rvt_colsum(a1, m, n1, ld1, colsum1, stream);
+    if (!rc && colsum2) rc = rvt_colsum(a2, m, n2, ld2, colsum2, stream);
+    if (rc) return rc;
+  } else {
+    a.colsum1 = colsum1; a.colsum2 = colsum2;
+  }
   static int epi_env = -1;
   if (epi_env < 0) { const char* e = getenv("RVT_TN_EPI"); epi_env = e ? atoi(e) : 1; }
   a.epi_bulk = (epi_env == 1 && s_j == 1 && s_i % 4 == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0) ? 1 : 0;
@@ -813,9 +821,24 @@ int rvt_im2col(const void* in, int in_dtype, int in_nchw, int batch, int cin, in
         in, g, static_cast<__half*>(col));
     return static_cast<int>(cudaGetLastError());
   }
+  if (!in_nchw && cin % 8 == 0 && in_dtype != 1 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+    const int64_t nitems = static_cast<int64_t>(batch) * hout * wout * ksize * ksize * (cin / 8);
+    im2col_nhwc8_kernel<<<static_cast<unsigned>((nitems + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        in, g, static_cast<__half*>(col));
+    return static_cast<int>(cudaGetLastError());
+  }
   const int64_t items = static_cast<int64_t>(batch) * hout * wout * (g.ldc / 2);
   im2col_kernel<<<static_cast<unsigned>((items + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, g,
                                                                                                         static_cast<__half*>(col));
+  return static_cast<int>(cudaGetLastError());
+}
+
+int rvt_nchw_to_nhwc_f16(const void* in, int in_dtype, int batch, int channels, int height, int width, int channels_padded,
+                         void* out, void* stream) {
+  if (!in || !out || channels_padded % 8 != 0 || channels_padded < channels || batch < 1) return kErrBadArg;
+  const int64_t n = static_cast<int64_t>(batch) * height * width;
+  nchw_to_nhwc_f16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, in_dtype, batch, channels, height, width, channels_padded, static_cast<__half*>(out));
   return static_cast<int>(cudaGetLastError());
 }
 

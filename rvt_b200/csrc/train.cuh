@@ -35,6 +35,8 @@ struct TnArgs {
   int epi_bulk;        // 1: rows of the accumulator tile are staged in smem and added to G with cp.reduce.async.bulk (s_j == 1)
   float* G;
   long long s_i, s_j;
+  float* colsum1;      // optional: colsum1[i] += sum_m A1[m, i]  (bias gradient of the layer whose output gradient is A1)
+  float* colsum2;      // optional: colsum2[j] += sum_m A2[m, j]
 };
 
 constexpr int kTnThreads = 192;
@@ -74,8 +76,11 @@ __global__ void __launch_bounds__(kTnThreads) gemm_tn_kernel(const __grid_consta
   const int nkc = kc_hi - kc_lo;
   if (nkc <= 0) return;
 
+  // column sums ride along: the idle epilogue warps add up the operand tiles while they sit in shared memory (MN-major form)
+  const bool cs1 = a.colsum1 != nullptr && blockIdx.y == 0 && !a.kmajor;
+  const bool cs2 = a.colsum2 != nullptr && blockIdx.x == 0 && !a.kmajor;
   if (tid == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (cs1 || cs2) ? 5 : 1); }
     mbar_init(accum, 1);
     fence_mbar_init();
   }
@@ -132,6 +137,39 @@ __global__ void __launch_bounds__(kTnThreads) gemm_tn_kernel(const __grid_consta
     }
     __syncwarp();
   } else {
+    if (cs1 || cs2) {
+      // thread ch of the 128 epilogue threads owns channel ch of the A tile (and of the B tile): element (token k, channel ch)
+      // of an MN-major SW128 box sits at box*8192 + k*128 + (((ch & 63) >> 3) ^ (k & 7))*16 + (ch & 7)*2
+      const int ch = (warp - 2) * 32 + lane;
+      const uint32_t box_off = static_cast<uint32_t>(ch >> 6) * 8192u, cchunk = (ch & 63) >> 3, cbyte = (ch & 7) * 2;
+      float acc1 = 0.f, acc2 = 0.f;
+      const bool do1 = cs1 && (ch >> 6) < na, do2 = cs2 && ch < BN && (ch >> 6) < nb;
+      for (int it = 0; it < nkc; ++it) {
+        const int s = it % stages;
+        mbar_wait(&full[s], (it / stages) & 1);
+        const uint32_t at = sA + s * 16384u + box_off, bt = sB + s * b_bytes + box_off;
+        if (do1) {
+#pragma unroll 8
+          for (uint32_t k = 0; k < 64; ++k) {
+            unsigned short h;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(at + k * 128u + ((cchunk ^ (k & 7u)) << 4) + cbyte));
+            acc1 += __half2float(__ushort_as_half(h));
+          }
+        }
+        if (do2) {
+#pragma unroll 8
+          for (uint32_t k = 0; k < 64; ++k) {
+            unsigned short h;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(bt + k * 128u + ((cchunk ^ (k & 7u)) << 4) + cbyte));
+            acc2 += __half2float(__ushort_as_half(h));
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+      }
+      if (do1 && i0 + ch < a.N1) atomicAdd(a.colsum1 + i0 + ch, acc1);
+      if (do2 && j0 + ch < a.N2) atomicAdd(a.colsum2 + j0 + ch, acc2);
+    }
     const int q = warp & 3;                                  // TMEM lane quarter this warp may read
     const int r = q * 32 + lane;
     const int i = i0 + r;
@@ -634,6 +672,62 @@ __global__ void __launch_bounds__(256) im2col_kernel(const void* __restrict__ in
     else v[e] = __ldg(reinterpret_cast<const float*>(in) + off);
   }
   *reinterpret_cast<uint32_t*>(col + static_cast<size_t>(tok) * g.ldc + k0) = pack_h2(v[0], v[1]);
+}
+
+// Channels-last fast path (Cin % 8 == 0, fp16 or fp32 input): one thread per (token, tap, 8-channel group) = one 16-byte
+// store; K = KS*KS*Cin = ldc.
+__global__ void __launch_bounds__(256) im2col_nhwc8_kernel(const void* __restrict__ in, ConvGeom g, __half* __restrict__ col) {
+  const int cg = g.Cin >> 3, per_tok = g.KS * g.KS * cg;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long n_tok = static_cast<long long>(g.B) * g.Hout * g.Wout;
+  if (idx >= n_tok * per_tok) return;
+  const long long tok = idx / per_tok;
+  const int rem0 = static_cast<int>(idx - tok * per_tok);
+  const int tap = rem0 / cg, c0 = (rem0 - tap * cg) * 8;
+  const int ky = tap / g.KS, kx = tap - ky * g.KS;
+  const int hw = g.Hout * g.Wout;
+  const int b = static_cast<int>(tok / hw), rem = static_cast<int>(tok - static_cast<long long>(b) * hw);
+  const int oy = rem / g.Wout, ox = rem - oy * g.Wout;
+  const int iy = oy * g.stride - g.pad + ky, ix = ox * g.stride - g.pad + kx;
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (iy >= 0 && iy < g.Hin && ix >= 0 && ix < g.Win) {
+    const size_t off = ((static_cast<size_t>(b) * g.Hin + iy) * g.Win + ix) * g.Cin + c0;
+    if (g.in_dtype == 2) {
+      o = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(in) + off));
+    } else {
+      float v[8];
+      load8(reinterpret_cast<const float*>(in) + off, v);
+      o = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+    }
+  }
+  *reinterpret_cast<uint4*>(col + static_cast<size_t>(tok) * g.ldc + tap * g.Cin + c0) = o;
+}
+
+// NCHW (u8 / f32 / f16) -> channels-last fp16 [B, H, W, Cp], channels [C, Cp) zero (Cp % 8 == 0): lets the stem use the
+// vectorised im2col above.  One thread per pixel: reads are coalesced along W per channel, the Cp-channel row is written
+// as 16-byte vectors.
+__global__ void __launch_bounds__(256) nchw_to_nhwc_f16_kernel(const void* __restrict__ in, int in_dtype, int B, int C, int H, int W,
+                                                               int Cp, __half* __restrict__ out) {
+  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long hw = static_cast<long long>(H) * W;
+  if (pix >= B * hw) return;
+  const long long b = pix / hw, r = pix - b * hw;
+  __half* op = out + pix * Cp;
+  for (int c0 = 0; c0 < Cp; c0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = c0 + e;
+      v[e] = 0.f;
+      if (c < C) {
+        const size_t off = (static_cast<size_t>(b) * C + c) * hw + r;
+        if (in_dtype == 1) v[e] = static_cast<float>(__ldg(reinterpret_cast<const uint8_t*>(in) + off));
+        else if (in_dtype == 2) v[e] = __half2float(__ldg(reinterpret_cast<const __half*>(in) + off));
+        else v[e] = __ldg(reinterpret_cast<const float*>(in) + off);
+      }
+    }
+    *reinterpret_cast<uint4*>(op + c0) = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+  }
 }
 
 // NCHW input (the stem): one thread per (token, ci, ky) writes the KS consecutive columns (ci, ky, 0..KS-1) from KS

@@ -143,7 +143,7 @@ def linear_ex(a: torch.Tensor, m: int, k: int, n: int, w_packed: torch.Tensor, o
 
 
 def gemm_tn(a1: torch.Tensor, n1: int, a2: torch.Tensor, n2: int, m: int, g: torch.Tensor, transpose_out: bool = False,
-            mode: Optional[int] = None) -> None:
+            mode: Optional[int] = None, colsum1: Optional[torch.Tensor] = None, colsum2: Optional[torch.Tensor] = None) -> None:
     """g[n1, n2] += a1[:m, :n1]^T @ a2[:m, :n2]  (g f32; transpose_out: g is [n2, n1] and receives the transpose).
     The MMA tile is 128 rows of a1^T x up to 128 of a2^T: pass the wider operand as a1."""
     assert a1.dtype == torch.float16 and a2.dtype == torch.float16 and g.dtype == torch.float32
@@ -154,8 +154,10 @@ def gemm_tn(a1: torch.Tensor, n1: int, a2: torch.Tensor, n2: int, m: int, g: tor
     if mode == 1:
         scratch = torch.empty(L.rvt_gemm_tn_scratch_elems(m, n1, n2), dtype=torch.float16, device=a1.device)
     s_i, s_j = (1, n1) if transpose_out else (n2, 1)
+    for cs, n in ((colsum1, n1), (colsum2, n2)):
+        assert cs is None or (cs.dtype == torch.float32 and cs.numel() >= n)
     _lib.check(L.rvt_gemm_tn(_lib.ptr(a1), n1, n1, _lib.ptr(a2), n2, n2, m, _lib.ptr(g), s_i, s_j, mode,
-                             _lib.ptr(scratch), _stream(a1)), 'gemm_tn')
+                             _lib.ptr(scratch), _lib.ptr(colsum1), _lib.ptr(colsum2), _stream(a1)), 'gemm_tn')
 
 
 def ln_rows_f16(x: torch.Tensor, map_mode: int, part, ln_w, ln_b, do_ln: bool, eps: float, out16: torch.Tensor) -> None:
@@ -210,3 +212,10 @@ def col2im(dcol: torch.Tensor, b, cin, hin, win, ksize, stride, pad, hout, wout,
 def colsum(a: torch.Tensor, m: int, n: int, acc: torch.Tensor) -> None:
     assert a.dtype == torch.float16 and acc.dtype == torch.float32 and acc.numel() >= n
     _lib.check(_lib.lib().rvt_colsum(_lib.ptr(a), m, n, n, _lib.ptr(acc), _stream(a)), 'colsum')
+
+
+def nchw_to_nhwc_f16(x: torch.Tensor, channels_padded: int, out: torch.Tensor) -> None:
+    b, c, h, w = x.shape
+    assert out.dtype == torch.float16 and out.numel() >= b * h * w * channels_padded
+    _lib.check(_lib.lib().rvt_nchw_to_nhwc_f16(_lib.ptr(x), _IN_DTYPES[x.dtype], b, c, h, w, channels_padded, _lib.ptr(out),
+                                               _stream(x)), 'nchw_to_nhwc_f16')

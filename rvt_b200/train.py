@@ -69,15 +69,18 @@ class TrainEngine:
             if st.mask_token is not None:
                 pass  # parameter exists but token masks are rejected in forward (enable_masking trains with masks)
             w = d.conv.weight.detach().to(device).float()
-            k = d.kernel_size * d.kernel_size * st.dim_in
-            ldc = _ru(k, 8)
-            w2 = w.permute(0, 2, 3, 1).reshape(c, k)                       # K order (ky, kx, ci)
+            cin_p = _ru(st.dim_in, 8)                                      # im2col channel groups of 8 (the stem's 20 -> 24)
+            k = d.kernel_size * d.kernel_size * cin_p
+            ldc = k
+            w2 = torch.zeros(c, d.kernel_size, d.kernel_size, cin_p, device=device)
+            w2[..., :st.dim_in] = w.permute(0, 2, 3, 1)
+            w2 = w2.reshape(c, k)                                          # K order (ky, kx, ci)
             e = {
                 'conv_w': packing.pack_conv_weight(w, channels_last_input=s > 0, bn=L.rvt_conv_tile_n(c)),
                 'conv_w_u8': (packing.pack_stem_weight_u8(w) if s == 0 and d.kernel_size == 7 and d.factor == 4 else None),
                 'conv_wT': (plw(w2.t().contiguous(), L.rvt_tile_n(ldc, c))
                             if (s > 0 and ldc == k and L.rvt_tile_n(ldc, c) > 0) else None),
-                'k': k, 'ldc': ldc,
+                'k': k, 'ldc': ldc, 'cin_p': cin_p,
                 'ds_ln_w': f32(getattr(d.norm, 'weight', None)), 'ds_ln_b': f32(getattr(d.norm, 'bias', None)),
                 'blocks': [],
             }
@@ -124,9 +127,9 @@ class TrainEngine:
         for s, st in enumerate(m.stages):
             c = st.dim
             d = st.downsample_cf2cl
-            k = d.kernel_size * d.kernel_size * st.dim_in
+            k = d.kernel_size * d.kernel_size * _ru(st.dim_in, 8)
             pre = f'stages.{s}.'
-            lay += [(pre + 'conv.GT', (_ru(k, 8), c)), (pre + 'conv.ln_w', (c,)), (pre + 'conv.ln_b', (c,))]
+            lay += [(pre + 'conv.GT', (k, c)), (pre + 'conv.ln_w', (c,)), (pre + 'conv.ln_b', (c,))]
             for bi, pair in enumerate(st.att_blocks):
                 for kind, att in (('att_window', pair.att_window), ('att_grid', pair.att_grid)):
                     bp = f'{pre}att_blocks.{bi}.{kind}.'
@@ -170,12 +173,9 @@ class TrainEngine:
             c = st.dim
             d = st.downsample_cf2cl
             pre = f'stages.{s}.'
-            k = d.kernel_size * d.kernel_size * st.dim_in
-            gt = A[pre + 'conv.GT'][:k].t()                          # [c, K]; K order (ci,ky,kx) for the NCHW stem, else (ky,kx,ci)
-            if s == 0:
-                g = gt.reshape(c, st.dim_in, d.kernel_size, d.kernel_size)
-            else:
-                g = gt.reshape(c, d.kernel_size, d.kernel_size, st.dim_in).permute(0, 3, 1, 2)
+            cin_p = _ru(st.dim_in, 8)
+            gt = A[pre + 'conv.GT'].t()                              # [c, K], K order (ky, kx, ci padded to 8)
+            g = gt.reshape(c, d.kernel_size, d.kernel_size, cin_p)[..., :st.dim_in].permute(0, 3, 1, 2)
             grads[pre + 'downsample_cf2cl.conv.weight'] = g.contiguous()
             if d.norm_affine:
                 grads[pre + 'downsample_cf2cl.norm.weight'] = A[pre + 'conv.ln_w'].clone()
@@ -293,8 +293,7 @@ class TrainEngine:
         dpre = f16(n_pad * 4 * c)
         dc_prev = torch.empty(shape, dtype=torch.float32, device=dev) if need_cp else None
         ops.lstm_gates_bwd(saved['gates'], cp, c_new, dh, dc, n_tok, c, dpre, dc_prev)
-        ops.gemm_tn(dpre, 4 * c, saved['xh'], 2 * c, n_tok, A[pre + 'lstm.G'])
-        ops.colsum(dpre, n_tok, 4 * c, A[pre + 'lstm.s'])
+        ops.gemm_tn(dpre, 4 * c, saved['xh'], 2 * c, n_tok, A[pre + 'lstm.G'], colsum1=A[pre + 'lstm.s'])
         dres = torch.empty(shape, dtype=torch.float32, device=dev)
         ops.linear_ex(dpre, n_tok, 4 * c, c, pk['lstm_wxT'], dres)
         dh_prev = None
@@ -308,12 +307,10 @@ class TrainEngine:
             # MLP half: x2 = x1 + g2 * (fc2(gelu(fc1(norm2(x1)))) )
             d0, d1 = f16(n_pad * c), (f16(n_pad * c) if blk['g2'] is not None else None)
             ops.gather_cast(dres, 0, None, blk['g2'], d0, d1)
-            ops.gemm_tn(sv['act'], hid, d0, c, n_tok, A[bp + 'fc2.G0T'])
-            ops.colsum(d0, n_tok, c, A[bp + 'fc2.s0'])
+            ops.gemm_tn(sv['act'], hid, d0, c, n_tok, A[bp + 'fc2.G0T'], colsum2=A[bp + 'fc2.s0'])
             dpre_m = f16(n_pad * hid)
             ops.linear_ex(d1 if d1 is not None else d0, n_tok, c, hid, blk['w2T'], dpre_m, act=2, aux=sv['pre'])
-            ops.gemm_tn(dpre_m, hid, sv['xn2'], c, n_tok, A[bp + 'fc1.G'])
-            ops.colsum(dpre_m, n_tok, hid, A[bp + 'fc1.s'])
+            ops.gemm_tn(dpre_m, hid, sv['xn2'], c, n_tok, A[bp + 'fc1.G'], colsum1=A[bp + 'fc1.s'])
             dxn = f16(n_pad * c)
             ops.linear_ex(dpre_m, n_tok, hid, c, blk['w1T'], dxn)
             ops.ln_bwd(sv['x_mid'], dxn, shape, 0, None, blk['n2_w'], True, eps, dres, None, A[bp + 'n2_w'], A[bp + 'n2_b'])
@@ -322,16 +319,14 @@ class TrainEngine:
             rows, mm, part = sv['rows'], blk['map_mode'], blk['part']
             d0, d1 = f16(rows * c), (f16(rows * c) if blk['g1'] is not None else None)
             ops.gather_cast(dres, mm, part, blk['g1'], d0, d1)
-            ops.gemm_tn(d0, c, sv['o'], c, rows, A[bp + 'proj.G0'])
-            ops.colsum(d0, rows, c, A[bp + 'proj.s0'])
+            ops.gemm_tn(d0, c, sv['o'], c, rows, A[bp + 'proj.G0'], colsum1=A[bp + 'proj.s0'])
             do = f16(rows * c)
             ops.linear_ex(d1 if d1 is not None else d0, rows, c, c, blk['wprojT'], do)
             groups_rows = b * (hh // part[0]) * (ww // part[1]) * _lib.lib().rvt_rows_per_group(part[0] * part[1])
             dqkv = f16(rows * 3 * c) if groups_rows == rows else torch.zeros(rows * 3 * c, dtype=torch.float16, device=dev)
             ops.attn_core_bwd(sv['qkv'], sv['o'], do, dqkv, shape, part, blk['dh'])
             do_ln = blk['n1_w'] is not None
-            ops.gemm_tn(dqkv, 3 * c, sv['xn1'], c, rows, A[bp + 'qkv.G'])
-            ops.colsum(dqkv, rows, 3 * c, A[bp + 'qkv.s'])
+            ops.gemm_tn(dqkv, 3 * c, sv['xn1'], c, rows, A[bp + 'qkv.G'], colsum1=A[bp + 'qkv.s'])
             dxn = f16(rows * c)
             ops.linear_ex(dqkv, rows, 3 * c, c, blk['wqkvT'], dxn)
             ops.ln_bwd(sv['x_in'] if do_ln else None, dxn, shape, mm, part, blk['n1_w'], do_ln, eps, dres, None,
@@ -344,7 +339,13 @@ class TrainEngine:
                    A[pre + 'conv.ln_b'] if pk['ds_ln_w'] is not None else None)
         ldc = pk['ldc']
         col = f16(n_tok * ldc)
-        ops.im2col(saved['cur'], saved['cur_nchw'], ks, stride, pad, hh, ww, col)
+        src = saved['cur']
+        if saved['cur_nchw']:
+            # the stem's NCHW events -> channels-last fp16 (channels padded to a multiple of 8) so im2col is 16-byte vectors
+            nhwc = f16(bq * hin * win * pk['cin_p'])
+            ops.nchw_to_nhwc_f16(src, pk['cin_p'], nhwc)
+            src = nhwc.view(bq, hin, win, pk['cin_p'])
+        ops.im2col(src, False, ks, stride, pad, hh, ww, col)
         ops.gemm_tn(col, ldc, dy16, c, n_tok, A[pre + 'conv.GT'])
         d_cur = None
         if need_in:
@@ -418,7 +419,13 @@ def _nhwc(t: torch.Tensor) -> torch.Tensor:
 
 
 def forward_train(model, x: torch.Tensor, prev_states, token_mask):
-    """RNNDetector.forward under grad mode (maxvit_rnn.py:93-105)."""
+    """RNNDetector.forward under grad mode (maxvit_rnn.py:93-105).
+
+    ``model.train_wavefront = True`` (opt-in) enqueues stage s on its own CUDA stream (stage s of step t only waits for
+    stage s-1 of step t and — by stream order — for its own step t-1), exactly like ``forward_sequence``: consecutive
+    forward calls then overlap across stages, and because autograd replays every node's backward on the stream of its
+    forward, the backward pass gets the mirrored wavefront for free.  The current stream waits for all stage streams
+    before this function returns, so callers may use the outputs as usual."""
     if token_mask is not None:
         raise NotImplementedError('rvt_b200 training: token_mask is not built (enable_masking is False in every released config)')
     eng: TrainEngine = model._train_engine()
@@ -432,17 +439,57 @@ def forward_train(model, x: torch.Tensor, prev_states, token_mask):
     if token is None:
         token = _GradSink.apply(eng, *eng.params)
     x = model._prep_input(x)
-    eng.packed(x.device)                              # re-pack if an optimizer step changed the parameters
+    dev = x.device
+    eng.packed(dev)                                   # re-pack if an optimizer step changed the parameters
+    eng.acc(dev)                                      # accumulators exist before any stage stream may touch them
+    n = model.num_stages
+    main = torch.cuda.current_stream(dev)
+    wavefront = bool(getattr(model, 'train_wavefront', False))
+    if wavefront:
+        if getattr(eng, '_streams', None) is None or eng._streams[0].device != dev:
+            eng._streams = [torch.cuda.Stream(dev, priority=(-1 if s >= 2 else 0)) for s in range(n)]
+        streams = eng._streams
+        capturing = torch.cuda.is_current_stream_capturing()
+        ready = torch.cuda.Event()
+        ready.record(main)                             # inputs / states / re-packed weights prepared on the caller's stream
     states, output = [], {}
     cur, cur_nchw = x, True
-    for s in range(model.num_stages):
-        hp = cp = None
-        if prev_states[s] is not None:
-            hp, cp = (_nhwc(t) for t in prev_states[s])
-        h_new, c_new = _StageFn.apply(eng, s, cur_nchw, token, cur, hp, cp)
+    prev_done = None
+    for s in range(n):
+        if wavefront:
+            streams[s].wait_event(ready)
+            if prev_done is not None:
+                streams[s].wait_event(prev_done)
+            ctx_mgr = torch.cuda.stream(streams[s])
+        else:
+            ctx_mgr = _NullCtx()
+        with ctx_mgr:
+            hp = cp = None
+            if prev_states[s] is not None:
+                hp, cp = (_nhwc(t) for t in prev_states[s])
+            h_new, c_new = _StageFn.apply(eng, s, cur_nchw, token, cur, hp, cp)
+            if wavefront:
+                prev_done = torch.cuda.Event()
+                prev_done.record(streams[s])
+                if not capturing:
+                    h_new.record_stream(main)
+                    c_new.record_stream(main)
+                    if s + 1 < n:
+                        h_new.record_stream(streams[s + 1])
         h_nchw, c_nchw = h_new.permute(0, 3, 1, 2), c_new.permute(0, 3, 1, 2)
         h_nchw._rvt_token = (token, eng.gen)
         states.append((h_nchw, c_nchw))
         output[s + 1] = h_nchw
         cur, cur_nchw = h_new, False
+    if wavefront:
+        for st_ in streams:
+            main.wait_stream(st_)
     return output, states
+
+
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False

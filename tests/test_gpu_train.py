@@ -44,10 +44,12 @@ def run_ours(m, xs, dev):
     return outs, st
 
 
+@pytest.mark.parametrize('wavefront', [False, True])
 @pytest.mark.parametrize('name', list(GRAD_CASES))
-def test_gradients_match_reference_golden(name, dev):
+def test_gradients_match_reference_golden(name, wavefront, dev):
     case = BACKBONE_CASES[name]
     m, params, spec = build(case, dev)
+    m.train_wavefront = wavefront        # stage-per-stream schedule (forward and, through autograd, backward)
     xs = case_inputs(case, GRAD_CASES[name])
     outs, st = run_ours(m, xs, dev)
     for o in outs:

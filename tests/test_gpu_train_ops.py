@@ -34,9 +34,11 @@ def _check_gemm_tn(dev, mode, m, n1, n2):
     a2 = (torch.randn(m, n2, generator=g) * 0.5).to(dev).half()
     ref = a1.float().t() @ a2.float()
     acc = torch.zeros(n1, n2, device=dev)
-    ops.gemm_tn(a1, n1, a2, n2, m, acc, mode=mode)
+    cs1, cs2 = torch.ones(n1, device=dev), torch.ones(n2, device=dev)
+    ops.gemm_tn(a1, n1, a2, n2, m, acc, mode=mode, colsum1=cs1, colsum2=cs2)       # column sums ride along
     torch.cuda.synchronize()
     assert rel_l2(acc, ref) < 1e-3, (mode, rel_l2(acc, ref))
+    assert rel_l2(cs1 - 1, a1.float().sum(0)) < 1e-4 and rel_l2(cs2 - 1, a2.float().sum(0)) < 1e-4
     ops.gemm_tn(a1, n1, a2, n2, m, acc, mode=mode)          # accumulates
     assert rel_l2(acc, 2 * ref) < 1e-3
     acc_t = torch.zeros(n2, n1, device=dev)
@@ -261,3 +263,11 @@ def test_colsum(dev):
     acc = torch.ones(n, device=dev)
     ops.colsum(a, m, n, acc)
     assert rel_l2(acc - 1, a[:m].float().sum(0)) < 1e-4
+
+
+def test_nchw_to_nhwc_f16(dev):
+    from rvt_b200 import ops
+    x = torch.randint(0, 11, (2, 20, 13, 36), dtype=torch.uint8, device=dev)
+    out = torch.full((2, 13, 36, 24), 5.0, device=dev).half()
+    ops.nchw_to_nhwc_f16(x, 24, out)
+    assert torch.equal(out[..., :20], x.permute(0, 2, 3, 1).half()) and float(out[..., 20:].abs().max()) == 0.0
