@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(kTnThreads) gemm_tn_kernel(const __grid_consta
       }
       if (do1 && i0 + ch < a.N1) atomicAdd(a.colsum1 + i0 + ch, acc1);
       if (do2 && j0 + ch < a.N2) atomicAdd(a.colsum2 + j0 + ch, acc2);
+      named_bar_sync(1, 128);    // every epilogue warp is done reading the operand stages before any of them is reused as staging
     }
     const int q = warp & 3;                                  // TMEM lane quarter this warp may read
     const int r = q * 32 + lane;
