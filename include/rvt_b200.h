@@ -125,8 +125,9 @@ int rvt_linear_f16(const void* a, int64_t m, int k, int n, const void* w_packed,
  * s2d_scratch / stem_mode as in rvt_downsample_cf2cl. */
 int rvt_downsample_cf2cl_train(const void* in, int in_dtype, int in_nchw, int batch, int cin, int hin, int win,
                                int ksize, int stride, int pad, int hout, int wout, int cout, const void* w_packed,
-                               const float* ln_w, const float* ln_b, float eps, float* out, float* raw_out,
-                               void* s2d_scratch, int stem_mode, void* stream);
+                               const float* ln_w, const float* ln_b, float eps, const uint8_t* token_mask,
+                               const float* mask_token, float* out, float* raw_out, void* s2d_scratch, int stem_mode,
+                               void* stream);
 /* a4-a7 forward, training: out of place (x_out = x_in + ...), always the row-LN + three-kernel path; weights packed with
  * pack_linear_weight(bn = rvt_tile_n(...)); xn_save f16 [rows,C] (= norm1(x) rows in partition order), qkv_save f16
  * [rows,3C] and o_save f16 [rows,C] are kept for the backward. */

@@ -31,7 +31,7 @@ SIGNATURES = {
     'rvt_linear_f16': (_i, [_vp, _i64, _i, _i, _vp, _vp, _i, _vp, _vp]),
     # ---- training step ----
     'rvt_downsample_cf2cl_train': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f,
-                                         _vp, _vp, _vp, _i, _vp]),
+                                         _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     'rvt_partition_attention_train': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp,
                                             _vp, _vp, _vp, _vp, _vp, _vp]),
     'rvt_mlp_block_train': (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -311,11 +311,11 @@ int rvt_downsample_cf2cl(const void* in, int in_dtype, int in_nchw, int batch, i
 
 int rvt_downsample_cf2cl_train(const void* in, int in_dtype, int in_nchw, int batch, int cin, int hin, int win, int ksize,
                                int stride, int pad, int hout, int wout, int cout, const void* w_packed, const float* ln_w,
-                               const float* ln_b, float eps, float* out, float* raw_out, void* s2d_scratch, int stem_mode,
-                               void* stream) {
-  if (!raw_out) return kErrBadArg;
+                               const float* ln_b, float eps, const uint8_t* token_mask, const float* mask_token, float* out,
+                               float* raw_out, void* s2d_scratch, int stem_mode, void* stream) {
+  if (!raw_out || (token_mask && !mask_token)) return kErrBadArg;
   return downsample_impl(in, in_dtype, in_nchw, batch, cin, hin, win, ksize, stride, pad, hout, wout, cout, w_packed, ln_w,
-                         ln_b, eps, nullptr, nullptr, out, s2d_scratch, stem_mode, raw_out, stream);
+                         ln_b, eps, token_mask, mask_token, out, s2d_scratch, stem_mode, raw_out, stream);
 }
 
 static int partition_attention_impl(const float* x, float* x_out, int force_unfused, int batch, int height, int width, int dim,

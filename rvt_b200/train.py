@@ -66,8 +66,6 @@ class TrainEngine:
             d = st.downsample_cf2cl
             if st.lstm.dws_conv:
                 raise NotImplementedError('rvt_b200 training: dws_conv=True is not built (released configs use False)')
-            if st.mask_token is not None:
-                pass  # parameter exists but token masks are rejected in forward (enable_masking trains with masks)
             w = d.conv.weight.detach().to(device).float()
             cin_p = _ru(st.dim_in, 8)                                      # im2col channel groups of 8 (the stem's 20 -> 24)
             k = d.kernel_size * d.kernel_size * cin_p
@@ -82,6 +80,7 @@ class TrainEngine:
                             if (s > 0 and ldc == k and L.rvt_tile_n(ldc, c) > 0) else None),
                 'k': k, 'ldc': ldc, 'cin_p': cin_p,
                 'ds_ln_w': f32(getattr(d.norm, 'weight', None)), 'ds_ln_b': f32(getattr(d.norm, 'bias', None)),
+                'mask_token': f32(st.mask_token.reshape(-1)) if st.mask_token is not None else None,
                 'blocks': [],
             }
             for bi, pair in enumerate(st.att_blocks):
@@ -130,6 +129,8 @@ class TrainEngine:
             k = d.kernel_size * d.kernel_size * _ru(st.dim_in, 8)
             pre = f'stages.{s}.'
             lay += [(pre + 'conv.GT', (k, c)), (pre + 'conv.ln_w', (c,)), (pre + 'conv.ln_b', (c,))]
+            if st.mask_token is not None:
+                lay += [(pre + 'mask_token', (c,))]
             for bi, pair in enumerate(st.att_blocks):
                 for kind, att in (('att_window', pair.att_window), ('att_grid', pair.att_grid)):
                     bp = f'{pre}att_blocks.{bi}.{kind}.'
@@ -177,6 +178,8 @@ class TrainEngine:
             gt = A[pre + 'conv.GT'].t()                              # [c, K], K order (ky, kx, ci padded to 8)
             g = gt.reshape(c, d.kernel_size, d.kernel_size, cin_p)[..., :st.dim_in].permute(0, 3, 1, 2)
             grads[pre + 'downsample_cf2cl.conv.weight'] = g.contiguous()
+            if st.mask_token is not None:
+                grads[pre + 'mask_token'] = A[pre + 'mask_token'].reshape(1, 1, 1, c).clone()
             if d.norm_affine:
                 grads[pre + 'downsample_cf2cl.norm.weight'] = A[pre + 'conv.ln_w'].clone()
                 grads[pre + 'downsample_cf2cl.norm.bias'] = A[pre + 'conv.ln_b'].clone()
@@ -222,7 +225,7 @@ class TrainEngine:
         return self._zero_tok
 
     # ------------------------------------------------------------------ one stage, forward
-    def stage_forward(self, s: int, cur: torch.Tensor, cur_nchw: bool, hp, cp):
+    def stage_forward(self, s: int, cur: torch.Tensor, cur_nchw: bool, hp, cp, token_mask=None):
         """Training-mode RNNDetectorStage.forward; returns (h_new, c_new, saved)."""
         m = self.model
         st = m.stages[s]
@@ -248,10 +251,16 @@ class TrainEngine:
         conv_w, stem_mode = pk['conv_w'], 0
         if s == 0 and pk['conv_w_u8'] is not None and ops.stem_u8_ok(cur, cin, ks, stride, pad, (vh, vw), c):
             conv_w, stem_mode = pk['conv_w_u8'], 2
+        if token_mask is not None:
+            assert pk['mask_token'] is not None, 'No mask token present in this stage'
+            token_mask = token_mask.to(device=dev, dtype=torch.uint8).contiguous()
+            assert tuple(token_mask.shape) == (b, hh, ww)
         _lib.check(L.rvt_downsample_cf2cl_train(
             ptr(cur), ops._IN_DTYPES[cur.dtype], int(cur_nchw), b, cin, hin, win, ks, stride, pad, hh, ww, c, ptr(conv_w),
-            ptr(pk['ds_ln_w']), ptr(pk['ds_ln_b']), 1e-5, ptr(x), ptr(raw), None, stem_mode, stream), 'downsample_cf2cl_train')
-        saved = {'cur': cur, 'cur_nchw': cur_nchw, 'raw': raw, 'geom': (b, cin, hin, win, ks, stride, pad, hh, ww), 'blocks': []}
+            ptr(pk['ds_ln_w']), ptr(pk['ds_ln_b']), 1e-5, ptr(token_mask), ptr(pk['mask_token']), ptr(x), ptr(raw), None,
+            stem_mode, stream), 'downsample_cf2cl_train')
+        saved = {'cur': cur, 'cur_nchw': cur_nchw, 'raw': raw, 'geom': (b, cin, hin, win, ks, stride, pad, hh, ww), 'blocks': [],
+                 'token_mask': token_mask}
         for blk in pk['blocks']:
             rows = ops.attention_scratch_rows(b, hh, ww, blk['part'])
             hid = blk['hidden']
@@ -332,6 +341,12 @@ class TrainEngine:
             ops.ln_bwd(sv['x_in'] if do_ln else None, dxn, shape, mm, part, blk['n1_w'], do_ln, eps, dres, None,
                        A[bp + 'n1_w'] if do_ln else None, A[bp + 'n1_b'] if do_ln else None)
             del d0, d1, do, dqkv, dxn
+        # ---- mask token (maxvit_rnn.py:174-176): masked tokens took the token's value -> their gradient goes to it
+        if saved.get('token_mask') is not None:
+            mk = saved['token_mask'].reshape(-1, 1).to(torch.float32)
+            d2 = dres.view(-1, c)
+            A[pre + 'mask_token'].add_((d2 * mk).sum(0))
+            d2.mul_(1.0 - mk)
         # ---- downsample conv + LayerNorm (maxvit.py:174-178)
         bq, cin, hin, win, ks, stride, pad, _, _ = saved['geom']
         dy16 = f16(n_pad * c)
@@ -392,8 +407,8 @@ class _StageFn(torch.autograd.Function):
     """One RNNDetectorStage.forward (maxvit_rnn.py:169-182) as a single autograd node."""
 
     @staticmethod
-    def forward(ctx, engine: TrainEngine, s: int, cur_nchw: bool, token, cur, hp, cp):
-        h_new, c_new, saved = engine.stage_forward(s, cur, cur_nchw, hp, cp)
+    def forward(ctx, engine: TrainEngine, s: int, cur_nchw: bool, token, cur, hp, cp, token_mask=None):
+        h_new, c_new, saved = engine.stage_forward(s, cur, cur_nchw, hp, cp, token_mask)
         ctx.engine, ctx.s, ctx.saved = engine, s, saved
         ctx.save_for_backward(cp, c_new)
         return h_new, c_new
@@ -404,10 +419,10 @@ class _StageFn(torch.autograd.Function):
         cp, c_new = ctx.saved_tensors
         dh = None if dh is None else dh.contiguous().float()
         dc = None if dc is None else dc.contiguous().float()
-        need = ctx.needs_input_grad                    # (engine, s, cur_nchw, token, cur, hp, cp)
+        need = ctx.needs_input_grad                    # (engine, s, cur_nchw, token, cur, hp, cp, token_mask)
         d_cur, dh_prev, dc_prev = eng.stage_backward(ctx.s, ctx.saved, cp, c_new, dh, dc, need[4], need[5], need[6])
         ctx.saved = None
-        return None, None, None, eng.zero_token_grad(c_new.device), d_cur, dh_prev, dc_prev
+        return None, None, None, eng.zero_token_grad(c_new.device), d_cur, dh_prev, dc_prev, None
 
 
 def _nhwc(t: torch.Tensor) -> torch.Tensor:
@@ -426,8 +441,6 @@ def forward_train(model, x: torch.Tensor, prev_states, token_mask):
     forward calls then overlap across stages, and because autograd replays every node's backward on the stream of its
     forward, the backward pass gets the mirrored wavefront for free.  The current stream waits for all stage streams
     before this function returns, so callers may use the outputs as usual."""
-    if token_mask is not None:
-        raise NotImplementedError('rvt_b200 training: token_mask is not built (enable_masking is False in every released config)')
     eng: TrainEngine = model._train_engine()
     token = None
     for st in prev_states:
@@ -467,7 +480,7 @@ def forward_train(model, x: torch.Tensor, prev_states, token_mask):
             hp = cp = None
             if prev_states[s] is not None:
                 hp, cp = (_nhwc(t) for t in prev_states[s])
-            h_new, c_new = _StageFn.apply(eng, s, cur_nchw, token, cur, hp, cp)
+            h_new, c_new = _StageFn.apply(eng, s, cur_nchw, token, cur, hp, cp, token_mask if s == 0 else None)
             if wavefront:
                 prev_done = torch.cuda.Event()
                 prev_done.record(streams[s])

@@ -162,3 +162,34 @@ def test_optimizer_step_repacks_weights(dev):
         assert e < 2e-2, (s, e)
         moved = max(moved, float((st[s][0].detach() - before[s]).abs().max()))
     assert moved > 1e-3      # the step really changed the function
+
+
+def test_token_mask_gradients(dev):
+    """enable_masking: masked stage-1 tokens take the mask token (maxvit_rnn.py:174-176); its gradient and all others
+    match autograd through the oracle."""
+    case = BACKBONE_CASES['ls_init_mask']
+    spec = spec_of(case)
+    params = bo.synth_params(spec, case['seed'], 'uniform')
+    import rvt_b200
+    m = rvt_b200.RNNDetector(make_cfg(spec))
+    m.load_state_dict(params, strict=True)
+    m = m.to(dev).train()
+    xs = case_inputs(case, 2)
+    b, h, w = case['batch'], case['height'], case['width']
+    masks = [torch.from_numpy(np.random.RandomState(5 + t).uniform(size=(b, h // 4, w // 4)) < 0.2).to(dev) for t in range(2)]
+    outs, st = [], None
+    for x, mk in zip(xs, masks):
+        o, st = m(x.to(dev), st, mk)
+        outs.append(o)
+    train_loss(outs, st).backward()
+    po = {k: v.to(dev).requires_grad_(True) for k, v in params.items()}
+    o_outs, o_st = [], None
+    for x, mk in zip(xs, masks):
+        o, o_st = bo.backbone_forward(x.to(dev).float(), o_st, po, spec, mk)
+        o_outs.append(o)
+    train_loss(o_outs, o_st).backward()
+    worst = {k: float((p.grad - po[k].grad).double().norm() / po[k].grad.double().norm().clamp_min(1e-20))
+             for k, p in m.named_parameters()}
+    assert 'stages.0.mask_token' in worst
+    bad = {k: v for k, v in worst.items() if v > GRAD_TOL}
+    assert not bad, bad
