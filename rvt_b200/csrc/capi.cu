@@ -780,6 +780,27 @@ int rvt_attn_core_bwd(const void* qkv, const void* o, const void* dout, void* dq
   a.C = dim; a.dh = dim_head; a.nh = dim / dim_head; a.P = P; a.rows_per_win = rpg;
   a.n_groups = batch * (height / ph) * (width / pw);
   a.scale = 1.0f / sqrtf(static_cast<float>(dim_head));
+  static int tc_mode = -1;       // RVT_ATTN_BWD: 1 (default) tcgen05 kernel with paired tiles, 2 separate tiles, 0 fp32 SIMT kernel
+  if (tc_mode < 0) { const char* e = getenv("RVT_ATTN_BWD"); tc_mode = e ? atoi(e) : 1; }
+  if (tc_mode != 0 && dim_head % 8 == 0) {
+    const int64_t rows = rvt_attention_scratch_rows(batch, height, width, ph, pw);
+    AttnBwdTcArgs t{};
+    t.qkv = a.qkv; t.o = a.o; t.dout = a.dout; t.dqkv = a.dqkv;
+    t.C = dim; t.dh = dim_head; t.nh = a.nh; t.P = P; t.rows_per_win = rpg; t.n_groups = a.n_groups;
+    t.nkeys = rpg == 64 ? 128 : ((P + 15) / 16) * 16;
+    t.pair_tiles = tc_mode == 1 ? 1 : 0;
+    t.scale = a.scale; t.scale_log2e = a.scale * 1.4426950408889634f;
+    static bool tc_attr = false;
+    if (!tc_attr) {
+      cudaError_t e = cudaFuncSetAttribute(attn_core_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      tc_attr = true;
+    }
+    if (rows <= 0) return 0;
+    attn_core_bwd_tc_kernel<<<dim3(static_cast<unsigned>(rows / 128), t.nh), 128, attn_bwd_tc_smem_bytes(t.pair_tiles),
+                              static_cast<cudaStream_t>(stream)>>>(t);
+    return static_cast<int>(cudaGetLastError());
+  }
   const size_t smem = attn_bwd_smem_bytes(P);
   static bool attr_set = false;
   if (!attr_set) {

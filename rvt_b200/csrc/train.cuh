@@ -586,6 +586,185 @@ __global__ void __launch_bounds__(256) attn_core_bwd_kernel(const __grid_constan
 }
 
 // ----------------------------------------------------------------------------------------
+// Attention core backward on the tensor cores: one CTA per (128-row tile, head), thread t = tile row t.
+//   S = Q K^T and dA = dO V^T            (K-major operands: rows = tokens, 64 B of head dim, two tensors per 128-B row)
+//   A = softmax(S) over the row's own partition group, dS = A * (dA - delta) * scale, delta = rowsum(dO * O)
+//   dV = A^T dO, dK = dS^T Q             (contraction over QUERY rows: A / dS and dO / Q are consumed in place as MN-major
+//                                         operands — the row index is the K dimension — so nothing is transposed)
+//   dQ = dS K                            (dS K-major, K as MN-major B)
+// TMEM: S [0,128), dA [128,256); afterwards dV [0,32), dK [32,64), dQ [64,96).  Block-diagonal structure (two 64-row
+// groups per tile) and padding rows / keys are handled by zeros in the A / dS tiles.
+// pair_tiles = 1: Q|K share one SW128 tile (chunks 0-3 / 4-7 of a row) and V|dO another; 0: four separate tiles.
+// ----------------------------------------------------------------------------------------
+struct AttnBwdTcArgs {
+  const __half* qkv; const __half* o; const __half* dout; __half* dqkv;
+  int C, dh, nh, P, rows_per_win, n_groups, nkeys, pair_tiles;
+  float scale, scale_log2e;
+};
+__host__ __device__ inline size_t attn_bwd_tc_smem_bytes(int pair_tiles) {
+  return 1024 + (pair_tiles ? 2 : 4) * 16384 + 2 * 32768 + 64;
+}
+
+__global__ void __launch_bounds__(128) attn_core_bwd_tc_kernel(const __grid_constant__ AttnBwdTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw_addr);
+  const int nt = a.pair_tiles ? 2 : 4;
+  // operand homes: tile base + byte offset inside the 128-byte row
+  const uint32_t tQ = base, oQ = 0;
+  const uint32_t tK = a.pair_tiles ? base : base + 16384, oK = a.pair_tiles ? 64 : 0;
+  const uint32_t tV = a.pair_tiles ? base + 16384 : base + 32768, oV = 0;
+  const uint32_t tD = a.pair_tiles ? base + 16384 : base + 49152, oD = a.pair_tiles ? 64 : 0;
+  const uint32_t sP = base + nt * 16384, sDS = sP + 32768;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + nt * 16384 + 65536);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+
+  const int t = threadIdx.x, warp = t >> 5;
+  const int mt = blockIdx.x, hd = blockIdx.y;
+  const int dh = a.dh, P = a.P, rpw = a.rows_per_win, nkeys = a.nkeys;
+  const int C3 = 3 * a.C;
+
+  if (t == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  // zero the A / dS tiles (off-diagonal blocks, padding rows and keys stay zero) and the operand tiles' unused chunks
+  for (int i = t; i < (nt * 16384 + 65536) / 16; i += 128) st_smem_16B(base + i * 16, 0u, 0u, 0u, 0u);
+  __syncthreads();
+
+  // ---- stage row t of Q, K, V, dO; delta_t = sum_d dO[t][d] * O[t][d] ----
+  const size_t grow = static_cast<size_t>(mt) * 128 + t;
+  const __half* qrow = a.qkv + grow * C3 + hd * 3 * dh;
+  const __half* drow = a.dout + grow * a.C + hd * dh;
+  const __half* orow = a.o + grow * a.C + hd * dh;
+  float delta = 0.f;
+  for (int c = 0; c * 8 < dh; ++c) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(qrow + c * 8));
+    const uint4 k = __ldg(reinterpret_cast<const uint4*>(qrow + dh + c * 8));
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(qrow + 2 * dh + c * 8));
+    const uint4 d = __ldg(reinterpret_cast<const uint4*>(drow + c * 8));
+    const uint4 ov = __ldg(reinterpret_cast<const uint4*>(orow + c * 8));
+    st_smem_16B(tQ + sw128_offset(t, (oQ >> 4) + c), q.x, q.y, q.z, q.w);
+    st_smem_16B(tK + sw128_offset(t, (oK >> 4) + c), k.x, k.y, k.z, k.w);
+    st_smem_16B(tV + sw128_offset(t, (oV >> 4) + c), v.x, v.y, v.z, v.w);
+    st_smem_16B(tD + sw128_offset(t, (oD >> 4) + c), d.x, d.y, d.z, d.w);
+    const __half2* dh2 = reinterpret_cast<const __half2*>(&d);
+    const __half2* oh2 = reinterpret_cast<const __half2*>(&ov);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f0 = __half22float2(dh2[e]), f1 = __half22float2(oh2[e]);
+      delta = fmaf(f0.x, f1.x, fmaf(f0.y, f1.y, delta));
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_s = tmem, t_da = tmem + 128;
+
+  if (t == 0) {
+    const uint32_t idesc = umma_idesc_f16(128, nkeys, 0);
+    for (int k = 0; k < 2; ++k) {                               // head dim padded to 32 = 2 K steps
+      umma_f16(t_s, umma_desc_sw128(tQ + oQ + k * 32), umma_desc_sw128(tK + oK + k * 32), idesc, k != 0);
+      umma_f16(t_da, umma_desc_sw128(tD + oD + k * 32), umma_desc_sw128(tV + oV + k * 32), idesc, k != 0);
+    }
+    umma_commit(&bars[0]);
+  }
+  mbar_wait(&bars[0], 0);
+  tc_fence_after();
+
+  // ---- row t: softmax over its own group's keys, dS ----
+  const uint32_t trow = static_cast<uint32_t>(warp * 32) << 16;
+  const int key_lo = (t / rpw) * rpw;
+  const bool row_valid = (t - key_lo) < P && static_cast<int>(grow / rpw) < a.n_groups;
+  if (row_valid) {
+    float mx = -INFINITY;
+    for (int c0 = 0; c0 < P; c0 += 16) {
+      float v[16];
+      tmem_ld_x16(t_s + trow + key_lo + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 16; ++e)
+        if (c0 + e < P) mx = fmaxf(mx, v[e]);
+    }
+    float sum = 0.f;
+    for (int c0 = 0; c0 < P; c0 += 16) {
+      float v[16];
+      tmem_ld_x16(t_s + trow + key_lo + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 16; ++e)
+        if (c0 + e < P) sum += ex2_approx((v[e] - mx) * a.scale_log2e);
+    }
+    const float inv = 1.0f / sum;
+    for (int c0 = 0; c0 < P; c0 += 16) {
+      float v[16], g[16];
+      tmem_ld_x16(t_s + trow + key_lo + c0, v);
+      tmem_ld_x16(t_da + trow + key_lo + c0, g);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        float p = 0.f, ds = 0.f;
+        if (c0 + e < P) {
+          p = ex2_approx((v[e] - mx) * a.scale_log2e) * inv;
+          ds = p * (g[e] - delta) * a.scale;
+        }
+        v[e] = p; g[e] = ds;
+      }
+      const int key = key_lo + c0;
+      const uint32_t off = static_cast<uint32_t>(key >> 6) * 16384u, ch = (key & 63) >> 3;
+      st_smem_16B(sP + off + sw128_offset(t, ch), pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+      st_smem_16B(sP + off + sw128_offset(t, ch + 1), pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+      st_smem_16B(sDS + off + sw128_offset(t, ch), pack_h2(g[0], g[1]), pack_h2(g[2], g[3]), pack_h2(g[4], g[5]), pack_h2(g[6], g[7]));
+      st_smem_16B(sDS + off + sw128_offset(t, ch + 1), pack_h2(g[8], g[9]), pack_h2(g[10], g[11]), pack_h2(g[12], g[13]), pack_h2(g[14], g[15]));
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (t == 0) {
+    const uint32_t id_mn = umma_idesc_f16(128, 32, 0) | (1u << 15) | (1u << 16);     // A, B both MN-major
+    const uint32_t id_kmn = umma_idesc_f16(128, 32, 0) | (1u << 16);                 // A K-major, B MN-major
+    for (int k = 0; k < 8; ++k) {                               // contraction over the 128 query rows, 16 per step
+      umma_f16(tmem + 0, umma_desc_sw128_mn(sP + k * 2048, 16384), umma_desc_sw128_mn(tD + oD + k * 2048, 16384), id_mn, k != 0);
+      umma_f16(tmem + 32, umma_desc_sw128_mn(sDS + k * 2048, 16384), umma_desc_sw128_mn(tQ + oQ + k * 2048, 16384), id_mn, k != 0);
+    }
+    for (int kk = 0; kk < nkeys / 16; ++kk) {                   // contraction over the keys
+      const uint32_t atom = kk >> 2, ks = kk & 3;
+      umma_f16(tmem + 64, umma_desc_sw128(sDS + atom * 16384 + ks * 32), umma_desc_sw128_mn(tK + oK + kk * 2048, 16384), id_kmn, kk != 0);
+    }
+    umma_commit(&bars[1]);
+  }
+  mbar_wait(&bars[1], 0);
+  tc_fence_after();
+
+  {
+    float dv[32], dk[32], dq[32];
+    tmem_ld_x32(tmem + trow + 0, dv);
+    tmem_ld_x32(tmem + trow + 32, dk);
+    tmem_ld_x32(tmem + trow + 64, dq);
+    tmem_ld_wait();
+    __half* orow2 = a.dqkv + grow * C3 + hd * 3 * dh;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c * 8 >= dh) break;
+      const float* p;
+      p = dq + c * 8;
+      *reinterpret_cast<uint4*>(orow2 + c * 8) = make_uint4(pack_h2(p[0], p[1]), pack_h2(p[2], p[3]), pack_h2(p[4], p[5]), pack_h2(p[6], p[7]));
+      p = dk + c * 8;
+      *reinterpret_cast<uint4*>(orow2 + dh + c * 8) = make_uint4(pack_h2(p[0], p[1]), pack_h2(p[2], p[3]), pack_h2(p[4], p[5]), pack_h2(p[6], p[7]));
+      p = dv + c * 8;
+      *reinterpret_cast<uint4*>(orow2 + 2 * dh + c * 8) = make_uint4(pack_h2(p[0], p[1]), pack_h2(p[2], p[3]), pack_h2(p[4], p[5]), pack_h2(p[6], p[7]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+// ----------------------------------------------------------------------------------------
 // Conv-LSTM gate backward (rnn.py:57-67): with activated gates f, i, o, g, c_t = f c_{t-1} + i g, h_t = o tanh(c_t):
 //   dc = dc_t + dh_t * o * (1 - tanh(c_t)^2);  dc_{t-1} = dc * f;
 //   dpre = [dc * c_{t-1} * f(1-f) | dc * g * i(1-i) | dh_t * tanh(c_t) * o(1-o) | dc * i * (1 - g^2)]
