@@ -677,7 +677,9 @@ __global__ void __launch_bounds__(128) attn_core_bwd_tc_kernel(const __grid_cons
   const uint32_t trow = static_cast<uint32_t>(warp * 32) << 16;
   const int key_lo = (t / rpw) * rpw;
   const bool row_valid = (t - key_lo) < P && static_cast<int>(grow / rpw) < a.n_groups;
-  if (row_valid) {
+  // NOTE tcgen05.ld is warp-collective (.sync.aligned): every lane executes every load, only the arithmetic / the stores
+  // are predicated (a tile's padding rows share warps with real rows).
+  {
     float mx = -INFINITY;
     for (int c0 = 0; c0 < P; c0 += 16) {
       float v[16];
@@ -702,21 +704,23 @@ __global__ void __launch_bounds__(128) attn_core_bwd_tc_kernel(const __grid_cons
       tmem_ld_x16(t_s + trow + key_lo + c0, v);
       tmem_ld_x16(t_da + trow + key_lo + c0, g);
       tmem_ld_wait();
+      if (row_valid) {
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        float p = 0.f, ds = 0.f;
-        if (c0 + e < P) {
-          p = ex2_approx((v[e] - mx) * a.scale_log2e) * inv;
-          ds = p * (g[e] - delta) * a.scale;
+        for (int e = 0; e < 16; ++e) {
+          float p = 0.f, ds = 0.f;
+          if (c0 + e < P) {
+            p = ex2_approx((v[e] - mx) * a.scale_log2e) * inv;
+            ds = p * (g[e] - delta) * a.scale;
+          }
+          v[e] = p; g[e] = ds;
         }
-        v[e] = p; g[e] = ds;
+        const int key = key_lo + c0;
+        const uint32_t off = static_cast<uint32_t>(key >> 6) * 16384u, ch = (key & 63) >> 3;
+        st_smem_16B(sP + off + sw128_offset(t, ch), pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+        st_smem_16B(sP + off + sw128_offset(t, ch + 1), pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+        st_smem_16B(sDS + off + sw128_offset(t, ch), pack_h2(g[0], g[1]), pack_h2(g[2], g[3]), pack_h2(g[4], g[5]), pack_h2(g[6], g[7]));
+        st_smem_16B(sDS + off + sw128_offset(t, ch + 1), pack_h2(g[8], g[9]), pack_h2(g[10], g[11]), pack_h2(g[12], g[13]), pack_h2(g[14], g[15]));
       }
-      const int key = key_lo + c0;
-      const uint32_t off = static_cast<uint32_t>(key >> 6) * 16384u, ch = (key & 63) >> 3;
-      st_smem_16B(sP + off + sw128_offset(t, ch), pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-      st_smem_16B(sP + off + sw128_offset(t, ch + 1), pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
-      st_smem_16B(sDS + off + sw128_offset(t, ch), pack_h2(g[0], g[1]), pack_h2(g[2], g[3]), pack_h2(g[4], g[5]), pack_h2(g[6], g[7]));
-      st_smem_16B(sDS + off + sw128_offset(t, ch + 1), pack_h2(g[8], g[9]), pack_h2(g[10], g[11]), pack_h2(g[12], g[13]), pack_h2(g[14], g[15]));
     }
   }
   fence_proxy_async_smem();
