@@ -592,7 +592,7 @@ __global__ void __launch_bounds__(256) attn_core_bwd_kernel(const __grid_constan
 //   dV = A^T dO, dK = dS^T Q             (contraction over QUERY rows: A / dS and dO / Q are consumed in place as MN-major
 //                                         operands — the row index is the K dimension — so nothing is transposed)
 //   dQ = dS K                            (dS K-major, K as MN-major B)
-// TMEM: S [0,128), dA [128,256); afterwards dV [0,32), dK [32,64), dQ [64,96).  Block-diagonal structure (two 64-row
+// TMEM: S [0,128), dA [128,256); afterwards dV / dK / dQ accumulator blocks at [0,64), [64,128), [128,192).  Block-diagonal structure (two 64-row
 // groups per tile) and padding rows / keys are handled by zeros in the A / dS tiles.
 // pair_tiles = 1: Q|K share one SW128 tile (chunks 0-3 / 4-7 of a row) and V|dO another; 0: four separate tiles.
 // ----------------------------------------------------------------------------------------
@@ -728,16 +728,23 @@ __global__ void __launch_bounds__(128) attn_core_bwd_tc_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
 
+  // MN-major B operands: with paired tiles the B operand is the whole 128-byte row (N = 64 = one full MN-major atom, the
+  // layout gemm_tn_kernel uses): the wanted 32 head-dim columns are the half of the accumulator block that belongs to the
+  // tensor we need, the other half (the row's other tensor) is ignored.  Separate tiles use N = 32 at offset 0.
+  const int nB = a.pair_tiles ? 64 : 32;
+  const uint32_t c_dv = 0 + (a.pair_tiles ? 32 : 0);        // dO is the second half of [V | dO]
+  const uint32_t c_dk = 64 + 0;                             // Q is the first half of [Q | K]
+  const uint32_t c_dq = 128 + (a.pair_tiles ? 32 : 0);      // K is the second half of [Q | K]
   if (t == 0) {
-    const uint32_t id_mn = umma_idesc_f16(128, 32, 0) | (1u << 15) | (1u << 16);     // A, B both MN-major
-    const uint32_t id_kmn = umma_idesc_f16(128, 32, 0) | (1u << 16);                 // A K-major, B MN-major
+    const uint32_t id_mn = umma_idesc_f16(128, nB, 0) | (1u << 15) | (1u << 16);     // A, B both MN-major
+    const uint32_t id_kmn = umma_idesc_f16(128, nB, 0) | (1u << 16);                 // A K-major, B MN-major
     for (int k = 0; k < 8; ++k) {                               // contraction over the 128 query rows, 16 per step
-      umma_f16(tmem + 0, umma_desc_sw128_mn(sP + k * 2048, 16384), umma_desc_sw128_mn(tD + oD + k * 2048, 16384), id_mn, k != 0);
-      umma_f16(tmem + 32, umma_desc_sw128_mn(sDS + k * 2048, 16384), umma_desc_sw128_mn(tQ + oQ + k * 2048, 16384), id_mn, k != 0);
+      umma_f16(tmem + 0, umma_desc_sw128_mn(sP + k * 2048, 16384), umma_desc_sw128_mn(tD + k * 2048, 16384), id_mn, k != 0);
+      umma_f16(tmem + 64, umma_desc_sw128_mn(sDS + k * 2048, 16384), umma_desc_sw128_mn(tQ + k * 2048, 16384), id_mn, k != 0);
     }
     for (int kk = 0; kk < nkeys / 16; ++kk) {                   // contraction over the keys
       const uint32_t atom = kk >> 2, ks = kk & 3;
-      umma_f16(tmem + 64, umma_desc_sw128(sDS + atom * 16384 + ks * 32), umma_desc_sw128_mn(tK + oK + kk * 2048, 16384), id_kmn, kk != 0);
+      umma_f16(tmem + 128, umma_desc_sw128(sDS + atom * 16384 + ks * 32), umma_desc_sw128_mn(tK + kk * 2048, 16384), id_kmn, kk != 0);
     }
     umma_commit(&bars[1]);
   }
@@ -746,9 +753,9 @@ __global__ void __launch_bounds__(128) attn_core_bwd_tc_kernel(const __grid_cons
 
   {
     float dv[32], dk[32], dq[32];
-    tmem_ld_x32(tmem + trow + 0, dv);
-    tmem_ld_x32(tmem + trow + 32, dk);
-    tmem_ld_x32(tmem + trow + 64, dq);
+    tmem_ld_x32(tmem + trow + c_dv, dv);
+    tmem_ld_x32(tmem + trow + c_dk, dk);
+    tmem_ld_x32(tmem + trow + c_dq, dq);
     tmem_ld_wait();
     __half* orow2 = a.dqkv + grow * C3 + hd * 3 * dh;
 #pragma unroll
