@@ -780,10 +780,10 @@ int rvt_attn_core_bwd(const void* qkv, const void* o, const void* dout, void* dq
   a.C = dim; a.dh = dim_head; a.nh = dim / dim_head; a.P = P; a.rows_per_win = rpg;
   a.n_groups = batch * (height / ph) * (width / pw);
   a.scale = 1.0f / sqrtf(static_cast<float>(dim_head));
-  // RVT_ATTN_BWD: 0 (default) the verified fp32 SIMT kernel; 1 tcgen05 kernel with paired operand tiles, 2 with separate tiles
-  // (written at the end of round 1; opt-in until it has passed tests/test_gpu_train_ops.py::test_attn_core_bwd on hardware)
+  // RVT_ATTN_BWD: 1 (default) tcgen05 kernel, paired operand tiles; 2 tcgen05 with separate tiles (N = 32 half-atom B operands,
+  // never validated on hardware); 0 the fp32 SIMT kernel
   static int tc_mode = -1;
-  if (tc_mode < 0) { const char* e = getenv("RVT_ATTN_BWD"); tc_mode = e ? atoi(e) : 0; }
+  if (tc_mode < 0) { const char* e = getenv("RVT_ATTN_BWD"); tc_mode = e ? atoi(e) : 1; }
   if (tc_mode != 0 && dim_head % 8 == 0) {
     const int64_t rows = rvt_attention_scratch_rows(batch, height, width, ph, pw);
     AttnBwdTcArgs t{};
