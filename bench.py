@@ -34,6 +34,30 @@ LOSS_SCALE = 65536.0      # static stand-in for the harness' GradScaler (precisi
 GFLOP_PER_FRAME = 20.62                                 # BASELINE.md §3 (algorithmic, MAC = 2 FLOP)
 
 
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """stdout must carry exactly ONE JSON line, but NCCL prints its version banner to fd 1 (at NCCL_DEBUG=VERSION, the
+    image default, and at WARN too) and other libraries may chat as well: keep a private copy of the real stdout for the
+    result line and point fd 1 at stderr for everything else."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+
+
+def emit(obj):
+    data = (json.dumps(obj) + '\n').encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def rvt_b_spec():
     from oracle import backbone_oracle as bo
     return bo.BackboneSpec(embed_dim=64, dim_head=32, partition_size=(6, 10))
@@ -133,14 +157,14 @@ def run_reference(args, rank, world):
     v = sum(vals) / len(vals)
     sample = (f'{n_ts} timesteps x batch {B_PER_GPU} of the 21-timestep sequence per step (states carried), fp32; '
               f'{cores} torch threads (best of a sweep up to os.cpu_count()={os.cpu_count()})')
-    print(json.dumps({
+    emit({
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'frames/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * B_PER_GPU * SEQ_LEN / v,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': 'RVT-Base 1Mpx 360x640 (padded 384x640) T=10 seq_len=21 bs=8 inference, CPU'},
         'cpu_baseline': {'value': v, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': v, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-    }))
+    })
 
 
 def make_uint8_sequence(seed, length, batch):
@@ -191,12 +215,12 @@ def run_reference_gpu(args, rank, world, local_rank):
         e1.record()
         torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1)
-        print(json.dumps({
+        emit({
             'impl': 'reference-gpu', 'metric': TRAIN_METRIC, 'value': B * SEQ_LEN * args.steps / (ms * 1e-3), 'unit': 'frames/s',
             'n_gpus': 1, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
             'higher_is_better': True, 'dtype': 'f16 autocast', 'data': 'synthetic',
             'config': {'workload': f'RVT-Base 1Mpx bs={B} TBPTT seq_len=21 training step, PyTorch eager + autograd on the GPU '
-                                   '(oracle port of the reference op sequence), fp16 autocast'}}))
+                                   '(oracle port of the reference op sequence), fp16 autocast'}})
         return
     seq = make_uint8_sequence(1234, SEQ_LEN, B_PER_GPU).to(dev)
 
@@ -219,12 +243,12 @@ def run_reference_gpu(args, rank, world, local_rank):
         torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1)
     v = B_PER_GPU * SEQ_LEN * args.steps / (ms * 1e-3)
-    print(json.dumps({
+    emit({
         'impl': 'reference-gpu', 'metric': METRIC, 'value': v, 'unit': 'frames/s', 'n_gpus': 1, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f16 autocast', 'data': 'synthetic',
         'config': {'workload': 'RVT-Base 1Mpx 360x640 (padded 384x640) seq_len=21 bs=8 inference, PyTorch eager on the GPU '
-                               '(oracle port of the reference op sequence), fp16 autocast, inputs resident'}}))
+                               '(oracle port of the reference op sequence), fp16 autocast, inputs resident'}})
 
 
 
@@ -348,7 +372,7 @@ def run_train(args, rank, world, local_rank):
     frames = B * SEQ_LEN * args.steps * world
     if rank == 0:
         n_par = sum(p.numel() for p in params)
-        print(json.dumps({
+        emit({
             'metric': TRAIN_METRIC, 'value': frames / (ms * 1e-3), 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic',
@@ -361,7 +385,7 @@ def run_train(args, rank, world, local_rank):
             'schedule': ('eager launches' if args.train_eager else 'fwd+bwd replayed as one CUDA graph; all-reduce + Adam eager') +
                         ('; stage-per-stream wavefront (4 streams)' if args.train_wavefront else ''),
             'clocks': clocks, 'phases_ms': acc_ms, 'cpu_issue_ms': cpu_ms if args.train_eager else None, 'final_loss': float(loss.detach()) / LOSS_SCALE, 'grads_finite': grad_ok,
-        }), flush=True)
+        })
     if world > 1:
         dist.destroy_process_group()
 
@@ -386,6 +410,7 @@ def main():
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    protect_stdout()
 
     if args.impl == 'reference':
         run_reference(args, rank, world)
@@ -577,7 +602,7 @@ def main():
             line['cpu_baseline'] = {'value': v, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
                                     'sample': '2 timesteps x batch 8 (after 1 warm-up timestep), fp32 torch CPU ops; '
                                               f'{cores} threads = best of a sweep up to os.cpu_count()={os.cpu_count()}'}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
