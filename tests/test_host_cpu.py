@@ -125,8 +125,20 @@ def test_no_cpu_fallback():
     m = rvt_b200.RNNDetector(make_cfg(spec)).eval()
     with torch.no_grad(), pytest.raises(RuntimeError, match='no CPU fallback'):
         m(torch.zeros(1, 20, 64, 96))
+    m.train()
+    with pytest.raises(RuntimeError, match='no CPU fallback'):       # grad mode = the training path: same rule
+        m(torch.zeros(1, 20, 64, 96))
     sh = rvt_b200.StackedHistogram(10, 8, 8, 10)
     z = torch.zeros(0, dtype=torch.int64)
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         sh.construct(z, z, z, z)
     assert sh.get_shape() == (20, 8, 8) and sh.dtype == torch.uint8
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under rvt_b200/ may import or execute it (task rule 3)."""
+    pkg = os.path.join(ROOT, 'rvt_b200')
+    for fn in os.listdir(pkg):
+        if fn.endswith('.py'):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), fn
