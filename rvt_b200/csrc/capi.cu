@@ -147,6 +147,13 @@ const char* rvt_error_string(int code) {
   return cudaGetErrorString(static_cast<cudaError_t>(code));
 }
 
+// RVT_GELU_F16X2=1: packed-half GELU (gemm_fused.cuh gelu_f16x2) in the inference MLP kernels; default 0 = fp32 exact-erf
+static int rvt_gelu_f16x2() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("RVT_GELU_F16X2"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
 static int rvt_wide_bn() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("RVT_WIDE_BN"); v = e ? atoi(e) : 128; }
@@ -449,6 +456,7 @@ static int mlp_block_impl(const float* x, float* x_out, int force_unfused, void*
     ma.w1p = static_cast<const __half*>(w1_packed); ma.b1 = b1;
     ma.w2p = static_cast<const __half*>(w2_packed); ma.b2 = b2; ma.gamma = gamma2;
     if (!b1 || !b2) return kErrUnsupported;
+    ma.gelu_f16x2 = rvt_gelu_f16x2();
     int stages = hidden / kMlpHC < 4 ? hidden / kMlpHC : 4;
     while (stages > 2 && mlp_smem_bytes(dim, stages) > 110 * 1024) --stages;
     ma.stages = stages;
@@ -464,6 +472,20 @@ static int mlp_block_impl(const float* x, float* x_out, int force_unfused, void*
       attr_set = true;
     }
     if (n_mtiles <= 0) return 0;
+    if (ma.gelu_f16x2) {
+      static bool h2_attr = false;
+      if (!h2_attr) {
+        cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fused_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        cudaFuncSetAttribute(mlp_fused_kernel<1, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(mlp_fused_kernel<2, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        h2_attr = true;
+      }
+      if (dim <= 64) mlp_fused_kernel<1, true><<<n_mtiles, kMlpThreads, smem, st>>>(ma);
+      else mlp_fused_kernel<2, true><<<n_mtiles, kMlpThreads, smem, st>>>(ma);
+      return static_cast<int>(cudaGetLastError());
+    }
     if (dim <= 64) mlp_fused_kernel<1><<<n_mtiles, kMlpThreads, smem, st>>>(ma);
     else mlp_fused_kernel<2><<<n_mtiles, kMlpThreads, smem, st>>>(ma);
     return static_cast<int>(cudaGetLastError());
@@ -473,7 +495,8 @@ static int mlp_block_impl(const float* x, float* x_out, int force_unfused, void*
     GemmArgs a{};
     a.K = dim; a.BN = bn1;
     a.Wp = static_cast<const __half*>(w1_packed); a.bias = b1; a.map = m;
-    a.o16 = static_cast<__half*>(scratch_hidden); a.ldo = hidden; a.act = 1;
+    a.o16 = static_cast<__half*>(scratch_hidden); a.ldo = hidden;
+    a.act = (rvt_gelu_f16x2() && !force_unfused) ? 3 : 1;      // the training forward keeps the exact GELU its backward differentiates
     a.o16_pre = static_cast<__half*>(pre_out);
     int rc;
     if (force_unfused || (dim >= kWideDim && dim % 128 == 0)) {

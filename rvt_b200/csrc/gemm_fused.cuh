@@ -131,6 +131,24 @@ __device__ __forceinline__ float gelu_erf(float v) {
   const float r = v * q;
   return v >= 0.f ? v - r : r;
 }
+// Packed-half GELU for results that are rounded to fp16 anyway (opt-in, RVT_GELU_F16X2=1; profiles/gelu_f16x2_study.py):
+//   gelu(v) = 0.5 v (1 + erf(v / sqrt2)),  erf(v / sqrt2) ~= tanh(v (c1 + c3 v^2))  with (c1, c3) least-squares fitted to erf
+// itself (NOT the textbook tanh-GELU constants): |gelu error| <= 3e-4 before rounding; with every step in fp16 and
+// tanh.approx.f16x2's 2^-10.99 error the result has rel-L2 3.1e-4 against exact GELU, vs 1.9e-4 for exact-GELU-then-round.
+// 7 instructions per TWO elements instead of ~17 per element.  Monotone argument polynomial: no clamp needed; v^2 overflowing
+// to inf gives tanh(+-inf) = +-1, i.e. gelu = v or 0.
+__device__ __forceinline__ uint32_t gelu_f16x2(uint32_t packed_v) {
+  const __half2 v = *reinterpret_cast<const __half2*>(&packed_v);
+  const __half2 c1 = __float2half2_rn(0.79978222f), c3 = __float2half2_rn(0.03487167f);
+  const __half2 u = __hmul2(v, v);
+  const __half2 p = __hmul2(__hfma2(c3, u, c1), v);
+  uint32_t t;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(*reinterpret_cast<const uint32_t*>(&p)));
+  const __half2 hv = __hmul2(v, __float2half2_rn(0.5f));
+  const __half2 o = __hfma2(hv, *reinterpret_cast<const __half2*>(&t), hv);
+  return *reinterpret_cast<const uint32_t*>(&o);
+}
+
 // d/dv gelu(v) = Phi(v) + v * phi(v), same A&S erf polynomial as gelu_erf
 __device__ __forceinline__ float gelu_erf_grad(float v) {
   const float u = fabsf(v) * 0.70710678118654752f;
@@ -578,6 +596,13 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_fused_kernel(const __gri
               make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
           *reinterpret_cast<uint4*>(pp + 8) =
               make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+        }
+        if (a.act == 3) {            // packed-half GELU (opt-in): convert first, then 2 elements per instruction
+          *reinterpret_cast<uint4*>(dst + c0) = make_uint4(gelu_f16x2(pack_h2(v[0], v[1])), gelu_f16x2(pack_h2(v[2], v[3])),
+                                                           gelu_f16x2(pack_h2(v[4], v[5])), gelu_f16x2(pack_h2(v[6], v[7])));
+          *reinterpret_cast<uint4*>(dst + c0 + 8) = make_uint4(gelu_f16x2(pack_h2(v[8], v[9])), gelu_f16x2(pack_h2(v[10], v[11])),
+                                                               gelu_f16x2(pack_h2(v[12], v[13])), gelu_f16x2(pack_h2(v[14], v[15])));
+          continue;
         }
         if (a.act == 1) {
 #pragma unroll

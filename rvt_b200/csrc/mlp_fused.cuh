@@ -27,6 +27,7 @@ struct MlpArgs {
   const float* b2;
   const float* gamma;       // LayerScale or null
   int stages;               // weight ring depth
+  int gelu_f16x2;           // 1: packed-half GELU (gemm_fused.cuh gelu_f16x2, opt-in) instead of the fp32 exact-erf evaluation
 };
 
 constexpr int kMlpThreads = 320;      // 8 worker warps + MMA warp + loader warp
@@ -40,7 +41,9 @@ __host__ __device__ inline size_t mlp_smem_bytes(int C, int stages) {
   return 1024 + static_cast<size_t>(mlp_kc1(C)) * kATileBytes + stages * mlp_stage_bytes(C) + 2 * kATileBytes + 256;
 }
 
-template <int KC1>   // K atoms of the C-wide operand: 1 (C <= 64) or 2 (C <= 128); sizes the register-resident x rows
+// KC1: K atoms of the C-wide operand, 1 (C <= 64) or 2 (C <= 128) — sizes the register-resident x rows.  GELU_H2: the opt-in
+// packed-half GELU as a separate instantiation, so the default kernel's code is exactly what was measured.
+template <int KC1, bool GELU_H2 = false>
 __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fused_kernel(const __grid_constant__ MlpArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -167,21 +170,37 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fused_kernel(const __grid_
       tmem_ld_x16(t_hid + lane_off + b * kMlpHC + hsel * 32, v);
       tmem_ld_x16(t_hid + lane_off + b * kMlpHC + hsel * 32 + 16, v + 16);
       tmem_ld_wait();
-      {
+      const uint32_t dst = sH + b * kATileBytes;
+      if (GELU_H2) {
+        // opt-in: bias in fp32, then the packed-half GELU on two activations per instruction
+        uint32_t hp[16];
         float bv[16];
         load16(a.b1 + j * kMlpHC + hsel * 32, bv);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = gelu_erf(v[e] + bv[e]);
+        for (int e = 0; e < 8; ++e) hp[e] = gelu_f16x2(pack_h2(v[2 * e] + bv[2 * e], v[2 * e + 1] + bv[2 * e + 1]));
         load16(a.b1 + j * kMlpHC + hsel * 32 + 16, bv);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) v[16 + e] = gelu_erf(v[16 + e] + bv[e]);
-      }
-      mbar_wait(&sh_empty[b], ((j >> 1) & 1) ^ 1);
-      const uint32_t dst = sH + b * kATileBytes;
+        for (int e = 0; e < 8; ++e) hp[8 + e] = gelu_f16x2(pack_h2(v[16 + 2 * e] + bv[2 * e], v[16 + 2 * e + 1] + bv[2 * e + 1]));
+        mbar_wait(&sh_empty[b], ((j >> 1) & 1) ^ 1);
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        st_smem_16B(dst + sw128_offset(erow, hsel * 4 + c), pack_h2(v[8 * c], v[8 * c + 1]), pack_h2(v[8 * c + 2], v[8 * c + 3]),
-                    pack_h2(v[8 * c + 4], v[8 * c + 5]), pack_h2(v[8 * c + 6], v[8 * c + 7]));
+        for (int c = 0; c < 4; ++c)
+          st_smem_16B(dst + sw128_offset(erow, hsel * 4 + c), hp[4 * c], hp[4 * c + 1], hp[4 * c + 2], hp[4 * c + 3]);
+      } else {
+        {
+          float bv[16];
+          load16(a.b1 + j * kMlpHC + hsel * 32, bv);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = gelu_erf(v[e] + bv[e]);
+          load16(a.b1 + j * kMlpHC + hsel * 32 + 16, bv);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[16 + e] = gelu_erf(v[16 + e] + bv[e]);
+        }
+        mbar_wait(&sh_empty[b], ((j >> 1) & 1) ^ 1);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          st_smem_16B(dst + sw128_offset(erow, hsel * 4 + c), pack_h2(v[8 * c], v[8 * c + 1]), pack_h2(v[8 * c + 2], v[8 * c + 3]),
+                      pack_h2(v[8 * c + 4], v[8 * c + 5]), pack_h2(v[8 * c + 6], v[8 * c + 7]));
+      }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&sh_full[b]);
