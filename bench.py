@@ -59,13 +59,44 @@ def emit(obj):
 
 
 def rvt_b_spec():
+    """oracle-side description of RVT-Base 1Mpx (reference arms only)."""
     from oracle import backbone_oracle as bo
     return bo.BackboneSpec(embed_dim=64, dim_head=32, partition_size=(6, 10))
 
 
-def make_cfg(spec):
-    from tests.test_host_cpu import make_cfg as mk
-    return mk(spec)
+def rvt_b_cfg():
+    """RVT-Base 1Mpx `mdl_config` (config/model/maxvit_yolox/default.yaml + base.yaml, partition size as
+    config/modifier.py:36-41 derives it for 384x640) as a plain dict — what the reference hands to the backbone."""
+    return dict(
+        name='MaxViTRNN', compile=dict(enable=False, args=dict(mode='reduce-overhead')),
+        input_channels=IN_C, enable_masking=False, partition_split_32=2, embed_dim=64, dim_multiplier=[1, 2, 4, 8],
+        num_blocks=[1, 1, 1, 1], T_max_chrono_init=[4, 8, 16, 32], stem=dict(patch_size=4),
+        stage=dict(downsample=dict(type='patch', overlap=True, norm_affine=True),
+                   attention=dict(use_torch_mha=False, partition_size=(6, 10), dim_head=32, attention_bias=True,
+                                  mlp_activation='gelu', mlp_gated=False, mlp_bias=True, mlp_ratio=4, drop_mlp=0, drop_path=0,
+                                  ls_init_value=1e-5, norm_eps=1e-5),
+                   lstm=dict(dws_conv=False, dws_conv_only_hidden=True, dws_conv_kernel_size=3, drop_cell_update=0)))
+
+
+def build_model(seed=0):
+    """rvt_b200.RNNDetector with random-init weights of the RVT-Base architecture: N(0, 1/fan_in) weights, N(0, 0.1) biases,
+    LayerNorm weights and LayerScale gammas ~ U(0.5, 1.5) (so no branch is numerically dead).  Nothing of
+    oracle/ is touched on the product arm."""
+    import rvt_b200
+    model = rvt_b200.RNNDetector(rvt_b_cfg())
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if name.endswith('gamma') or ('norm' in name and name.endswith('weight')):
+                p.copy_(torch.rand(p.shape, generator=g) + 0.5)
+            elif name.endswith('bias'):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+            elif name.endswith('mask_token'):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.5)
+            else:
+                fan_in = p[0].numel()
+                p.copy_(torch.randn(p.shape, generator=g) / fan_in ** 0.5)
+    return model
 
 
 class ClockSampler:
@@ -259,9 +290,8 @@ def run_train(args, rank, world, local_rank):
     21 timesteps (states carried) + synthetic loss on the last step's four feature maps + backward through all 21
     timesteps + gradient all-reduce + unscale + optimizer step."""
     import torch.distributed as dist
-    import rvt_b200
+    import rvt_b200  # noqa: F401
     from rvt_b200 import sharding
-    from oracle import backbone_oracle as bo     # synthetic parameter generator only
 
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
@@ -270,10 +300,7 @@ def run_train(args, rank, world, local_rank):
             os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=dev)
     B = args.train_batch
-    spec = rvt_b_spec()
-    model = rvt_b200.RNNDetector(make_cfg(spec))
-    model.load_state_dict(bo.synth_params(spec, 0), strict=True)
-    model = model.to(dev).train()
+    model = build_model(0).to(dev).train()
     model.pad_to_hw = (PAD_H, PAD_W)
     model.train_wavefront = args.train_wavefront      # stage-per-stream schedule (measured slower in training: off by default)
     lo, hi = sharding.batch_slice(B * world, rank, world)
@@ -425,7 +452,6 @@ def main():
     import torch.distributed as dist
     import rvt_b200
     from rvt_b200 import sharding
-    from oracle import backbone_oracle as bo     # synthetic parameter / input generators only
 
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
@@ -436,10 +462,7 @@ def main():
             os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=dev)
 
-    spec = rvt_b_spec()
-    model = rvt_b200.RNNDetector(make_cfg(spec))
-    model.load_state_dict(bo.synth_params(spec, 0), strict=True)
-    model = model.to(dev).eval()
+    model = build_model(0).to(dev).eval()
     model.pad_to_hw = (PAD_H, PAD_W)
 
     # weak scaling: the global batch is 8*N samples; this rank owns [lo, hi) and its states (no exchange)

@@ -8,15 +8,10 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
-import rvt_b200  # noqa: E402
-from oracle import backbone_oracle as bo  # noqa: E402
 
 L = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 dev = torch.device('cuda:0')
-spec = bench.rvt_b_spec()
-m = rvt_b200.RNNDetector(bench.make_cfg(spec))
-m.load_state_dict(bo.synth_params(spec, 0), strict=True)
-m = m.to(dev).train()
+m = bench.build_model(0).to(dev).train()
 m.pad_to_hw = (bench.PAD_H, bench.PAD_W)
 seq = bench.make_uint8_sequence(1, L, 3).to(dev)
 
