@@ -31,18 +31,36 @@ def _worker(rank, world, port, global_batch, q):
     dist.destroy_process_group()
 
 
+def _run_ranks(target, world, *extra, attempts=2):
+    """Spawn `world` gloo ranks and collect one queue item per rank; a rendezvous hiccup (the free port picked a moment ago
+    got taken, a slow container) gets one retry on a fresh port."""
+    import queue as _queue
+    last = None
+    for _ in range(attempts):
+        ctx = mp.get_context('spawn')
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=target, args=(r, world, port, *extra, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        try:
+            res = [q.get(timeout=120) for _ in range(world)]
+            for p in procs:
+                p.join(60)
+            if all(p.exitcode == 0 for p in procs):
+                return res
+            last = [p.exitcode for p in procs]
+        except _queue.Empty:
+            last = 'timeout'
+        for p in procs:
+            if p.is_alive():
+                p.terminate()
+    raise AssertionError(f'gloo ranks failed: {last}')
+
+
 def test_two_rank_sharding_gloo():
     world, gb = 2, 17
-    ctx = mp.get_context('spawn')
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, gb, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    res = sorted(q.get(timeout=120) for _ in range(world))
-    for p in procs:
-        p.join(60)
-        assert p.exitcode == 0
+    res = sorted(_run_ranks(_worker, world, gb))
     (r0, lo0, hi0, owned0, loc0, none0, mx0), (r1, lo1, hi1, owned1, loc1, none1, mx1) = res
     assert (lo0, hi0, lo1, hi1) == (0, 9, 9, 17)
     assert owned0 == owned1 == [1] * gb
@@ -90,16 +108,7 @@ def _grad_worker(rank, world, port, q):
 
 def test_allreduce_gradients_two_ranks_gloo():
     world = 2
-    ctx = mp.get_context('spawn')
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_grad_worker, args=(r, world, port, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    res = dict(q.get(timeout=120) for _ in range(world))
-    for p in procs:
-        p.join(60)
-        assert p.exitcode == 0
+    res = dict(_run_ranks(_grad_worker, world))
     for rank in range(world):
         n, g = res[rank]['flat']
         assert n == 1                                              # ONE collective
