@@ -229,10 +229,12 @@ class RNNDetector(nn.Module):
         self._packed_key = None
         self._scratch: Dict[str, torch.Tensor] = {}
         self._train = None
-        # Optional: model input resolution (config `in_res_hw`).  When set, an un-padded event
-        # tensor (e.g. 360x640) is accepted and the bottom/right zero padding the harness would
-        # add (utils/padding.py:29-44) is folded into the stem conv's bounds checks.
-        self.pad_to_hw: Optional[Tuple[int, int]] = None
+        # Optional: model input resolution.  When set, an un-padded event tensor (e.g. 360x640) is accepted and the
+        # bottom/right zero padding the harness would add (utils/padding.py:29-44) is folded into the stem conv's bounds
+        # checks.  Read from the backbone config's `in_res_hw` key when a caller put it there (the reference keeps it one
+        # level up, config/modifier.py:28-34), else set by hand.
+        hw = _cfg_get(mdl_config, 'in_res_hw', None)
+        self.pad_to_hw: Optional[Tuple[int, int]] = tuple(int(v) for v in hw) if hw is not None else None
         # test hook: when a dict, forward() stores clones of the residual stream after every
         # operator (keys mirror oracle.backbone_oracle taps) so parity failures localise.
         self.debug_taps: Optional[Dict[str, torch.Tensor]] = None
@@ -476,12 +478,18 @@ class RNNDetector(nn.Module):
         feats_prev = [None] * L              # output of stage s-1 per step (channels-last)
         done = [[None] * L for _ in range(n)]
         capturing = torch.cuda.is_current_stream_capturing()
+        # Every tensor that crosses streams (the fp16 copy of h_t that stage s+1 reads on ITS stream) is held until the
+        # call returns: under CUDA-graph capture record_stream() is not available to defer the allocator's reuse of the
+        # block, and a block recycled by stage s at step t+1 while stage s+1 (a full step behind) still reads it would be
+        # a silent race in the replayed graph.
+        keep_alive = []
         for t in range(L):
-            x_t = self._prep_input(xs[t])
             for s in range(n):
                 with torch.cuda.stream(streams[s]):
-                    if s == 0 and input_ready is not None:
-                        streams[0].wait_event(input_ready[t])
+                    if s == 0:
+                        if input_ready is not None:
+                            streams[0].wait_event(input_ready[t])
+                        x_t = self._prep_input(xs[t])      # any dtype / layout conversion runs on stage 0's stream
                     if wavefront and s > 0:
                         streams[s].wait_event(done[s - 1][t])
                     cur, nchw = (x_t, True) if s == 0 else (feats_prev[t], False)
@@ -498,12 +506,14 @@ class RNNDetector(nn.Module):
                         h_new.record_stream(main)
                         c_new.record_stream(main)
                     feats_prev[t] = h16 if h16 is not None else h_new
+                    keep_alive.append((x_t, feats_prev[t], h_new, c_new))
                     state[s] = (h_new.permute(0, 3, 1, 2), c_new.permute(0, 3, 1, 2))
                     outs[t][s + 1] = state[s][0]
         self.last_step_events = done[n - 1]
         if wavefront:
             for st_ in streams:
                 main.wait_stream(st_)
+        del keep_alive          # all streams have been joined into `main`: same-stream reuse from here on is ordered
         return outs, state
 
 

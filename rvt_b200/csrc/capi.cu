@@ -24,6 +24,22 @@ constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
 
 inline int cdiv(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
 
+// cudaFuncSetAttribute is per device: remember per (call site, device) instead of per process.
+constexpr int kMaxDevices = 64;
+struct DevOnce { bool done[kMaxDevices] = {}; };
+template <typename F>
+cudaError_t ensure_smem_attr(DevOnce& once, F* fn, int bytes) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const bool track = dev >= 0 && dev < kMaxDevices;
+  if (track && once.done[dev]) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return e;
+  cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (track) once.done[dev] = true;
+  return cudaSuccess;
+}
+
 // ---- TMA tensor maps (driver entry point resolved at run time: no link-time libcuda dependency) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -73,14 +89,8 @@ int launch_gemm(GemmArgs a, int n_mtiles, int n_ntiles, cudaStream_t st, const C
   a.stages = stages;
   const size_t smem = gemm_smem_bytes(stages, a.BN, extra_smem);
   if (smem > static_cast<size_t>(kMaxSmem) || a.BN > 512 || a.BN % 16 != 0) return kErrUnsupported;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_fused_kernel<LOADER, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    cudaFuncSetAttribute(gemm_fused_kernel<LOADER, EPI>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                         cudaSharedmemCarveoutMaxShared);
-    attr_set = true;
-  }
+  static DevOnce once;  // per instantiation
+  if (cudaError_t e = ensure_smem_attr(once, gemm_fused_kernel<LOADER, EPI>, kMaxSmem); e != cudaSuccess) return static_cast<int>(e);
   if (n_mtiles <= 0 || n_ntiles <= 0) return 0;
   alignas(64) CUtensorMap tm;
   if (tmap) tm = *tmap; else memset(&tm, 0, sizeof(tm));
@@ -355,15 +365,9 @@ static int partition_attention_impl(const float* x, float* x_out, int force_unfu
     if (!bqkv) return kErrBadArg;   // padded bias vector is mandatory on the fused path (zeros if the layer has none)
     const size_t smem = attn_fused_smem_bytes(dim);
     if (smem > static_cast<size_t>(kMaxSmem)) return kErrUnsupported;
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(attn_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-      if (e != cudaSuccess) return static_cast<int>(e);
-      cudaFuncSetAttribute(attn_fused_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      cudaFuncSetAttribute(attn_fused_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      attr_set = true;
-    }
+    static DevOnce once1, once2;
+    if (cudaError_t e = ensure_smem_attr(once1, attn_fused_kernel<1>, kMaxSmem); e != cudaSuccess) return static_cast<int>(e);
+    if (cudaError_t e = ensure_smem_attr(once2, attn_fused_kernel<2>, kMaxSmem); e != cudaSuccess) return static_cast<int>(e);
     if (dim <= 64) attn_fused_kernel<1><<<n_mtiles, kAfThreads, smem, st>>>(fa);
     else attn_fused_kernel<2><<<n_mtiles, kAfThreads, smem, st>>>(fa);
     return static_cast<int>(cudaGetLastError());
@@ -397,13 +401,8 @@ static int partition_attention_impl(const float* x, float* x_out, int force_unfu
     at.nkeys = rpg == 64 ? 128 : ((P + 15) / 16) * 16;
     at.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(dim_head));
     at.ab_fmt = 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(attention_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
-      if (e != cudaSuccess) return static_cast<int>(e);
-      cudaFuncSetAttribute(attention_core_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      attr_set = true;
-    }
+    static DevOnce once;
+    if (cudaError_t e = ensure_smem_attr(once, attention_core_kernel, kAttnSmemBytes); e != cudaSuccess) return static_cast<int>(e);
     attention_core_kernel<<<dim3(n_mtiles, at.nh), 128, kAttnSmemBytes, st>>>(at);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return static_cast<int>(e);
@@ -462,26 +461,14 @@ static int mlp_block_impl(const float* x, float* x_out, int force_unfused, void*
     ma.stages = stages;
     const size_t smem = mlp_smem_bytes(dim, stages);
     if (smem > static_cast<size_t>(kMaxSmem)) return kErrUnsupported;
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-      if (e != cudaSuccess) return static_cast<int>(e);
-      cudaFuncSetAttribute(mlp_fused_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      cudaFuncSetAttribute(mlp_fused_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      attr_set = true;
-    }
+    static DevOnce once1, once2;
+    if (cudaError_t e = ensure_smem_attr(once1, mlp_fused_kernel<1>, kMaxSmem); e != cudaSuccess) return static_cast<int>(e);
+    if (cudaError_t e = ensure_smem_attr(once2, mlp_fused_kernel<2>, kMaxSmem); e != cudaSuccess) return static_cast<int>(e);
     if (n_mtiles <= 0) return 0;
     if (ma.gelu_f16x2) {
-      static bool h2_attr = false;
-      if (!h2_attr) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fused_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-        if (e != cudaSuccess) return static_cast<int>(e);
-        cudaFuncSetAttribute(mlp_fused_kernel<1, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(mlp_fused_kernel<2, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        h2_attr = true;
-      }
+      static DevOnce h1, h2;
+      if (cudaError_t e = ensure_smem_attr(h1, mlp_fused_kernel<1, true>, kMaxSmem); e != cudaSuccess) return static_cast<int>(e);
+      if (cudaError_t e = ensure_smem_attr(h2, mlp_fused_kernel<2, true>, kMaxSmem); e != cudaSuccess) return static_cast<int>(e);
       if (dim <= 64) mlp_fused_kernel<1, true><<<n_mtiles, kMlpThreads, smem, st>>>(ma);
       else mlp_fused_kernel<2, true><<<n_mtiles, kMlpThreads, smem, st>>>(ma);
       return static_cast<int>(cudaGetLastError());
@@ -712,12 +699,8 @@ int rvt_gemm_tn(const void* a1, int ld1, int n1, const void* a2, int ld2, int n2
   splits = (a.kc_total + a.kc_per_split - 1) / a.kc_per_split;
   a.stages = 4;
   const size_t smem = tn_smem_bytes(a.stages, a.BN);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
-  }
+  static DevOnce once;
+  if (cudaError_t e = ensure_smem_attr(once, gemm_tn_kernel, kMaxSmem); e != cudaSuccess) return static_cast<int>(e);
   alignas(64) CUtensorMap tm1, tm2;
   if (a.kmajor) {
     if (!scratch_t) return kErrBadArg;
@@ -815,24 +798,16 @@ int rvt_attn_core_bwd(const void* qkv, const void* o, const void* dout, void* dq
     t.nkeys = rpg == 64 ? 128 : ((P + 15) / 16) * 16;
     t.pair_tiles = tc_mode == 1 ? 1 : 0;
     t.scale = a.scale; t.scale_log2e = a.scale * 1.4426950408889634f;
-    static bool tc_attr = false;
-    if (!tc_attr) {
-      cudaError_t e = cudaFuncSetAttribute(attn_core_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-      if (e != cudaSuccess) return static_cast<int>(e);
-      tc_attr = true;
-    }
+    static DevOnce tc_once;
+    if (cudaError_t e = ensure_smem_attr(tc_once, attn_core_bwd_tc_kernel, kMaxSmem); e != cudaSuccess) return static_cast<int>(e);
     if (rows <= 0) return 0;
     attn_core_bwd_tc_kernel<<<dim3(static_cast<unsigned>(rows / 128), t.nh), 128, attn_bwd_tc_smem_bytes(t.pair_tiles),
                               static_cast<cudaStream_t>(stream)>>>(t);
     return static_cast<int>(cudaGetLastError());
   }
   const size_t smem = attn_bwd_smem_bytes(P);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_core_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
-  }
+  static DevOnce once;
+  if (cudaError_t e = ensure_smem_attr(once, attn_core_bwd_kernel, kMaxSmem); e != cudaSuccess) return static_cast<int>(e);
   if (a.n_groups <= 0) return 0;
   attn_core_bwd_kernel<<<dim3(a.n_groups, a.nh), 256, smem, static_cast<cudaStream_t>(stream)>>>(a);
   return static_cast<int>(cudaGetLastError());

@@ -1,11 +1,25 @@
 """Thin tensor-level wrappers over the C-ABI operators (include/rvt_b200.h).  One function per
 reference function on the hot path; used by rvt_b200.backbone and by the parity
 tests.  Channels-last fp32 tensors [B, H, W, C]; CUDA only."""
+import functools
 from typing import Optional, Tuple
 
 import torch
 
 from . import _lib
+
+
+def device_guarded(fn):
+    """The C-ABI launches on the CURRENT device (kernel attributes, SM counts and tensor maps are per device): when the
+    first tensor argument lives on another GPU, run the call under that device."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        t = next((a for a in args if isinstance(a, torch.Tensor)), None)
+        if t is not None and t.is_cuda and t.device.index != torch.cuda.current_device():
+            with torch.cuda.device(t.device):
+                return fn(*args, **kw)
+        return fn(*args, **kw)
+    return wrapper
 
 _IN_DTYPES = {torch.float32: 0, torch.uint8: 1, torch.float16: 2}   # channels-last inputs: f32 or f16
 
@@ -14,6 +28,7 @@ def _stream(t: torch.Tensor):
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
+@device_guarded
 def downsample_cf2cl(x: torch.Tensor, x_is_nchw: bool, conv_w_packed: torch.Tensor, cout: int, ksize: int,
                      stride: int, pad: int, ln_w: Optional[torch.Tensor], ln_b: Optional[torch.Tensor],
                      virtual_hw: Optional[Tuple[int, int]] = None, token_mask: Optional[torch.Tensor] = None,
@@ -44,6 +59,7 @@ def downsample_cf2cl(x: torch.Tensor, x_is_nchw: bool, conv_w_packed: torch.Tens
     return out
 
 
+@device_guarded
 def stem_u8_ok(x: torch.Tensor, cin: int, ksize: int, stride: int, pad: int, virtual_hw, cout: int) -> bool:
     """uint8 NCHW input + the default stem geometry -> smem-patch loader (no scratch tensor)."""
     if x.dtype != torch.uint8 or x.data_ptr() % 16:
@@ -68,6 +84,7 @@ def attention_scratch_rows(b, h, w, part) -> int:
     return rows
 
 
+@device_guarded
 def partition_attention_(x: torch.Tensor, blk: dict, scratch_qkv: torch.Tensor, scratch_o: torch.Tensor,
                          scratch_xn: Optional[torch.Tensor] = None) -> None:
     """In place: x += ls1(proj(attn(partition(norm1(x)))))  (maxvit.py:252-268)."""
@@ -85,6 +102,7 @@ def partition_attention_(x: torch.Tensor, blk: dict, scratch_qkv: torch.Tensor, 
         'partition_attention')
 
 
+@device_guarded
 def mlp_block_(x: torch.Tensor, blk: dict, scratch_hidden: torch.Tensor,
                scratch_xn: Optional[torch.Tensor] = None) -> None:
     """In place: x += ls2(mlp(norm2(x)))  (maxvit.py:269)."""
@@ -100,6 +118,7 @@ def mlp_block_(x: torch.Tensor, blk: dict, scratch_hidden: torch.Tensor,
         _lib.ptr(scratch_hidden), _lib.ptr(scratch_xn), _stream(x)), 'mlp_block')
 
 
+@device_guarded
 def dws_conv_lstm(x: torch.Tensor, h_prev: Optional[torch.Tensor], c_prev: Optional[torch.Tensor], pk: dict,
                   dws_ks: int, scratch_xh: Optional[torch.Tensor] = None,
                   h16_out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -129,6 +148,7 @@ def round_up(n: int, m: int) -> int:
     return (n + m - 1) // m * m
 
 
+@device_guarded
 def linear_ex(a: torch.Tensor, m: int, k: int, n: int, w_packed: torch.Tensor, out: torch.Tensor,
               bias: Optional[torch.Tensor] = None, act: int = 0, aux: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = a[:m, :k] @ W^T (+bias, act); a f16 [>=m, k]; out f16 [round_up(m,128), n] or f32 [m, n]."""
@@ -142,6 +162,7 @@ def linear_ex(a: torch.Tensor, m: int, k: int, n: int, w_packed: torch.Tensor, o
     return out
 
 
+@device_guarded
 def gemm_tn(a1: torch.Tensor, n1: int, a2: torch.Tensor, n2: int, m: int, g: torch.Tensor, transpose_out: bool = False,
             mode: Optional[int] = None, colsum1: Optional[torch.Tensor] = None, colsum2: Optional[torch.Tensor] = None) -> None:
     """g[n1, n2] += a1[:m, :n1]^T @ a2[:m, :n2]  (g f32; transpose_out: g is [n2, n1] and receives the transpose).
@@ -160,6 +181,7 @@ def gemm_tn(a1: torch.Tensor, n1: int, a2: torch.Tensor, n2: int, m: int, g: tor
                              _lib.ptr(scratch), _lib.ptr(colsum1), _lib.ptr(colsum2), _stream(a1)), 'gemm_tn')
 
 
+@device_guarded
 def ln_rows_f16(x: torch.Tensor, map_mode: int, part, ln_w, ln_b, do_ln: bool, eps: float, out16: torch.Tensor) -> None:
     b, h, w, c = x.shape
     ph, pw = part if part is not None else (1, 1)
@@ -167,6 +189,7 @@ def ln_rows_f16(x: torch.Tensor, map_mode: int, part, ln_w, ln_b, do_ln: bool, e
                                           int(do_ln), eps, _lib.ptr(out16), _stream(x)), 'ln_rows_f16')
 
 
+@device_guarded
 def ln_bwd(x: Optional[torch.Tensor], dy: torch.Tensor, shape, map_mode: int, part, ln_w, do_ln: bool, eps: float,
            dres: Optional[torch.Tensor], dx16: Optional[torch.Tensor], dw_acc, db_acc) -> None:
     b, h, w, c = shape
@@ -176,6 +199,7 @@ def ln_bwd(x: Optional[torch.Tensor], dy: torch.Tensor, shape, map_mode: int, pa
                                      _lib.ptr(db_acc), _stream(dy)), 'ln_bwd')
 
 
+@device_guarded
 def gather_cast(dres: torch.Tensor, map_mode: int, part, gamma, d0, d1) -> None:
     b, h, w, c = dres.shape
     ph, pw = part if part is not None else (1, 1)
@@ -183,18 +207,21 @@ def gather_cast(dres: torch.Tensor, map_mode: int, part, gamma, d0, d1) -> None:
                                           _lib.ptr(d1), _stream(dres)), 'gather_cast')
 
 
+@device_guarded
 def attn_core_bwd(qkv, o, dout, dqkv, shape, part, dim_head: int) -> None:
     b, h, w, c = shape
     _lib.check(_lib.lib().rvt_attn_core_bwd(_lib.ptr(qkv), _lib.ptr(o), _lib.ptr(dout), _lib.ptr(dqkv), b, h, w, c, part[0],
                                             part[1], dim_head, _stream(qkv)), 'attn_core_bwd')
 
 
+@device_guarded
 def lstm_gates_bwd(gates, c_prev, c_new, dh, dc, n_tokens: int, dim: int, dpre, dc_prev) -> None:
     _lib.check(_lib.lib().rvt_lstm_gates_bwd(_lib.ptr(gates), _lib.ptr(c_prev), _lib.ptr(c_new), _lib.ptr(dh), _lib.ptr(dc),
                                              n_tokens, dim, _lib.ptr(dpre), _lib.ptr(dc_prev), _stream(gates)),
                'lstm_gates_bwd')
 
 
+@device_guarded
 def im2col(x: torch.Tensor, x_is_nchw: bool, ksize: int, stride: int, pad: int, hout: int, wout: int, col: torch.Tensor) -> None:
     if x_is_nchw:
         b, cin, hin, win = x.shape
@@ -204,16 +231,19 @@ def im2col(x: torch.Tensor, x_is_nchw: bool, ksize: int, stride: int, pad: int, 
                                      hout, wout, _lib.ptr(col), _stream(x)), 'im2col')
 
 
+@device_guarded
 def col2im(dcol: torch.Tensor, b, cin, hin, win, ksize, stride, pad, hout, wout, d_in: torch.Tensor) -> None:
     _lib.check(_lib.lib().rvt_col2im(_lib.ptr(dcol), b, cin, hin, win, ksize, stride, pad, hout, wout, _lib.ptr(d_in),
                                      _stream(dcol)), 'col2im')
 
 
+@device_guarded
 def colsum(a: torch.Tensor, m: int, n: int, acc: torch.Tensor) -> None:
     assert a.dtype == torch.float16 and acc.dtype == torch.float32 and acc.numel() >= n
     _lib.check(_lib.lib().rvt_colsum(_lib.ptr(a), m, n, n, _lib.ptr(acc), _stream(a)), 'colsum')
 
 
+@device_guarded
 def nchw_to_nhwc_f16(x: torch.Tensor, channels_padded: int, out: torch.Tensor) -> None:
     b, c, h, w = x.shape
     assert out.dtype == torch.float16 and out.numel() >= b * h * w * channels_padded

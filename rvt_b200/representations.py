@@ -53,6 +53,10 @@ class StackedHistogram:
     def _is_int_tensor(tensor: th.Tensor) -> bool:
         return not th.is_floating_point(tensor) and not th.is_complex(tensor)
 
+    @staticmethod
+    def _aligned16(t: th.Tensor) -> th.Tensor:
+        return t.clone() if (t.numel() and t.data_ptr() % 16) else t
+
     def _buffers(self, device):
         n_out = 2 * self.bins * self.height * self.width
         if self._counts is None or self._counts.device != device:
@@ -69,7 +73,11 @@ class StackedHistogram:
         for t in (x, y, pol, time):
             assert self._is_int_tensor(t)
         assert x.numel() == y.numel() == pol.numel() == time.numel()
-        x, y, pol, time = (t.to(th.int64).contiguous() for t in (x, y, pol, time))
+        # the kernel reads the event arrays as 16-byte vectors: a slice such as x[1:] is only 8-byte aligned -> copy it
+        x, y, pol, time = (self._aligned16(t.to(th.int64).contiguous()) for t in (x, y, pol, time))
+        if device.index is not None and device.index != th.cuda.current_device():
+            with th.cuda.device(device):          # the C-ABI launches on the current device
+                return self.construct(x, y, pol, time, out)
         counts, err = self._buffers(device)
         if out is None:
             out = th.empty(self.get_shape(), dtype=th.uint8, device=device)

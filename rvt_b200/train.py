@@ -416,6 +416,11 @@ class _StageFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dh, dc):
         eng = ctx.engine
+        if ctx.saved is None:
+            raise RuntimeError('rvt_b200: backward through the same stage a second time (retain_graph=True or two losses '
+                               'backpropagated separately) is not supported: the saved fp16 intermediates are released after '
+                               'the first pass and the weight-gradient accumulators already hold it; sum the losses and call '
+                               'backward once, or re-run the forward')
         cp, c_new = ctx.saved_tensors
         dh = None if dh is None else dh.contiguous().float()
         dc = None if dc is None else dc.contiguous().float()
@@ -450,6 +455,12 @@ def forward_train(model, x: torch.Tensor, prev_states, token_mask):
                 token = t[0]
                 break
     if token is None:
+        if eng.dirty:
+            # a previous backward never reached its sink (it raised part-way, or its graph was dropped): its partial sums
+            # must not leak into this sequence's gradients
+            eng._acc_flat.zero_()
+            eng.dirty = False
+            eng.gen += 1
         token = _GradSink.apply(eng, *eng.params)
     x = model._prep_input(x)
     dev = x.device

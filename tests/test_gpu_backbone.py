@@ -182,3 +182,35 @@ def test_graphed_sequence_matches_eager():
                 assert torch.equal(outs[t][k], ref_outs[t][k]), (rep, t, k)
         for (h, c), (h2, c2) in zip(st, ref_st):
             assert torch.equal(h, h2) and torch.equal(c, c2)
+
+
+def test_graphed_wavefront_sequence_at_bench_shape_matches_eager():
+    """BASELINE configs[1] shape (RVT-B 1Mpx, bs 8, 21 timesteps): the captured 4-stream wavefront graph, replayed twice
+    with refilled inputs, is bit-identical to the strictly sequential eager schedule.  Guards the cross-stream lifetime of
+    the per-step fp16 feature copies under capture (a recycled block would be a silent race in the replayed graph)."""
+    import rvt_b200
+    case = dict(BACKBONE_CASES['rvt_b_1mpx'])
+    m, _, _ = build_module(case)
+    m.pad_to_hw = (384, 640)
+    L, B = 21, 8
+    g = torch.Generator(device='cuda').manual_seed(5)
+
+    def fresh():
+        v = torch.randint(1, 11, (L, B, 20, 360, 640), generator=g, device='cuda', dtype=torch.uint8)
+        return v * (torch.randint(0, 10, v.shape, generator=g, device='cuda', dtype=torch.uint8) == 0)
+
+    xs = fresh()
+    graphed = rvt_b200.capture_sequence(m, xs)
+    for rep in range(2):
+        new = fresh()
+        xs.copy_(new)
+        outs, st = graphed()
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            ref_outs, ref_st = m.forward_sequence(new, None, wavefront=False)
+        torch.cuda.synchronize()
+        for t in (0, 1, 7, 19, 20):
+            for k in (1, 2, 3, 4):
+                assert torch.equal(outs[t][k], ref_outs[t][k]), (rep, t, k)
+        for (h, c), (h2, c2) in zip(st, ref_st):
+            assert torch.equal(h, h2) and torch.equal(c, c2)
