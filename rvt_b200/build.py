@@ -34,10 +34,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
     nvcc = os.environ.get('NVCC', 'nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB, SRC]
+    tmp = LIB + '.building'
+    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', tmp, SRC]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + res.stdout + res.stderr)
+    os.replace(tmp, LIB)          # atomic: a concurrent snapshot never sees a half-written library
     if verbose:
         print(res.stderr)
     return LIB

@@ -11,6 +11,7 @@
 #include "gemm_fused.cuh"
 #include "mlp_fused.cuh"
 #include "attn_fused.cuh"
+#include "attn_v2.cuh"
 #include "voxel.cuh"
 #include "train.cuh"
 
@@ -142,6 +143,61 @@ int launch_ln_rows_any_f16(const float* x, const RowMap& map, int64_t n_rows, in
   if (C <= 128) ln_rows_any_kernel<true, 1><<<grid, 256, 0, st>>>(x, map, static_cast<int>(n_rows), C, do_ln, w, b, eps, out, C);
   else ln_rows_any_kernel<true, 4><<<grid, 256, 0, st>>>(x, map, static_cast<int>(n_rows), C, do_ln, w, b, eps, out, C);
   return static_cast<int>(cudaGetLastError());
+}
+
+// 5-D view of a channels-last fp32 tensor [B, H, W, C] whose boxes are the partition groups in (py, px, c) order
+// (reference maxvit.py:273-304):
+//   window: dims (C, pw, nx, ph, B*ny), box (C, pw, 1, ph, 1) at (0, 0, gx, 0, b*ny + gy)
+//   grid  : dims (C, nx, pw, ny, B*ph), box (C, 1, pw, 1, ph) at (0, gx, 0, gy, b*ph)
+bool make_tmap_partition_f32(const float* x, int batch, int H, int W, int C, int ph, int pw, int grid, CUtensorMap* out) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn || (reinterpret_cast<uintptr_t>(x) & 15) || C % 4 != 0 || C > 256 || pw > 256 || ph > 256) return false;
+  const cuuint64_t ny = H / ph, nx = W / pw, cb = static_cast<cuuint64_t>(C) * 4;
+  cuuint64_t gdim[5], gstride[4];
+  cuuint32_t box[5];
+  if (!grid) {
+    gdim[0] = C; gdim[1] = pw; gdim[2] = nx; gdim[3] = ph; gdim[4] = static_cast<cuuint64_t>(batch) * ny;
+    gstride[0] = cb; gstride[1] = pw * cb; gstride[2] = W * cb; gstride[3] = static_cast<cuuint64_t>(ph) * W * cb;
+    box[0] = C; box[1] = pw; box[2] = 1; box[3] = ph; box[4] = 1;
+  } else {
+    gdim[0] = C; gdim[1] = nx; gdim[2] = pw; gdim[3] = ny; gdim[4] = static_cast<cuuint64_t>(batch) * ph;
+    gstride[0] = cb; gstride[1] = nx * cb; gstride[2] = W * cb; gstride[3] = ny * W * cb;
+    box[0] = C; box[1] = 1; box[2] = pw; box[3] = 1; box[4] = ph;
+  }
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(x), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int persistent_sms() {
+  // SMs a persistent kernel may fill (default: all).  RVT_PERSIST_SMS < SM count leaves room for the small grids of the
+  // late stages that run concurrently on other streams (RNNDetector.forward_sequence's wavefront).
+  static int cached = -1;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cached < 0) { const char* e = getenv("RVT_PERSIST_SMS"); cached = e ? atoi(e) : 0; }
+  return (cached > 0 && cached < sms) ? cached : sms;
+}
+
+template <int NH, int KC1>
+int launch_attn_v2(const AttnV2Args& a, const CUtensorMap& tm, cudaStream_t st) {
+  using Cfg = AttnV2Cfg<NH, KC1>;
+  static_assert(Cfg::SMEM <= kMaxSmem, "attn_v2 shared memory");
+  static DevOnce once;
+  if (cudaError_t e = ensure_smem_attr(once, attn_v2_kernel<NH, KC1>, static_cast<int>(Cfg::SMEM)); e != cudaSuccess)
+    return static_cast<int>(e);
+  int grid = persistent_sms() * Cfg::CTAS_PER_SM;
+  if (grid > a.n_tiles) grid = a.n_tiles;
+  if (grid <= 0) return 0;
+  attn_v2_kernel<NH, KC1><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(a, tm);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int attn_v2_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("RVT_ATTN_V2"); v = e ? atoi(e) : 0; }
+  return v;
 }
 
 }  // namespace
@@ -363,6 +419,21 @@ static int partition_attention_impl(const float* x, float* x_out, int force_unfu
     fa.wproj = static_cast<const __half*>(wproj_packed); fa.bproj = bproj; fa.gamma = gamma1;
     fa.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(dim_head));
     if (!bqkv) return kErrBadArg;   // padded bias vector is mandatory on the fused path (zeros if the layer has none)
+    const int nh = dim / dim_head;
+    if (attn_v2_enabled() && P <= 64 && ((nh <= 2 && dim <= 64) || (nh == 4 && dim > 64)) && dim % 16 == 0 && (dim / nh) % 8 == 0) {
+      // persistent, head-parallel kernel with TMA-staged partition tiles (attn_v2.cuh)
+      alignas(64) CUtensorMap tm;
+      if (make_tmap_partition_f32(x_out, batch, height, width, dim, ph, pw, grid, &tm)) {
+        AttnV2Args va{};
+        va.x = x_out; va.map = m; va.C = dim; va.dh = dim_head; va.nh = nh; va.n_tiles = n_mtiles;
+        va.ln_w = n1_w; va.ln_b = n1_b; va.eps = eps; va.do_ln = n1_w != nullptr;
+        va.wqkv = fa.wqkv; va.bqkv = bqkv; va.wproj = fa.wproj; va.bproj = bproj; va.gamma = gamma1;
+        va.scale_log2e = fa.scale_log2e;
+        if (nh == 1) return launch_attn_v2<1, 1>(va, tm, st);
+        if (nh == 2) return launch_attn_v2<2, 1>(va, tm, st);
+        return launch_attn_v2<4, 2>(va, tm, st);
+      }
+    }
     const size_t smem = attn_fused_smem_bytes(dim);
     if (smem > static_cast<size_t>(kMaxSmem)) return kErrUnsupported;
     static DevOnce once1, once2;

@@ -44,15 +44,6 @@ __host__ __device__ inline size_t tn_smem_bytes(int stages, int BN) {
   return 1024 + static_cast<size_t>(stages) * (16384 + static_cast<size_t>(BN) * 128) + (2 * kMaxStages + 1) * 8 + 16;
 }
 
-__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr_bytes, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr_bytes >> 4) & 0x3FFFu);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;   // LBO: between 64-element groups along M/N
-  d |= static_cast<uint64_t>(1024u >> 4) << 32;                    // SBO: between 8-row groups along K
-  d |= static_cast<uint64_t>(1u) << 46;
-  d |= static_cast<uint64_t>(2u) << 61;                            // SWIZZLE_128B
-  return d;
-}
 
 __global__ void __launch_bounds__(kTnThreads) gemm_tn_kernel(const __grid_constant__ TnArgs a,
                                                              const __grid_constant__ CUtensorMap tm1,

@@ -161,6 +161,29 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr_bytes) {
   return d;
 }
 
+// MN-major SW128 operand (the contraction index is the smem ROW index): rows of 64 fp16 = one 128-byte swizzled row per K
+// element, 8 rows per 1024-byte atom (SBO = 1024 B between 8-row groups along K), LBO between 64-element groups along M/N.
+// Advancing K by 16 = +2048 B on the start address.  Instruction descriptor: a_major / b_major bit = 1.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr_bytes, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr_bytes >> 4) & 0x3FFFu);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;   // LBO: between 64-element groups along M/N
+  d |= static_cast<uint64_t>(1024u >> 4) << 32;                    // SBO: between 8-row groups along K
+  d |= static_cast<uint64_t>(1u) << 46;
+  d |= static_cast<uint64_t>(2u) << 61;                            // SWIZZLE_128B
+  return d;
+}
+
+// 5-D tiled TMA load (window / grid partition boxes of a channels-last fp32 tensor, attn_v2.cuh)
+__device__ __forceinline__ void tma_load_5d(uint32_t smem_dst, const void* tmap, int c0, int c1, int c2, int c3, int c4,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
+          smem_dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
+      : "memory");
+}
+
 // Instruction descriptor, kind::f16: D fp32, A/B fp16 (fmt 0) or bf16 (fmt 1), K-major both.
 __host__ __device__ __forceinline__ constexpr uint32_t umma_idesc_f16(uint32_t m, uint32_t n, uint32_t ab_fmt) {
   return (1u << 4)             // c_format = F32
