@@ -12,6 +12,7 @@
 #include "mlp_fused.cuh"
 #include "attn_fused.cuh"
 #include "attn_v2.cuh"
+#include "mlp_v2.cuh"
 #include "voxel.cuh"
 #include "train.cuh"
 
@@ -191,6 +192,36 @@ int launch_attn_v2(const AttnV2Args& a, const CUtensorMap& tm, cudaStream_t st) 
   if (grid > a.n_tiles) grid = a.n_tiles;
   if (grid <= 0) return 0;
   attn_v2_kernel<NH, KC1><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(a, tm);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// fp32 row-major [rows, cols] -> box of all `cols` columns x 128 rows, no swizzle (token tiles of the residual stream)
+bool make_tmap_f32_rows(const float* base, int64_t rows, int cols, CUtensorMap* out) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn || (reinterpret_cast<uintptr_t>(base) & 15) || cols % 4 != 0 || cols > 256) return false;
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * 4};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(cols), 128};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int mlp_v2_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("RVT_MLP_V2"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
+template <bool H2>
+int launch_mlp_v2(const MlpV2Args& a, const CUtensorMap& tm, cudaStream_t st) {
+  static_assert(kMv2Smem <= kMaxSmem, "mlp_v2 shared memory");
+  static DevOnce once;
+  if (cudaError_t e = ensure_smem_attr(once, mlp_v2_kernel<H2>, static_cast<int>(kMv2Smem)); e != cudaSuccess) return static_cast<int>(e);
+  int grid = persistent_sms();
+  if (grid > a.n_tiles) grid = a.n_tiles;
+  if (grid <= 0) return 0;
+  mlp_v2_kernel<H2><<<grid, kMv2Threads, kMv2Smem, st>>>(a, tm);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -527,6 +558,16 @@ static int mlp_block_impl(const float* x, float* x_out, int force_unfused, void*
     ma.w2p = static_cast<const __half*>(w2_packed); ma.b2 = b2; ma.gamma = gamma2;
     if (!b1 || !b2) return kErrUnsupported;
     ma.gelu_f16x2 = rvt_gelu_f16x2();
+    if (mlp_v2_enabled() && dim <= 64 && hidden <= 256 && n_mtiles > 0) {
+      // persistent kernel, resident weights, TMA-staged token tiles (mlp_v2.cuh)
+      alignas(64) CUtensorMap tm;
+      if (make_tmap_f32_rows(x_out, n_tokens, dim, &tm)) {
+        MlpV2Args va{};
+        va.x = x_out; va.n_tokens = static_cast<int>(n_tokens); va.C = dim; va.hidden = hidden; va.n_tiles = n_mtiles;
+        va.ln_w = n2_w; va.ln_b = n2_b; va.eps = eps; va.w1p = ma.w1p; va.b1 = b1; va.w2p = ma.w2p; va.b2 = b2; va.gamma = gamma2;
+        return ma.gelu_f16x2 ? launch_mlp_v2<true>(va, tm, st) : launch_mlp_v2<false>(va, tm, st);
+      }
+    }
     int stages = hidden / kMlpHC < 4 ? hidden / kMlpHC : 4;
     while (stages > 2 && mlp_smem_bytes(dim, stages) > 110 * 1024) --stages;
     ma.stages = stages;
