@@ -23,7 +23,7 @@ _refshim.install()
 from oracle import backbone_oracle as bo  # noqa: E402
 from oracle import voxel_oracle as vo  # noqa: E402
 from tests.golden_configs import BACKBONE_CASES, VOXEL_CASES, spec_of, make_voxel_events  # noqa: E402
-from tests.helpers import GRAD_CASES, GRAD_SUB, case_inputs, train_loss  # noqa: E402
+from tests.helpers import GRAD_CASES, grad_sub, case_inputs, train_loss  # noqa: E402
 
 from models.detection.recurrent_backbone import build_recurrent_backbone  # noqa: E402
 from data.utils.representations import StackedHistogram  # noqa: E402
@@ -129,7 +129,7 @@ def run_backbone_grad_case(name, steps):
     assert worst < 1e-4 and abs(float(loss_o.detach()) - float(loss_r.detach())) <= 1e-5 * abs(float(loss_r.detach())), (name, worst)
     out = {'loss': np.float64(float(loss_r))}
     for k, g in g_ref.items():
-        out['g.' + k] = sub(g, GRAD_SUB)
+        out['g.' + k] = sub(g, grad_sub(name))
         out['n.' + k] = np.float64(g.double().norm().item())
     np.savez_compressed(os.path.join(GOLD, f'backbone_grads_{name}.npz'), **out)
     print(f'backbone grads {name}: oracle-vs-reference worst rel-L2 {worst:.2e}; loss {float(loss_r):.6f}; '
@@ -154,11 +154,17 @@ def run_voxel_case(name, case):
 if __name__ == '__main__':
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
+    only = [a.split('=', 1)[1] for a in sys.argv if a.startswith('--only=')]     # --only=<case>[,<case>...]
+    only = set(only[0].split(',')) if only else None
+    want = lambda n: only is None or n in only
     if '--grads-only' not in sys.argv:
         for n, c in VOXEL_CASES.items():
-            run_voxel_case(n, c)
+            if want(n):
+                run_voxel_case(n, c)
     if '--grads-only' not in sys.argv:
         for n, c in BACKBONE_CASES.items():
-            run_backbone_case(n, c)
+            if want(n):
+                run_backbone_case(n, c)
     for n, steps in GRAD_CASES.items():
-        run_backbone_grad_case(n, steps)
+        if want(n) and '--no-grads' not in sys.argv:
+            run_backbone_grad_case(n, steps)

@@ -28,6 +28,15 @@ BACKBONE_CASES = {
     # RVT-Base 1Mpx 384x640 (P=60), bs 1, 2 steps
     'rvt_b_1mpx': dict(embed_dim=64, dim_head=32, height=384, width=640, partition=(6, 10), batch=1,
                        steps=2, seed=17, sub=13),
+    # BASELINE configs[1] shape: RVT-Base 1Mpx, bs 8, seq_len 21 (state drift over a whole benchmark sequence)
+    'rvt_b_1mpx_bs8_l21': dict(embed_dim=64, dim_head=32, height=384, width=640, partition=(6, 10), batch=8,
+                               steps=21, seed=18, sub=997, save_steps=[0, 10, 20], heavy=True),
+    # BASELINE configs[3] shape: RVT-Small Gen1 256x320: dim_head 24 (padded head) WITH P = 80 (one window per 128-row tile)
+    'rvt_s_gen1': dict(embed_dim=48, dim_head=24, height=256, width=320, partition=(8, 10), batch=2,
+                       steps=3, seed=19, sub=11),
+    # BASELINE configs[2] per-GPU shape: RVT-Base 1Mpx bs 3 (gradient golden, tests.helpers.GRAD_CASES)
+    'rvt_b_1mpx_bs3': dict(embed_dim=64, dim_head=32, height=384, width=640, partition=(6, 10), batch=3,
+                           steps=2, seed=20, sub=211, heavy=True),
 }
 
 

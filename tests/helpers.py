@@ -85,8 +85,14 @@ GRAD_CASES = {
     # name -> (backbone case, unrolled steps)
     'tiny_p6': 3,
     'small_dh24': 2,
+    'rvt_b_1mpx_bs3': 2,      # BASELINE configs[2] per-GPU shape (C up to 512, P = 60, bs 3)
 }
 GRAD_SUB = 29   # stride of the committed gradient subsamples
+
+
+def grad_sub(name: str) -> int:
+    """stride of the committed gradient subsample of a case (bigger models: sparser)"""
+    return 211 if name == 'rvt_b_1mpx_bs3' else GRAD_SUB
 
 
 def case_inputs(case, steps):

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 from oracle import backbone_oracle as bo  # noqa: E402
 from tests.golden_configs import BACKBONE_CASES, spec_of  # noqa: E402
-from tests.helpers import GOLD, GRAD_CASES, GRAD_SUB, case_inputs, train_loss  # noqa: E402
+from tests.helpers import GOLD, GRAD_CASES, grad_sub, case_inputs, train_loss  # noqa: E402
 from tests.test_host_cpu import make_cfg  # noqa: E402
 
 GRAD_TOL = 3e-2
@@ -64,9 +64,9 @@ def test_gradients_match_reference_golden(name, wavefront, dev):
         assert p.grad is not None, k
         assert torch.isfinite(p.grad).all(), k
         ref = torch.from_numpy(gold['g.' + k]).double()
-        got = p.grad.detach().cpu().contiguous().reshape(-1)[::GRAD_SUB].double()
+        got = p.grad.detach().cpu().contiguous().reshape(-1)[::grad_sub(name)].double()
         # subsample error measured against the subsample's own norm (floor: 1/sqrt(stride) of the full norm)
-        den = max(float(ref.norm()), float(gold['n.' + k]) / np.sqrt(GRAD_SUB) * 0.1)
+        den = max(float(ref.norm()), float(gold['n.' + k]) / np.sqrt(grad_sub(name)) * 0.1)
         worst[k] = float((got - ref).norm()) / max(den, 1e-20)
     bad = {k: v for k, v in worst.items() if v > GRAD_TOL}
     print(f'{name}: worst grad rel-L2 vs reference golden: {max(worst.values()):.3e} ({max(worst, key=worst.get)})')

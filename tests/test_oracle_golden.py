@@ -72,7 +72,7 @@ def test_time_bin_fp32_edges():
 def test_backbone_oracle_gradients_match_reference_golden(name):
     """Training-step pin: autograd through the oracle reproduces the REFERENCE's gradients
     (tests/golden/backbone_grads_*.npz, minted by oracle/make_golden.py)."""
-    from tests.helpers import GRAD_CASES, GRAD_SUB, case_inputs, train_loss
+    from tests.helpers import GRAD_CASES, grad_sub, case_inputs, train_loss
     case = BACKBONE_CASES[name]
     spec = spec_of(case)
     gold = np.load(os.path.join(GOLD, f'backbone_grads_{name}.npz'))
@@ -86,6 +86,6 @@ def test_backbone_oracle_gradients_match_reference_golden(name):
     assert abs(float(loss.detach()) - float(gold['loss'])) <= 1e-5 * abs(float(gold['loss']))
     for k, p in params.items():
         ref = torch.from_numpy(gold['g.' + k])
-        got = p.grad.contiguous().reshape(-1)[::GRAD_SUB]
+        got = p.grad.contiguous().reshape(-1)[::grad_sub(name)]
         assert float((got - ref).norm()) <= 1e-4 * float(gold['n.' + k]) + 1e-12, k
         assert abs(float(p.grad.double().norm()) - float(gold['n.' + k])) <= 1e-4 * float(gold['n.' + k]) + 1e-12, k
