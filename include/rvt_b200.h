@@ -37,6 +37,8 @@ int rvt_attention_is_fused(int dim, int dim_head);
 int rvt_mlp_tiles(int dim, int hidden, int* bn_fc1, int* bn_fc2);
 /* N-tile of the downsample conv with cout output channels (cout itself = fused LayerNorm). */
 int rvt_conv_tile_n(int cout);
+/* K slices the wide-stage (Cout >= 256) downsample conv is split into when given a workspace (1 = none). */
+int rvt_conv_split_k(int64_t n_tokens, int cout, int k);
 /* Channels per CTA for the Conv-LSTM gate GEMM (tile = [f|i|o|g] x cw columns). */
 int rvt_lstm_cw(int dim);
 /* Rows one partition group occupies in a 128-row tile (64 or 128; <0 if P > 128). */
@@ -63,7 +65,9 @@ int rvt_stacked_histogram(const int64_t* x, const int64_t* y, const int64_t* pol
  * the input is first re-laid out space-to-depth so every conv tap is a 16-byte vector load, and
  * w_packed must come from packing.pack_stem_weight_s2d().  NULL selects the generic gather path.
  * stem_mode: 0/1 = paths above; 2 = uint8 NCHW 7x7/s4 stem with the input patch staged in shared memory
- * (needs rvt_stem_u8_ok(); w_packed from packing.pack_stem_weight_u8(); no scratch). */
+ * (needs rvt_stem_u8_ok(); w_packed from packing.pack_stem_weight_u8(); no scratch).
+ * Channels-last inputs (stages 2-4) with Cout >= 256: `s2d_scratch` is instead an optional split-K workspace, f32
+ * [rvt_conv_split_k(n_tokens, Cout, K)][n_tokens, Cout]; NULL = one K loop per CTA. */
 int rvt_downsample_cf2cl(const void* in, int in_dtype, int in_nchw, int batch, int cin, int hin, int win,
                          int ksize, int stride, int pad, int hout, int wout, int cout,
                          const void* w_packed, const float* ln_w, const float* ln_b, float eps,

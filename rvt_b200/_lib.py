@@ -17,6 +17,7 @@ SIGNATURES = {
     'rvt_attention_is_fused': (_i, [_i, _i]),
     'rvt_mlp_tiles': (_i, [_i, _i, _vp, _vp]),
     'rvt_conv_tile_n': (_i, [_i]),
+    'rvt_conv_split_k': (_i, [_i64, _i, _i]),
     'rvt_lstm_cw': (_i, [_i]),
     'rvt_rows_per_group': (_i, [_i]),
     'rvt_attention_scratch_rows': (_i64, [_i, _i, _i, _i, _i]),

@@ -393,11 +393,17 @@ class RNNDetector(nn.Module):
                 s2d = self._scratch_buf('s2d', b * cur.shape[2] * vw * st.dim_in, torch.float16, dev)
         if s == 0 and token_mask is not None:
             assert st.mask_token is not None, 'No mask token present in this stage'
+        split_ws = None
+        if s > 0 and c >= 256:
+            n_out = b * (cur.shape[1] // d.factor) * (cur.shape[2] // d.factor)
+            splits = _lib.lib().rvt_conv_split_k(n_out, c, st.dim_in * d.kernel_size ** 2)
+            if splits > 1:
+                split_ws = self._scratch_buf(f'convws{s}', splits * n_out * c, torch.float32, dev)
         xs = ops.downsample_cf2cl(
             cur, cur_nchw, conv_w, c, d.kernel_size, d.factor, d.padding, pk['ds_ln_w'], pk['ds_ln_b'],
             virtual_hw=self.pad_to_hw if s == 0 else None,
             token_mask=token_mask if s == 0 else None, mask_token=pk['mask_token'], s2d_scratch=s2d,
-            stem_mode=stem_mode)
+            stem_mode=stem_mode, split_ws=split_ws)
         _, hh, ww, _ = xs.shape
         n_tok = b * hh * ww
         if taps is not None:

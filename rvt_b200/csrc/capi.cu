@@ -76,16 +76,18 @@ bool make_tmap_f16_rows(const void* base, int64_t rows, int64_t cols, int64_t ld
 
 template <int LOADER, int EPI>
 int launch_gemm(GemmArgs a, int n_mtiles, int n_ntiles, cudaStream_t st, const CUtensorMap* tmap = nullptr,
-                size_t extra_smem = 0) {
+                size_t extra_smem = 0, int n_splits = 1) {
   a.KC = cdiv(a.K, 64);
+  if (n_splits > 1) a.kc_split = cdiv(a.KC, n_splits); else a.kc_split = 0;
   a.tmem_cols = static_cast<int>(tmem_cols_pow2(static_cast<uint32_t>(a.BN)));
   a.ab_fmt = 0;  // fp16 operands
-  int stages = a.KC < 4 ? a.KC : 4;
+  const int kc_cta = a.kc_split > 0 ? a.kc_split : a.KC;      // K chunks one CTA walks
+  int stages = kc_cta < 4 ? kc_cta : 4;
   static int smem_cap_kb = -1, tma_cap_kb = -1;
   if (smem_cap_kb < 0) { const char* e = getenv("RVT_GEMM_SMEM_KB"); smem_cap_kb = e ? atoi(e) : 110; }
   if (tma_cap_kb < 0) { const char* e = getenv("RVT_TMA_SMEM_KB"); tma_cap_kb = e ? atoi(e) : 110; }
   const size_t cap = static_cast<size_t>(LOADER == LD_TMA ? tma_cap_kb : smem_cap_kb) * 1024;
-  if (LOADER == LD_TMA && a.KC > stages) stages = a.KC < kMaxStages ? a.KC : kMaxStages;
+  if (LOADER == LD_TMA && kc_cta > stages) stages = kc_cta < kMaxStages ? kc_cta : kMaxStages;
   while (stages > 2 && gemm_smem_bytes(stages, a.BN, extra_smem) > cap) --stages;
   while (stages > 1 && gemm_smem_bytes(stages, a.BN, extra_smem) > static_cast<size_t>(kMaxSmem)) --stages;
   a.stages = stages;
@@ -96,7 +98,7 @@ int launch_gemm(GemmArgs a, int n_mtiles, int n_ntiles, cudaStream_t st, const C
   if (n_mtiles <= 0 || n_ntiles <= 0) return 0;
   alignas(64) CUtensorMap tm;
   if (tmap) tm = *tmap; else memset(&tm, 0, sizeof(tm));
-  gemm_fused_kernel<LOADER, EPI><<<dim3(n_mtiles, n_ntiles), kGemmThreads, smem, st>>>(a, tm);
+  gemm_fused_kernel<LOADER, EPI><<<dim3(n_mtiles, n_ntiles, a.kc_split > 0 ? cdiv(a.KC, a.kc_split) : 1), kGemmThreads, smem, st>>>(a, tm);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -115,11 +117,13 @@ constexpr int kWideDim = 256;
 
 template <bool OUT_F16>
 int launch_ln_rows(const float* x, const RowMap& map, int64_t n_rows, int C, int do_ln, const float* w, const float* b,
-                   float eps, void* out, const uint8_t* mask, const float* mask_token, cudaStream_t st) {
+                   float eps, void* out, const uint8_t* mask, const float* mask_token, cudaStream_t st, int n_splits = 1,
+                   long long split_stride = 0) {
   if (C % 128 != 0 || C > 512) return kErrUnsupported;
   if (n_rows <= 0) return 0;
   ln_rows_kernel<OUT_F16><<<static_cast<unsigned>((n_rows + 7) / 8), 256, 0, st>>>(x, map, static_cast<int>(n_rows), C, do_ln, w,
-                                                                                  b, eps, out, mask, mask_token);
+                                                                                  b, eps, out, mask, mask_token, n_splits,
+                                                                                  split_stride);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -290,6 +294,22 @@ int rvt_stem_u8_ok(int cin, int ksize, int stride, int pad, int win, int hout, i
 
 int rvt_conv_tile_n(int cout) { return (cout >= kWideDim && cout % 128 == 0) ? 128 : cout; }
 
+int rvt_conv_split_k(int64_t n_tokens, int cout, int k) {
+  // K slices of the N-split downsample conv of the wide stages (1 = no split).  Aim at >= 2 CTAs per SM, keep >= 4 chunks of 64
+  // per slice.  RVT_CONV_SPLITK=0 disables, =n forces n.
+  static int env = -2;
+  if (env == -2) { const char* e = getenv("RVT_CONV_SPLITK"); env = e ? atoi(e) : -1; }
+  if (env == 0 || cout < kWideDim || cout % 128 != 0) return 1;
+  const int kc = cdiv(k, 64);
+  const int ctas = cdiv(n_tokens, 128) * (cout / rvt_conv_tile_n(cout));
+  int splits = env > 0 ? env : cdiv(296, ctas);
+  if (splits > kc / 4) splits = kc / 4;
+  if (splits > 8) splits = 8;
+  if (splits < 1) splits = 1;
+  const int per = cdiv(kc, splits);
+  return cdiv(kc, per);                       // no empty slice
+}
+
 int rvt_lstm_cw(int dim) {
   static int cw_max = -1;
   if (cw_max < 0) { const char* e = getenv("RVT_LSTM_CW"); cw_max = e ? atoi(e) : 64; }
@@ -364,7 +384,7 @@ static int downsample_impl(const void* in, int in_dtype, int in_nchw, int batch,
     a.raw_out = raw_out;
     return launch_gemm<LD_STEM, EP_LN>(a, bm.n_groups, 1, st, nullptr, stem_patch_bytes(cin) + 128);
   }
-  if (s2d_scratch) {
+  if (s2d_scratch && in_nchw) {
     // space-to-depth stem: [B,Cin,H,W] -> f16 [B,H,Wg,f*Cin], then a (ks x 2)-tap vectorised conv
     const bool overlap = ksize == 2 * stride - 1 && pad == stride - 1;
     const bool patch = ksize == stride && pad == 0;
@@ -396,10 +416,16 @@ static int downsample_impl(const void* in, int in_dtype, int in_nchw, int batch,
     a.BN = rvt_conv_tile_n(cout);
     a.ldo = cout;
     float* raw = raw_out ? raw_out : out;
+    // split-K (inference, caller gave a workspace through `s2d_scratch`): few row tiles x K up to 2304 would leave most SMs idle
+    // behind one long serial K loop per CTA; every K slice writes its own fp32 partial tile, the LayerNorm pass sums them.
+    int splits = 1;
+    if (!raw_out && !in_nchw && s2d_scratch) splits = rvt_conv_split_k(n_tok, cout, a.K);
+    if (splits > 1) { raw = static_cast<float*>(s2d_scratch); a.split_stride = static_cast<long long>(n_tok) * cout; }
     a.yout = raw;
-    int rc = launch_gemm<LD_CONV, EP_RAW>(a, cdiv(n_tok, 128), cout / a.BN, st);
+    int rc = launch_gemm<LD_CONV, EP_RAW>(a, cdiv(n_tok, 128), cout / a.BN, st, nullptr, 0, splits);
     if (rc) return rc;
-    return launch_ln_rows<false>(raw, a.map, n_tok, cout, 1, ln_w, ln_b, eps, out, token_mask, mask_token, st);
+    return launch_ln_rows<false>(raw, a.map, n_tok, cout, 1, ln_w, ln_b, eps, out, token_mask, mask_token, st, splits,
+                                 a.split_stride);
   }
   a.raw_out = raw_out;
   return launch_gemm<LD_CONV, EP_LN>(a, cdiv(n_tok, 128), 1, st);

@@ -74,6 +74,8 @@ __device__ __forceinline__ int row_to_token(const RowMap& m, int row) {
 struct GemmArgs {
   // tiling
   int K, KC, BN, stages, tmem_cols, ab_fmt;
+  int kc_split;        // split-K: K chunks per blockIdx.z slice (0 = no split); EP_RAW stores slice z at yout + z * split_stride
+  long long split_stride;
   const __half* Wp;    // packed weights [n_ntiles][KC][BN x 64 SW128 image]
   const float* bias;   // [n_ntiles*BN] in tile column order, or null
   RowMap map;
@@ -237,6 +239,9 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_fused_kernel(const __gri
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int mt = blockIdx.x, nt = blockIdx.y;
   const int stages = a.stages, KC = a.KC, BN = a.BN;
+  // split-K (deterministic: every z slice writes its own partial tile, ln_rows_kernel sums the slices in a fixed order)
+  const int kc0 = a.kc_split > 0 ? static_cast<int>(blockIdx.z) * a.kc_split : 0;
+  const int kcn = a.kc_split > 0 ? min(a.kc_split, KC - kc0) : KC;
   const uint32_t b_bytes = static_cast<uint32_t>(BN) * 128u;
 
   const uint32_t sA_addr = base_addr;
@@ -492,9 +497,10 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_fused_kernel(const __gri
       named_bar_sync(1, kWorkers);
       // ---- K loop: k = (ky*Cin + ci)*8 + kx8, the 8 bytes [4*ox-4, 4*ox+4) of input row 4*oy-3+ky (kx8 = 0 has zero weight)
       const int npairs = 7 * Cin;
-      for (int kc = 0; kc < KC; ++kc) {
-        const int s = kc % stages;
-        const uint32_t ph = (kc / stages) & 1;
+      for (int i = 0; i < kcn; ++i) {
+        const int kc = kc0 + i;
+        const int s = i % stages;
+        const uint32_t ph = (i / stages) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         if (tid == 0) {
           mbar_expect_tx(&full[s], b_bytes);
@@ -533,12 +539,13 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_fused_kernel(const __gri
       }
     } else {
     uint32_t raw_a[4][8], raw_b[4][8];
-    fetch(0, raw_a);
-    for (int kc = 0; kc < KC; ++kc) {
-      const int s = kc % stages;
-      const uint32_t ph = (kc / stages) & 1;
-      const bool even = (kc & 1) == 0;
-      if (kc + 1 < KC) { if (even) fetch(kc + 1, raw_b); else fetch(kc + 1, raw_a); }
+    fetch(kc0, raw_a);
+    for (int i = 0; i < kcn; ++i) {
+      const int kc = kc0 + i;
+      const int s = i % stages;
+      const uint32_t ph = (i / stages) & 1;
+      const bool even = (i & 1) == 0;
+      if (i + 1 < kcn) { if (even) fetch(kc + 1, raw_b); else fetch(kc + 1, raw_a); }
       mbar_wait(&empty[s], ph ^ 1);
       if (tid == 0) {
         mbar_expect_tx(&full[s], b_bytes);
@@ -660,7 +667,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_fused_kernel(const __gri
         tmem_ld_x16(trow + c0, v);
         tmem_ld_wait();
         if (etok >= 0) {
-          float* op = a.yout + static_cast<size_t>(etok) * a.ldo + nt * BN + c0;
+          float* op = a.yout + static_cast<size_t>(blockIdx.z) * a.split_stride + static_cast<size_t>(etok) * a.ldo + nt * BN + c0;
 #pragma unroll
           for (int qd = 0; qd < 4; ++qd)
             *reinterpret_cast<float4*>(op + qd * 4) = make_float4(v[qd * 4], v[qd * 4 + 1], v[qd * 4 + 2], v[qd * 4 + 3]);
@@ -786,9 +793,10 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_fused_kernel(const __gri
     // =========================== TMA producer (LD_TMA only) ===========================
     if (LOADER == LD_TMA && lane == 0) {
       tma_prefetch_desc(&tmap_a);
-      for (int kc = 0; kc < KC; ++kc) {
-        const int s = kc % stages;
-        mbar_wait(&empty[s], ((kc / stages) & 1) ^ 1);
+      for (int i = 0; i < kcn; ++i) {
+        const int kc = kc0 + i;
+        const int s = i % stages;
+        mbar_wait(&empty[s], ((i / stages) & 1) ^ 1);
         mbar_arrive_expect_tx(&full[s], kATileBytes + b_bytes);
         tma_load_2d(sA_addr + s * kATileBytes, &tmap_a, kc * 64, mt * 128, &full[s]);
         bulk_g2s(sB + static_cast<size_t>(s) * b_bytes,
@@ -803,9 +811,10 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_fused_kernel(const __gri
       const int n1 = BN - n0;
       const uint32_t idesc0 = umma_idesc_f16(128, n0, a.ab_fmt);
       const uint32_t idesc1 = n1 > 0 ? umma_idesc_f16(128, n1, a.ab_fmt) : 0u;
-      for (int kc = 0; kc < KC; ++kc) {
-        const int s = kc % stages;
-        const uint32_t ph = (kc / stages) & 1;
+      for (int i = 0; i < kcn; ++i) {
+        const int kc = kc0 + i;
+        const int s = i % stages;
+        const uint32_t ph = (i / stages) & 1;
         mbar_wait(&full[s], ph);
         tc_fence_after();
         const uint32_t at = sA_addr + s * kATileBytes;
@@ -813,7 +822,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_fused_kernel(const __gri
         const int krem = a.K - kc * 64;
         const int ksteps = krem >= 64 ? 4 : (krem + 15) >> 4;
         for (int k = 0; k < ksteps; ++k) {
-          const uint32_t acc = (kc | k) != 0 ? 1u : 0u;
+          const uint32_t acc = (i | k) != 0 ? 1u : 0u;
           const uint64_t ad = umma_desc_sw128(at + k * 32);
           umma_f16(tmem_base, ad, umma_desc_sw128(bt + k * 32), idesc0, acc);
           if (n1 > 0) umma_f16(tmem_base + 256, ad, umma_desc_sw128(bt + 256 * 128 + k * 32), idesc1, acc);
@@ -842,7 +851,8 @@ template <bool OUT_F16>
 __global__ void __launch_bounds__(256) ln_rows_kernel(const float* x, RowMap map, int n_rows, int C, int do_ln, const float* __restrict__ ln_w,
                                                       const float* __restrict__ ln_b, float eps, void* out,
                                                       const uint8_t* __restrict__ token_mask,
-                                                      const float* __restrict__ mask_token) {
+                                                      const float* __restrict__ mask_token, int n_splits = 1,
+                                                      long long split_stride = 0) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n_rows) return;
@@ -852,7 +862,13 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* x, RowMap map
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (g < ng && tok >= 0) t = *reinterpret_cast<const float4*>(x + static_cast<size_t>(tok) * C + g * 128 + lane * 4);
+    if (g < ng && tok >= 0) {
+      t = *reinterpret_cast<const float4*>(x + static_cast<size_t>(tok) * C + g * 128 + lane * 4);
+      for (int z = 1; z < n_splits; ++z) {          // split-K partial sums of the producing conv, fixed order
+        const float4 u = *reinterpret_cast<const float4*>(x + z * split_stride + static_cast<size_t>(tok) * C + g * 128 + lane * 4);
+        t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+      }
+    }
     v[4 * g] = t.x; v[4 * g + 1] = t.y; v[4 * g + 2] = t.z; v[4 * g + 3] = t.w;
   }
   if (do_ln) {

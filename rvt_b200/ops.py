@@ -33,7 +33,8 @@ def downsample_cf2cl(x: torch.Tensor, x_is_nchw: bool, conv_w_packed: torch.Tens
                      stride: int, pad: int, ln_w: Optional[torch.Tensor], ln_b: Optional[torch.Tensor],
                      virtual_hw: Optional[Tuple[int, int]] = None, token_mask: Optional[torch.Tensor] = None,
                      mask_token: Optional[torch.Tensor] = None, eps: float = 1e-5,
-                     s2d_scratch: Optional[torch.Tensor] = None, stem_mode: int = 0) -> torch.Tensor:
+                     s2d_scratch: Optional[torch.Tensor] = None, stem_mode: int = 0,
+                     split_ws: Optional[torch.Tensor] = None) -> torch.Tensor:
     """ConvDownsampling_Cf2Cl.forward (maxvit.py:174-178) [+ mask token, maxvit_rnn.py:174-176].
     x: [B,Cin,H,W] (f32/u8/f16) if x_is_nchw else [B,H,W,Cin] f32.  -> f32 [B,Hout,Wout,cout]."""
     assert x.is_cuda and x.is_contiguous() and x.dtype in _IN_DTYPES
@@ -52,6 +53,13 @@ def downsample_cf2cl(x: torch.Tensor, x_is_nchw: bool, conv_w_packed: torch.Tens
         token_mask = token_mask.to(device=x.device, dtype=torch.uint8).contiguous()
         assert tuple(token_mask.shape) == (b, hout, wout) and mask_token is not None
     L = _lib.lib()
+    if s2d_scratch is None and not x_is_nchw and cout >= 256:
+        # wide stages: split-K workspace (one fp32 partial tile per K slice, summed by the LayerNorm pass)
+        splits = L.rvt_conv_split_k(b * hout * wout, cout, cin * ksize * ksize)
+        if splits > 1:
+            s2d_scratch = split_ws if split_ws is not None else torch.empty(splits * b * hout * wout * cout, dtype=torch.float32,
+                                                                           device=x.device)
+            assert s2d_scratch.dtype == torch.float32 and s2d_scratch.numel() >= splits * b * hout * wout * cout
     _lib.check(L.rvt_downsample_cf2cl(
         _lib.ptr(x), _IN_DTYPES[x.dtype], int(x_is_nchw), b, cin, hin, win, ksize, stride, pad, hout, wout, cout,
         _lib.ptr(conv_w_packed), _lib.ptr(ln_w), _lib.ptr(ln_b), eps, _lib.ptr(token_mask), _lib.ptr(mask_token),
