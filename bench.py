@@ -178,21 +178,33 @@ def best_cpu_threads():
 
 
 def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (oracle port) on the host cores.  A step is one full 21-timestep, bs-8
+    sequence (the product arm's own config) whenever K + W of them fit in ~4 minutes of CPU time; otherwise a bounded sample
+    (fewer timesteps per step) and the line says so."""
     if rank != 0:
         return
     cores = best_cpu_threads()
-    n_ts = 2                     # bounded sample: 2 timesteps x 8 samples per "step"
-    vals = []
-    for _ in range(max(1, min(args.steps, 3))):
-        vals.append(cpu_reference_fps(n_ts, B_PER_GPU, cores))
+    t0 = time.perf_counter()
+    fps1 = cpu_reference_fps(2, B_PER_GPU, cores)                       # probe (also the warm-up)
+    est_seq_s = B_PER_GPU * SEQ_LEN / fps1
+    budget_s = 240.0 - (time.perf_counter() - t0)
+    steps = max(1, args.steps)
+    n_ts = SEQ_LEN
+    if steps * est_seq_s > budget_s:
+        n_ts = max(2, min(SEQ_LEN, int(SEQ_LEN * budget_s / (steps * est_seq_s))))
+    vals = [cpu_reference_fps(n_ts, B_PER_GPU, cores) for _ in range(steps)]
     v = sum(vals) / len(vals)
-    sample = (f'{n_ts} timesteps x batch {B_PER_GPU} of the 21-timestep sequence per step (states carried), fp32; '
-              f'{cores} torch threads (best of a sweep up to os.cpu_count()={os.cpu_count()})')
+    full = n_ts == SEQ_LEN
+    sample = ((f'full sequences: {SEQ_LEN} timesteps x batch {B_PER_GPU} per step' if full else
+               f'{n_ts} of the {SEQ_LEN} timesteps x batch {B_PER_GPU} per step (bounded to ~4 min of CPU time)') +
+              f', states carried, fp32; {cores} torch threads (best of a sweep up to os.cpu_count()={os.cpu_count()})')
     emit({
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'frames/s', 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * B_PER_GPU * SEQ_LEN / v,
+        'steps': steps, 'warmup': 1, 'ms_per_step': 1e3 * B_PER_GPU * n_ts / v,     # what was actually timed per step
+        'timed_timesteps_per_step': n_ts, 'same_config': full,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'RVT-Base 1Mpx 360x640 (padded 384x640) T=10 seq_len=21 bs=8 inference, CPU'},
+        'config': {'workload': 'RVT-Base 1Mpx 8x20x360x640 uint8 (model res 384x640) seq_len=21 bs=8/GPU '
+                               'inference, states carried', 'frames_per_step': B_PER_GPU * SEQ_LEN, 'device': 'CPU'},
         'cpu_baseline': {'value': v, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': v, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     })
@@ -284,7 +296,7 @@ def run_reference_gpu(args, rank, world, local_rank):
 
 
 
-def run_train(args, rank, world, local_rank):
+def train_leg(args, rank, world, local_rank, steps, warmup):
     """BASELINE configs[2]: RVT-Base 1Mpx training step, TBPTT over seq_len 21, 3 samples per GPU, batch-sharded,
     ONE NCCL all-reduce over the flat gradient buffer, fused Adam on the backbone parameters.  A step = forward of
     21 timesteps (states carried) + synthetic loss on the last step's four feature maps + backward through all 21
@@ -293,12 +305,7 @@ def run_train(args, rank, world, local_rank):
     import rvt_b200  # noqa: F401
     from rvt_b200 import sharding
 
-    torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
-    if world > 1:
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-            os.environ['NCCL_DEBUG'] = 'WARN'
-        dist.init_process_group('nccl', device_id=dev)
     B = args.train_batch
     model = build_model(0).to(dev).train()
     model.pad_to_hw = (PAD_H, PAD_W)
@@ -374,7 +381,7 @@ def run_train(args, rank, world, local_rank):
 
     if not args.train_eager:
         capture()            # (no eager step before this: AccumulateGrad nodes must first be created on the capture stream)
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         loss, n_coll = step()
     assert torch.isfinite(loss.detach()).item(), 'non-finite training loss'
     sampler = ClockSampler(local_rank)
@@ -383,7 +390,7 @@ def run_train(args, rank, world, local_rank):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         loss, n_coll = step()
     e1.record()
     torch.cuda.synchronize(dev)
@@ -396,25 +403,185 @@ def run_train(args, rank, world, local_rank):
         for k in ev:
             acc_ms[k] += ev[k][0].elapsed_time(ev[k][1]) / 2
     grad_ok = all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in params)
-    frames = B * SEQ_LEN * args.steps * world
+    ar_ms = sharding.max_over_ranks(acc_ms['ar'], dev)
+    frames = B * SEQ_LEN * steps * world
+    n_par = sum(p.numel() for p in params)
+    return {
+        'metric': TRAIN_METRIC, 'value': frames / (ms * 1e-3), 'unit': 'frames/s', 'n_gpus': world, 'steps': steps,
+        'warmup': max(warmup, 3), 'ms_per_step': ms / steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic',
+        'config': {'workload': f'RVT-Base 1Mpx {B}x20x360x640 uint8 per GPU (model res 384x640) TBPTT seq_len=21 training step: '
+                               'fwd + bwd through 21 timesteps + grad all-reduce + fused Adam (backbone only)',
+                   'global_batch': B * world, 'frames_per_step': B * SEQ_LEN,
+                   'l2_policy': f'{n_seq} rotating input sequences ({n_seq * seqs[0].numel() >> 20} MB) > L2',
+                   'parallelism': f'batch-sharded x{world}; {n_coll} NCCL all-reduce of {n_par * 4 >> 20} MB fp32 gradients per step',
+                   'loss_scale': LOSS_SCALE},
+        'schedule': ('eager launches' if args.train_eager else 'fwd+bwd replayed as one CUDA graph; all-reduce + Adam eager') +
+                    ('; stage-per-stream wavefront (4 streams)' if args.train_wavefront else ''),
+        'clocks': clocks, 'phases_ms': acc_ms, 'allreduce_ms_max_over_ranks': ar_ms, 'n_collectives': n_coll,
+        'allreduce_bytes': n_par * 4, 'cpu_issue_ms': cpu_ms if args.train_eager else None,
+        'final_loss': float(loss.detach()) / LOSS_SCALE, 'grads_finite': grad_ok,
+    }
+
+
+def run_train(args, rank, world, local_rank):
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    line = train_leg(args, rank, world, local_rank, args.steps, args.warmup)
     if rank == 0:
-        n_par = sum(p.numel() for p in params)
-        emit({
-            'metric': TRAIN_METRIC, 'value': frames / (ms * 1e-3), 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
-            'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic',
-            'config': {'workload': f'RVT-Base 1Mpx {B}x20x360x640 uint8 per GPU (model res 384x640) TBPTT seq_len=21 training step: '
-                                   'fwd + bwd through 21 timesteps + grad all-reduce + fused Adam (backbone only)',
-                       'global_batch': B * world, 'frames_per_step': B * SEQ_LEN,
-                       'l2_policy': f'{n_seq} rotating input sequences ({n_seq * seqs[0].numel() >> 20} MB) > L2',
-                       'parallelism': f'batch-sharded x{world}; {n_coll} NCCL all-reduce of {n_par * 4 >> 20} MB fp32 gradients per step',
-                       'loss_scale': LOSS_SCALE},
-            'schedule': ('eager launches' if args.train_eager else 'fwd+bwd replayed as one CUDA graph; all-reduce + Adam eager') +
-                        ('; stage-per-stream wavefront (4 streams)' if args.train_wavefront else ''),
-            'clocks': clocks, 'phases_ms': acc_ms, 'cpu_issue_ms': cpu_ms if args.train_eager else None, 'final_loss': float(loss.detach()) / LOSS_SCALE, 'grads_finite': grad_ok,
-        })
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def count_kernel_launches(fn, dev):
+    """MEASURED number of GPU kernels one call of `fn` launches (CUPTI activity records through torch.profiler; kernels
+    launched by CUDA-graph replay and through the ctypes C-ABI are included).  Returns (count, {name: count})."""
+    try:
+        from torch.profiler import profile, ProfilerActivity
+        torch.cuda.synchronize(dev)
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize(dev)
+        names = {}
+        for e in prof.events():
+            if getattr(e, 'device_type', None) is not None and 'cuda' in str(e.device_type).lower():
+                n = e.name
+                if n.startswith('Memcpy') or n.startswith('Memset'):
+                    continue
+                names[n] = names.get(n, 0) + 1
+        return sum(names.values()), names
+    except Exception as ex:            # profiler unavailable: fall back to the analytic count, and say so
+        return None, {'error': repr(ex)}
+
+
+def voxel_leg(dev, peak_gbs):
+    """BASELINE configs[4]: 50 M synthetic (x, y, t, p) events -> StackedHistogram 2 x 10 x 720 x 1280 (uint8)."""
+    import rvt_b200
+    n, H, W, bins = 50_000_000, 720, 1280, 10
+    g = torch.Generator(device=dev).manual_seed(0)
+    x = torch.randint(0, W, (n,), generator=g, device=dev, dtype=torch.int64)
+    y = torch.randint(0, H, (n,), generator=g, device=dev, dtype=torch.int64)
+    p = torch.randint(0, 2, (n,), generator=g, device=dev, dtype=torch.int64)
+    t = torch.sort(torch.randint(0, 50000, (n,), generator=g, device=dev, dtype=torch.int64)).values
+    sh = rvt_b200.StackedHistogram(bins, H, W, 10, fastmode=True, validate=False)
+    out = torch.empty(sh.get_shape(), dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        sh.construct(x, y, p, t, out=out)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        sh.construct(x, y, p, t, out=out)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    total = int(out.sum(dtype=torch.int64).item())
+    algo_bytes = 32 * n + out.numel()                       # SURVEY 8(d): 32 B/event (int64 x, y, p, t) + 1 B per output bin
+    del x, y, p, t
+    return {'events': n, 'ms': ms, 'events_per_s': n / (ms * 1e-3), 'algorithmic_bytes': algo_bytes,
+            'gbs': algo_bytes / ms / 1e6, 'frac_of_hbm_peak': algo_bytes / ms / 1e6 / peak_gbs, 'out_sum': total,
+            'workload': '50 M uniform events, sorted timestamps, 2x10x720x1280 uint8, count_cutoff 10, fastmode; 1.6 GB of int64 inputs > L2'}
+
+
+def eager_gpu_leg(dev, steps=2):
+    """The reference's op-by-op PyTorch path on the SAME GPU (oracle port = the same ATen / cuDNN / cuBLAS calls) under fp16
+    autocast + inference_mode, inputs resident: the denominator of north_star's '>= 10x PyTorch-eager'."""
+    from oracle import backbone_oracle as bo
+    spec = rvt_b_spec()
+    params = {k: v.to(dev) for k, v in bo.synth_params(spec, 0).items()}
+    seq = make_uint8_sequence(1234, SEQ_LEN, B_PER_GPU).to(dev)
+
+    def step():
+        st = None
+        for t in range(SEQ_LEN):
+            x = torch.nn.functional.pad(seq[t].float(), (0, PAD_W - IN_W, 0, PAD_H - IN_H))   # modules/detection.py:133-134
+            _, st = bo.backbone_forward(x, st, params, spec)
+
+    with torch.inference_mode(), torch.autocast('cuda', dtype=torch.float16):
+        step()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    return {'frames_per_s': B_PER_GPU * SEQ_LEN / (ms * 1e-3), 'ms_per_step': ms, 'steps': steps,
+            'what': 'oracle port of the reference op sequence, PyTorch eager, fp16 autocast, inference_mode, inputs resident'}
+
+
+def dropin_leg(model, seq_dev, dev, steps=3):
+    """Exactly what the UNMODIFIED harness does (modules/detection.py:131-148): a Python loop over the timesteps, every
+    timestep uint8 -> float32 + zero pad to the model resolution, then forward(x, prev_states) -- eager launches, one
+    stream, no graph, no wavefront."""
+    model.pad_to_hw = None
+
+    def step():
+        st = None
+        for t in range(SEQ_LEN):
+            x = torch.nn.functional.pad(seq_dev[t].to(torch.float32), (0, PAD_W - IN_W, 0, PAD_H - IN_H))
+            _, st = model(x, st)
+
+    with torch.inference_mode():
+        step()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+    model.pad_to_hw = (PAD_H, PAD_W)
+    ms = e0.elapsed_time(e1) / steps
+    return {'frames_per_s': B_PER_GPU * SEQ_LEN / (ms * 1e-3), 'ms_per_step': ms, 'steps': steps,
+            'what': 'per-timestep RNNDetector.forward() from a Python loop, fp32 padded input, eager launches (reference harness call pattern)'}
+
+
+def rvt_s_gen1_leg(dev, steps=5):
+    """BASELINE configs[3]: RVT-Small Gen1 (240x304 -> 256x320, dim_head 24, P = 80) eval, batch 64."""
+    import rvt_b200
+    cfg = rvt_b_cfg()
+    cfg['embed_dim'] = 48
+    cfg['partition_split_32'] = 1
+    cfg['stage']['attention']['dim_head'] = 24
+    cfg['stage']['attention']['partition_size'] = (8, 10)
+    model = rvt_b200.RNNDetector(cfg)
+    g = torch.Generator(device='cpu').manual_seed(3)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if name.endswith('gamma') or ('norm' in name and name.endswith('weight')):
+                p.copy_(torch.rand(p.shape, generator=g) + 0.5)
+            elif name.endswith('bias'):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+            else:
+                p.copy_(torch.randn(p.shape, generator=g) / p[0].numel() ** 0.5)
+    model = model.to(dev).eval()
+    model.pad_to_hw = (256, 320)
+    L, B = 5, 64
+    gg = torch.Generator(device=dev).manual_seed(9)
+    seq = torch.randint(1, 11, (L, B, IN_C, 240, 304), generator=gg, device=dev, dtype=torch.uint8)
+    seq = seq * (torch.randint(0, 10, seq.shape, generator=gg, device=dev, dtype=torch.uint8) == 0)
+    with torch.inference_mode():
+        run = rvt_b200.GraphedCallable(lambda: model.forward_sequence(seq, None, wavefront=True)[1], warmup=2)
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            run()
+        e1.record()
+        torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    return {'frames_per_s': L * B / (ms * 1e-3), 'ms_per_step': ms, 'steps': steps,
+            'workload': f'RVT-Small Gen1 {B}x20x240x304 uint8 (model res 256x320), {L} timesteps, states carried, graph replay'}
 
 
 def main():
@@ -424,14 +591,16 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference', 'reference-gpu'])
     ap.add_argument('--mode', default='infer', choices=['infer', 'train'],
-                    help="infer: BASELINE configs[1] (the headline metric); train: configs[2], the batch-sharded training step")
-    ap.add_argument('--train-batch', type=int, default=3, help='samples per GPU in --mode train (BASELINE configs[2]: 3)')
-    ap.add_argument('--train-wavefront', action='store_true', help='--mode train: stage-per-stream schedule (fwd and bwd)')
+                    help="infer: BASELINE configs[1] (the headline metric) + the extra legs; train: configs[2] alone")
+    ap.add_argument('--train-batch', type=int, default=3, help='samples per GPU of the training step (BASELINE configs[2]: 3)')
+    ap.add_argument('--train-wavefront', action='store_true', help='training step: stage-per-stream schedule (fwd and bwd)')
     ap.add_argument('--train-eager', action='store_true',
-                    help='--mode train: launch forward+backward eagerly instead of replaying one CUDA graph of them')
+                    help='training step: launch forward+backward eagerly instead of replaying one CUDA graph of them')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch eagerly instead of replaying CUDA graphs')
     ap.add_argument('--no-wavefront', action='store_true', help='run the four stages strictly one after the other')
+    ap.add_argument('--extras', default='train,voxel,eager_gpu,dropin,rvt_s_gen1_bs64',
+                    help='comma list of the extra legs reported under "extra" (empty string: none)')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', 0))
@@ -453,6 +622,7 @@ def main():
     import rvt_b200
     from rvt_b200 import sharding
 
+    extras_wanted = [e for e in args.extras.split(',') if e]
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
@@ -545,10 +715,13 @@ def main():
         for _ in range(3):
             step_e2e()
         ms_e2e = timed(step_e2e, args.steps)
+        launches_per_step, launch_names = (None, {})
+        if rank == 0:
+            launches_per_step, launch_names = count_kernel_launches(step_resident, dev)
 
     # ---- roofline of the dominant kernel, timed live with CUDA events on its launch stream ----
-    # attn_fused_kernel, stage-1 instance (largest share of the step in profiles/launches_r01.txt): one
-    # launch = the attention half of one PartitionAttentionCl block over 8 x 96 x 160 tokens, C = 64.
+    # fused attention, stage-1 instance (largest single-kernel share of the step): one launch = the attention half of one
+    # PartitionAttentionCl block over 8 x 96 x 160 tokens, C = 64.
     roof = None
     if rank == 0:
         from rvt_b200 import ops
@@ -573,28 +746,56 @@ def main():
             del bufs
         algo_bytes = 2 * n_tok * c * 4                               # x read + x written, fp32
         algo_flops = 8 * n_tok * c * c + 4 * n_tok * P * c           # qkv + proj + QK^T + PV
-        roof = {'kernel': 'attn_fused_kernel (stage 1, C=64, 122880 tokens)', 'us_per_launch': us,
+        kname = next((k for k in launch_names if 'attn' in k), 'attn kernel')
+        roof = {'kernel': f'{kname.split("(")[0]} (stage 1 window block, C=64, 122880 tokens)', 'us_per_launch': us,
                 'algorithmic_bytes': algo_bytes, 'algorithmic_flops': algo_flops}
+
+    # ---- extra legs (all inside this one driver-run line) ----
+    extra = {}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak_gbs = peaks.get('hbm_gbs', 6650.0)
+    if 'train' in extras_wanted:
+        del step_resident, step_e2e
+        torch.cuda.empty_cache()
+        tr = train_leg(args, rank, world, local_rank, steps=min(args.steps, 5), warmup=3)
+        extra['train'] = {k: tr[k] for k in ('value', 'unit', 'ms_per_step', 'steps', 'n_gpus', 'phases_ms',
+                                             'allreduce_ms_max_over_ranks', 'n_collectives', 'allreduce_bytes', 'schedule',
+                                             'grads_finite')}
+        extra['train']['config'] = tr['config']
+        torch.cuda.empty_cache()
+    if rank == 0:
+        def guarded(name, fn):
+            if name not in extras_wanted:
+                return
+            try:
+                extra[name] = fn()
+            except Exception as ex:
+                extra[name] = {'error': repr(ex)}
+            torch.cuda.empty_cache()
+        guarded('dropin', lambda: dropin_leg(model, seq_dev, dev))
+        guarded('voxel', lambda: voxel_leg(dev, peak_gbs))
+        guarded('rvt_s_gen1_bs64', lambda: rvt_s_gen1_leg(dev))
+        guarded('eager_gpu', lambda: eager_gpu_leg(dev))
 
     frames = B_PER_GPU * SEQ_LEN * args.steps * world
     value = frames / (ms * 1e-3)
     e2e = frames / (ms_e2e * 1e-3)
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-        except Exception:
-            pass
         peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
-        peak_gbs = peaks.get('hbm_gbs', 6650.0)
         peak_src = 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback (B200_PROFILING.md)'
         ach_tf = value / world * GFLOP_PER_FRAME / 1e3
         ach_gbs = roof['algorithmic_bytes'] / roof['us_per_launch'] / 1e3
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic_r01.json'))).get('attn_fused_s1_dram_bytes')
+            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic_r02.json'))).get('attn_s1_dram_bytes')
         except Exception:
             pass
+        if 'eager_gpu' in extra and 'frames_per_s' in extra['eager_gpu']:
+            extra['eager_gpu']['ours_over_eager'] = value / world / extra['eager_gpu']['frames_per_s']
         line = {
             'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
@@ -608,7 +809,10 @@ def main():
             'e2e': {'value': e2e, 'unit': 'frames/s',
                     'h2d_bytes_per_step': SEQ_LEN * B_PER_GPU * IN_C * IN_H * IN_W,
                     'd2h_bytes_per_step': SEQ_LEN * feat_host.numel() * 4},
-            'gpu_launches': LAUNCHES_PER_TIMESTEP * SEQ_LEN * args.steps,
+            'gpu_launches': (launches_per_step if launches_per_step is not None else LAUNCHES_PER_TIMESTEP * SEQ_LEN) * args.steps,
+            'gpu_launches_how': ('measured: CUPTI kernel records of one replayed step x steps' if launches_per_step is not None
+                                 else 'analytic (profiler unavailable)'),
+            'kernels_per_step': launch_names,
             'clocks': clocks,
             # C = 64: 94 FLOP/B algorithmic intensity, below the 263 FLOP/B ridge -> HBM is the bounding roof
             'roofline': {'bound': 'hbm', 'achieved': ach_gbs, 'peak': peak_gbs, 'unit': 'GB/s',
@@ -618,13 +822,14 @@ def main():
                          'note': 'algorithmic bytes = x read + written (fp32) = 62.9 MB per launch; see DESIGN.md §6'},
             'whole_step': {'algorithmic_tflops': ach_tf, 'frac_of_sustained_bf16_peak': ach_tf / peak_tf,
                            'gflop_per_frame': GFLOP_PER_FRAME},
+            'extra': extra,
         }
         if not args.no_cpu_baseline:
             cores = best_cpu_threads()
-            v = cpu_reference_fps(2, B_PER_GPU, cores)
+            v = cpu_reference_fps(SEQ_LEN, B_PER_GPU, cores)
             line['cpu_baseline'] = {'value': v, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
-                                    'sample': '2 timesteps x batch 8 (after 1 warm-up timestep), fp32 torch CPU ops; '
-                                              f'{cores} threads = best of a sweep up to os.cpu_count()={os.cpu_count()}'}
+                                    'sample': f'one full sequence: {SEQ_LEN} timesteps x batch {B_PER_GPU} (after 1 warm-up timestep), '
+                                              f'fp32 torch CPU ops; {cores} threads = best of a sweep up to os.cpu_count()={os.cpu_count()}'}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
