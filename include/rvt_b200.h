@@ -196,6 +196,38 @@ int rvt_col2im(const void* dcol, int batch, int cin, int hin, int win, int ksize
 /* acc[n] += sum_m a[m,n]  (a f16, leading dimension ld): bias gradients. */
 int rvt_colsum(const void* a, int64_t m, int n, int ld, float* acc, void* stream);
 
+/* ======================================================================================
+ * SURVEY.md §8(f) "next" rows, built to the same bar: the callers / data formats either side of the path.
+ * ====================================================================================== */
+
+/* ---- f3: harness glue inside an L-step sequence (modules/utils/detection.py) -------------
+ * RNNStates.reset -> recursive_reset (:96-113; modules/detection.py:117,217): state[mask] = 0 in place.
+ * h, c: f32 [batch, per_sample] (c may be NULL); mask: u8 [batch] (is_first_sample). */
+int rvt_state_reset(float* h, float* c, const uint8_t* mask, int batch, int64_t per_sample, void* stream);
+/* BackboneFeatureSelector (:24-46): dst[j, :] = src[idx[j], :], j < n_idx; src f32 [n_src_rows, row_elems] holds the L*B
+ * feature maps of a sequence, idx = t*B + b of the labelled (step, sample) pairs; idx[j] < 0 => zero row. */
+int rvt_gather_rows(const float* src, const int32_t* idx, int n_idx, int64_t n_src_rows, int64_t row_elems, float* dst,
+                    void* stream);
+
+/* ---- f4: preprocessing neighbours of the voxelizer ---------------------------------------
+ * downsample_ev_repr(x, 0.5) = F.interpolate(mode='nearest-exact') (scripts/genx/preprocess_dataset.py:467-477,525-528):
+ * out[c,y,x] = in[c, min(2y+1,H-1), min(2x+1,W-1)], out: [channels, height/2, width/2] bytes (uint8 or int8 alike). */
+int rvt_downsample2_nearest(const uint8_t* in, int channels, int height, int width, uint8_t* out, void* stream);
+/* H5Reader._correct_time (preprocess_dataset.py:163-172): t[i] = max(floor_value, t[0..i]) in place (floor_value = 0 there).
+ * scratch: int64 [rvt_cummax_scratch_elems(n)]. */
+int64_t rvt_cummax_scratch_elems(int64_t n);
+int rvt_cummax_i64(int64_t* t, int64_t n, int64_t floor_value, int64_t* scratch, void* stream);
+/* np.searchsorted(sorted, queries, side) (preprocess_dataset.py:511-516): right = 0 'left', 1 'right'. */
+int rvt_searchsorted_i64(const int64_t* sorted, int64_t n, const int64_t* queries, int64_t n_queries, int right, int64_t* out,
+                         void* stream);
+/* MixedDensityEventStack.construct (data/utils/representations.py:130-218) -> int8 [bins, H, W].  thresholds: f32 [bins-1],
+ * t_idx = #{k: t_norm >= thresholds[k]} (found on the host from the reference's own fp32 expression, so binning is bit-exact);
+ * t_lo / t_hi: the fp32 clamp bounds of t_norm; count_cutoff < 0 = none; counts: i32 [bins*H*W] scratch, zero at rest;
+ * err_flag as rvt_stacked_histogram. */
+int rvt_mixed_density_stack(const int64_t* x, const int64_t* y, const int64_t* pol, const int64_t* t, int64_t n, int bins,
+                            int height, int width, int count_cutoff, float t_lo, float t_hi, const float* thresholds,
+                            int32_t* counts, int8_t* out, int* err_flag, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,11 +22,13 @@ from oracle import _refshim  # noqa: E402
 _refshim.install()
 from oracle import backbone_oracle as bo  # noqa: E402
 from oracle import voxel_oracle as vo  # noqa: E402
-from tests.golden_configs import BACKBONE_CASES, VOXEL_CASES, spec_of, make_voxel_events  # noqa: E402
+from tests.golden_configs import (BACKBONE_CASES, MIXED_DENSITY_CASES, VOXEL_CASES, make_time_glitched, make_voxel_events,  # noqa: E402
+                                  spec_of)
+from oracle import neighbours_oracle as no  # noqa: E402
 from tests.helpers import GRAD_CASES, grad_sub, case_inputs, train_loss  # noqa: E402
 
 from models.detection.recurrent_backbone import build_recurrent_backbone  # noqa: E402
-from data.utils.representations import StackedHistogram  # noqa: E402
+from data.utils.representations import MixedDensityEventStack, StackedHistogram  # noqa: E402
 
 GOLD = os.path.join(ROOT, 'tests', 'golden')
 
@@ -151,12 +153,73 @@ def run_voxel_case(name, case):
     print(f'voxel {name}: bit-exact; n={len(x)} max={out["fast"].max()}')
 
 
+def _reference_function(path, name, extra_globals):
+    """Pull ONE function out of a reference source file that cannot be imported as a module here (its imports need h5py /
+    hdf5plugin) and compile it as is -- decorators dropped (numba's @jit is an optimisation, not semantics)."""
+    import ast
+    src = open(path).read()
+    tree = ast.parse(src)
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name == name:
+            node.decorator_list = []
+            mod = ast.Module(body=[node], type_ignores=[])
+            ns = dict(extra_globals)
+            exec(compile(ast.fix_missing_locations(mod), path, 'exec'), ns)
+            return ns[name]
+    raise KeyError(name)
+
+
+def run_neighbour_cases():
+    """oracle.neighbours_oracle vs the reference's own code; the REFERENCE's outputs go to tests/golden/neigh.npz"""
+    out = {}
+    pre = '/root/reference/scripts/genx/preprocess_dataset.py'
+    ref_downsample = _reference_function(pre, 'downsample_ev_repr', {'torch': torch})
+    ref_correct_time = _reference_function(pre, '_correct_time', {'np': np})
+    # downsample_ev_repr on a StackedHistogram output (uint8) and on a MixedDensity output (int8)
+    c = VOXEL_CASES['uniform']
+    x, y, p, t = make_voxel_events(c)
+    sh = StackedHistogram(c['bins'], c['height'], c['width'], 10, True).construct(*(torch.from_numpy(a) for a in (x, y, p, t)))
+    ds = ref_downsample(sh.unsqueeze(0), 0.5)[0].numpy()
+    assert np.array_equal(ds, no.downsample_ev_repr(sh.numpy())), 'downsample_ev_repr (uint8)'
+    out['ds_u8'] = ds
+    odd = torch.from_numpy(np.random.RandomState(3).randint(0, 255, (3, 37, 51)).astype(np.uint8))     # odd H, W
+    ds_odd = ref_downsample(odd.unsqueeze(0), 0.5)[0].numpy()
+    assert np.array_equal(ds_odd, no.downsample_ev_repr(odd.numpy())), 'downsample_ev_repr (odd sizes)'
+    out['ds_odd_in'], out['ds_odd'] = odd.numpy(), ds_odd
+    # _correct_time
+    tg = make_time_glitched(31, 20000)
+    tr = tg.copy()
+    ref_correct_time(tr)
+    assert np.array_equal(tr, no.correct_time(tg)), '_correct_time'
+    out['ct'] = tr
+    # window indices: the reference's expression IS np.searchsorted (:511-516); pin the two branches
+    ts = np.sort(np.random.RandomState(32).randint(0, 2_000_000, 50000).astype(np.int64))
+    q = np.arange(50_000, 2_000_000, 50_000, dtype=np.int64)
+    s_d, e_d = no.event_window_indices(ts, q, None, 50)
+    s_n, e_n = no.event_window_indices(ts, q, 3000, None)
+    assert np.array_equal(e_d, np.searchsorted(ts, q, side='right')) and np.array_equal(s_d, np.searchsorted(ts, q - 50000, side='left'))
+    out['win_start_dt'], out['win_end'], out['win_start_n'] = s_d, e_d, s_n
+    # MixedDensityEventStack
+    for name, c in MIXED_DENSITY_CASES.items():
+        x, y, p, t = make_voxel_events(c)
+        ref = MixedDensityEventStack(c['bins'], c['height'], c['width'], c['cutoff']).construct(
+            *(torch.from_numpy(a) for a in (x, y, p, t))).numpy()
+        mine = no.mixed_density_stack(x, y, p, t, c['bins'], c['height'], c['width'], c['cutoff'])
+        assert ref.dtype == np.int8 and np.array_equal(ref, mine), name
+        out[name] = ref
+        print(f'mixed density {name}: bit-exact; n={len(x)} range [{ref.min()}, {ref.max()}]')
+    np.savez_compressed(os.path.join(GOLD, 'neigh.npz'), **out)
+    print('neighbours: downsample / correct_time / window indices / mixed density pinned to the reference')
+
+
 if __name__ == '__main__':
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     only = [a.split('=', 1)[1] for a in sys.argv if a.startswith('--only=')]     # --only=<case>[,<case>...]
     only = set(only[0].split(',')) if only else None
     want = lambda n: only is None or n in only
+    if '--grads-only' not in sys.argv and want('neigh'):
+        run_neighbour_cases()
     if '--grads-only' not in sys.argv:
         for n, c in VOXEL_CASES.items():
             if want(n):

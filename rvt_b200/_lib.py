@@ -49,6 +49,14 @@ SIGNATURES = {
     'rvt_im2col': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     'rvt_col2im': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     'rvt_colsum': (_i, [_vp, _i64, _i, _i, _vp, _vp]),
+    # ---- harness glue + preprocessing neighbours ----
+    'rvt_state_reset': (_i, [_vp, _vp, _vp, _i, _i64, _vp]),
+    'rvt_gather_rows': (_i, [_vp, _vp, _i, _i64, _i64, _vp, _vp]),
+    'rvt_downsample2_nearest': (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    'rvt_cummax_scratch_elems': (_i64, [_i64]),
+    'rvt_cummax_i64': (_i, [_vp, _i64, _i64, _vp, _vp]),
+    'rvt_searchsorted_i64': (_i, [_vp, _i64, _vp, _i64, _i, _vp, _vp]),
+    'rvt_mixed_density_stack': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

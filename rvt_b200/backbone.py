@@ -372,7 +372,7 @@ class RNNDetector(nn.Module):
         return x.contiguous()
 
     def _stage_step(self, s: int, pk: dict, cur: torch.Tensor, cur_nchw: bool, prev_state: LstmState,
-                    token_mask: Optional[torch.Tensor], want_h16: bool = True):
+                    token_mask: Optional[torch.Tensor], want_h16: bool = True, h_out: Optional[torch.Tensor] = None):
         """One RNNDetectorStage.forward (maxvit_rnn.py:169-182) enqueued on the CURRENT stream:
         downsample(+LN) -> [window block, grid block] x num_blocks -> Conv-LSTM.  Scratch buffers are
         per stage, so different stages may run concurrently on different streams."""
@@ -430,12 +430,13 @@ class RNNDetector(nn.Module):
             sxh = self._scratch_buf(f'xh{s}', ((n_tok + 127) // 128) * 128 * 2 * c, torch.float16, dev)
         # fp16 copy of h_t for the next stage's im2col loader (half the bytes, no conversion)
         h16 = torch.empty(xs.shape, dtype=torch.float16, device=dev) if (want_h16 and s + 1 < self.num_stages) else None
-        h_new, c_new = ops.dws_conv_lstm(xs, hp, cp, pk, st.lstm.ks, sxh, h16)
+        h_new, c_new = ops.dws_conv_lstm(xs, hp, cp, pk, st.lstm.ks, sxh, h16, h_out=h_out)
         return h_new, c_new, h16
 
     @torch.no_grad()
     def forward_sequence(self, xs, prev_states: Optional[LstmStates] = None, token_masks=None,
-                         wavefront: bool = True, input_ready=None):
+                         wavefront: bool = True, input_ready=None, reset_mask: Optional[torch.Tensor] = None,
+                         select: Optional[torch.Tensor] = None):
         """Run consecutive timesteps (extension of the reference API; the reference's time loop lives
         in the harness, modules/detection.py:131-148 / :231-243).
 
@@ -450,6 +451,17 @@ class RNNDetector(nn.Module):
         input_ready: optional per-step CUDA events (e.g. of host->device copies on a copy stream) the
         first stage waits on.  After the call ``self.last_step_events[t]`` is the event recorded when
         step t's last stage finished (lets a caller overlap device->host reads of step t).
+
+        Harness glue on the device, so one captured graph serves a whole batch of the reference's
+        ``training_step`` / ``_val_test_step_impl`` time loop (modules/detection.py:117-159, :217-255):
+
+        reset_mask: bool / uint8 [B] device tensor = the batch's ``is_first_sample``: the given ``prev_states`` are zeroed IN PLACE
+        for those samples before step 0, exactly ``RNNStates.reset`` (modules/utils/detection.py:96-113).
+
+        select: int32 [S] device tensor of ``t * B + b`` for every labelled (step, sample) pair in harness order (t ascending,
+        then ``valid_batch_indices``), negative = unused slot.  When given, a third value is returned:
+        ``{stage: [S, C, H, W]}`` = what ``BackboneFeatureSelector.get_batched_backbone_features()`` would hold (:24-46);
+        refill ``select`` in place before each graph replay and slice ``[:n_selected]``.
         """
         L = len(xs)
         if prev_states is None:
@@ -480,6 +492,17 @@ class RNNDetector(nn.Module):
         else:
             streams = [main] * n
         state = list(prev_states)
+        if reset_mask is not None:
+            assert reset_mask.device == dev and reset_mask.dtype in (torch.bool, torch.uint8)
+            reset_mask = reset_mask.contiguous()
+            for s in range(n):
+                if state[s] is None:
+                    continue
+                with torch.cuda.stream(streams[s]):
+                    hv, cv = (self._as_nhwc_f32(t_) for t_ in state[s])        # views of the caller's tensors when channels-last fp32
+                    ops.state_reset_(hv, cv, reset_mask)
+                    state[s] = (hv.permute(0, 3, 1, 2), cv.permute(0, 3, 1, 2))
+        seq_feats = None                     # select: every step's h_t of a stage lands in one [L, B, H, W, C] buffer
         outs = [dict() for _ in range(L)]
         feats_prev = [None] * L              # output of stage s-1 per step (channels-last)
         done = [[None] * L for _ in range(n)]
@@ -500,7 +523,17 @@ class RNNDetector(nn.Module):
                         streams[s].wait_event(done[s - 1][t])
                     cur, nchw = (x_t, True) if s == 0 else (feats_prev[t], False)
                     tm = token_masks[t] if (token_masks is not None and s == 0) else None
-                    h_new, c_new, h16 = self._stage_step(s, packed[s], cur, nchw, state[s], tm)
+                    h_dst = None
+                    if select is not None:
+                        if seq_feats is None:
+                            seq_feats = [None] * n
+                        if seq_feats[s] is None:
+                            bsz = x_t.shape[0]
+                            vh, vw = self.pad_to_hw if self.pad_to_hw is not None else (x_t.shape[2], x_t.shape[3])
+                            seq_feats[s] = torch.empty((L, bsz, vh // self.strides[s], vw // self.strides[s], self.stage_dims[s]),
+                                                       dtype=torch.float32, device=dev)
+                        h_dst = seq_feats[s][t]
+                    h_new, c_new, h16 = self._stage_step(s, packed[s], cur, nchw, state[s], tm, h_out=h_dst)
                     if wavefront or s == n - 1:
                         ev = torch.cuda.Event()
                         ev.record(streams[s])
@@ -516,11 +549,22 @@ class RNNDetector(nn.Module):
                     state[s] = (h_new.permute(0, 3, 1, 2), c_new.permute(0, 3, 1, 2))
                     outs[t][s + 1] = state[s][0]
         self.last_step_events = done[n - 1]
+        selected = None
+        if select is not None:
+            assert select.device == dev and select.dtype == torch.int32
+            selected = {}
+            for s in range(n):
+                with torch.cuda.stream(streams[s]):
+                    buf = seq_feats[s]
+                    sel = ops.gather_rows(buf.view((buf.shape[0] * buf.shape[1],) + tuple(buf.shape[2:])), select.contiguous())
+                    if wavefront and not capturing:
+                        sel.record_stream(main)
+                    selected[s + 1] = sel.permute(0, 3, 1, 2)
         if wavefront:
             for st_ in streams:
                 main.wait_stream(st_)
         del keep_alive          # all streams have been joined into `main`: same-stream reuse from here on is ordered
-        return outs, state
+        return (outs, state) if select is None else (outs, state, selected)
 
 
 def build_recurrent_backbone(backbone_cfg):

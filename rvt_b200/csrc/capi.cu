@@ -14,6 +14,7 @@
 #include "attn_v2.cuh"
 #include "mlp_v2.cuh"
 #include "voxel.cuh"
+#include "neighbours.cuh"
 #include "train.cuh"
 
 using namespace rvt;
@@ -1021,6 +1022,87 @@ int rvt_colsum(const void* a, int64_t m, int n, int ld, float* acc, void* stream
   if (rows_per_block < min_rows) rows_per_block = min_rows;
   colsum_kernel<<<cdiv(m, rows_per_block), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(a), m, n, ld, acc, static_cast<int>(rows_per_block));
+  return static_cast<int>(cudaGetLastError());
+}
+
+
+// ======================================================================================
+// harness glue and preprocessing neighbours (neighbours.cuh)
+// ======================================================================================
+static unsigned stream_grid(int64_t items, int per_cta) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t blocks = (items + per_cta - 1) / per_cta;
+  const int64_t cap = static_cast<int64_t>(sms) * 8;
+  if (blocks > cap) blocks = cap;
+  return static_cast<unsigned>(blocks < 1 ? 1 : blocks);
+}
+
+int rvt_state_reset(float* h, float* c, const uint8_t* mask, int batch, int64_t per_sample, void* stream) {
+  if (!h || !mask || batch < 0 || per_sample < 0 || per_sample % 4 != 0) return kErrBadArg;
+  if ((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(c)) & 15) return kErrBadArg;
+  if (batch == 0 || per_sample == 0) return 0;
+  const int64_t per4 = per_sample / 4;
+  state_reset_kernel<<<stream_grid(batch * per4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(h, c, mask, batch, per4);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int rvt_gather_rows(const float* src, const int32_t* idx, int n_idx, int64_t n_src_rows, int64_t row_elems, float* dst, void* stream) {
+  if (!src || !idx || !dst || n_idx < 0 || row_elems < 0 || row_elems % 4 != 0) return kErrBadArg;
+  if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) return kErrBadArg;
+  if (n_idx == 0 || row_elems == 0) return 0;
+  const int64_t row4 = row_elems / 4;
+  gather_rows_kernel<<<stream_grid(n_idx * row4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, idx, n_idx, n_src_rows, row4, dst);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int rvt_downsample2_nearest(const uint8_t* in, int channels, int height, int width, uint8_t* out, void* stream) {
+  if (!in || !out || channels < 1 || height < 2 || width < 2) return kErrBadArg;
+  const int ho = height / 2, wo = width / 2;
+  downsample2_nearest_kernel<<<stream_grid(static_cast<int64_t>(channels) * ho * wo, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, channels, height, width, out, ho, wo);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int64_t rvt_cummax_scratch_elems(int64_t n) { return (n + kScanChunk - 1) / kScanChunk + 1; }
+
+int rvt_cummax_i64(int64_t* t, int64_t n, int64_t floor_value, int64_t* scratch, void* stream) {
+  if (n < 0 || (n > 0 && (!t || !scratch))) return kErrBadArg;
+  if (n == 0) return 0;
+  const int64_t parts = (n + kScanChunk - 1) / kScanChunk;
+  if (parts > 0x7fffffffLL) return kErrUnsupported;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cummax_chunk_max_kernel<<<static_cast<unsigned>(parts), 256, 0, st>>>(t, n, scratch);
+  cummax_scan_parts_kernel<<<1, 1024, 0, st>>>(scratch, static_cast<int>(parts), floor_value);
+  cummax_apply_kernel<<<static_cast<unsigned>(parts), 256, 0, st>>>(t, n, scratch);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int rvt_searchsorted_i64(const int64_t* sorted, int64_t n, const int64_t* queries, int64_t n_queries, int right, int64_t* out,
+                         void* stream) {
+  if (n < 0 || n_queries < 0 || (n_queries > 0 && (!queries || !out)) || (n > 0 && !sorted)) return kErrBadArg;
+  if (n_queries == 0) return 0;
+  searchsorted_kernel<<<static_cast<unsigned>((n_queries + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      sorted, n, queries, n_queries, right, out);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int rvt_mixed_density_stack(const int64_t* x, const int64_t* y, const int64_t* pol, const int64_t* t, int64_t n, int bins, int height,
+                            int width, int count_cutoff, float t_lo, float t_hi, const float* thresholds, int32_t* counts,
+                            int8_t* out, int* err_flag, void* stream) {
+  if (bins < 1 || height < 1 || width < 1 || n < 0 || !counts || !out || !err_flag || (bins > 1 && !thresholds)) return kErrBadArg;
+  const int64_t hw = static_cast<int64_t>(height) * width;
+  if (hw * bins >= (static_cast<int64_t>(1) << 31)) return kErrUnsupported;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n > 0) {
+    if (!x || !y || !pol || !t) return kErrBadArg;
+    mixed_density_accumulate_kernel<<<stream_grid(n, 256), 256, 0, st>>>(x, y, pol, t, n, bins, height, width, t_lo, t_hi, thresholds,
+                                                                       counts, err_flag);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  mixed_density_finalize_kernel<<<static_cast<unsigned>((hw + 255) / 256), 256, 0, st>>>(counts, out, bins, hw, count_cutoff);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -129,19 +129,53 @@ def mlp_block_(x: torch.Tensor, blk: dict, scratch_hidden: torch.Tensor,
 @device_guarded
 def dws_conv_lstm(x: torch.Tensor, h_prev: Optional[torch.Tensor], c_prev: Optional[torch.Tensor], pk: dict,
                   dws_ks: int, scratch_xh: Optional[torch.Tensor] = None,
-                  h16_out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """DWSConvLSTM2d.forward (rnn.py:36-69) on channels-last tensors -> (h_t, c_t)."""
+                  h16_out: Optional[torch.Tensor] = None, h_out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """DWSConvLSTM2d.forward (rnn.py:36-69) on channels-last tensors -> (h_t, c_t).  h_out: optional destination of h_t
+    (a slice of a whole-sequence feature buffer, see RNNDetector.forward_sequence(select=...))."""
     assert x.is_cuda and x.is_contiguous() and x.dtype == torch.float32
     b, h, w, c = x.shape
     for t in (h_prev, c_prev):
         assert t is None or (t.shape == x.shape and t.is_contiguous() and t.dtype == torch.float32)
-    h_new, c_new = torch.empty_like(x), torch.empty_like(x)
+    if h_out is not None:
+        assert h_out.shape == x.shape and h_out.is_contiguous() and h_out.dtype == torch.float32 and h_out.device == x.device
+    h_new, c_new = (h_out if h_out is not None else torch.empty_like(x)), torch.empty_like(x)
     L = _lib.lib()
     _lib.check(L.rvt_dws_conv_lstm(
         _lib.ptr(x), _lib.ptr(h_prev), _lib.ptr(c_prev), b, h, w, c, _lib.ptr(pk['lstm_w']), _lib.ptr(pk['lstm_b']),
         _lib.ptr(pk['dw_w']), _lib.ptr(pk['dw_b']), pk['dws_mode'], dws_ks, _lib.ptr(h_new), _lib.ptr(c_new),
         _lib.ptr(scratch_xh), _lib.ptr(h16_out), _stream(x)), 'dws_conv_lstm')
     return h_new, c_new
+
+
+# =============================================================================================
+# SURVEY.md 8(f3): harness glue of modules/utils/detection.py as device-side ops (graph-capturable, no host sync)
+# =============================================================================================
+@device_guarded
+def state_reset_(h: torch.Tensor, c: Optional[torch.Tensor], mask: torch.Tensor) -> None:
+    """RNNStates.reset -> recursive_reset (modules/utils/detection.py:96-113): ``state[mask] = 0`` in place for one stage's
+    (h, c); h / c contiguous f32 with the batch as the leading dimension, mask bool / uint8 [B] on the same device."""
+    assert h.is_cuda and h.is_contiguous() and h.dtype == torch.float32
+    assert c is None or (c.shape == h.shape and c.is_contiguous() and c.dtype == torch.float32)
+    assert mask.device == h.device and mask.numel() == h.shape[0] and mask.dtype in (torch.bool, torch.uint8) and mask.is_contiguous()
+    b = h.shape[0]
+    _lib.check(_lib.lib().rvt_state_reset(_lib.ptr(h), _lib.ptr(c), _lib.ptr(mask), b, h.numel() // max(b, 1), _stream(h)),
+               'state_reset')
+
+
+@device_guarded
+def gather_rows(src: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """BackboneFeatureSelector (modules/utils/detection.py:24-46) over a whole sequence: out[j] = src[idx[j]] for the leading
+    dimension (idx int32 [S] on the device, negative = empty slot -> zeros)."""
+    assert src.is_cuda and src.is_contiguous() and src.dtype == torch.float32
+    assert idx.device == src.device and idx.dtype == torch.int32 and idx.is_contiguous()
+    rows = src.shape[0]
+    row_elems = src.numel() // max(rows, 1)
+    if out is None:
+        out = torch.empty((idx.numel(),) + tuple(src.shape[1:]), dtype=torch.float32, device=src.device)
+    assert out.is_contiguous() and out.numel() == idx.numel() * row_elems
+    _lib.check(_lib.lib().rvt_gather_rows(_lib.ptr(src), _lib.ptr(idx), idx.numel(), rows, row_elems, _lib.ptr(out), _stream(src)),
+               'gather_rows')
+    return out
 
 
 # =============================================================================================

@@ -73,3 +73,25 @@ def make_voxel_events(case):
         t = np.full(n, 12345, np.int64)
     t = t + np.int64(case.get('t_offset', 0))
     return x, y, p, t
+
+
+# ---- neighbours of the voxelizer -------------------------------------------------------------------
+MIXED_DENSITY_CASES = {
+    'md_uniform': dict(n=120000, height=48, width=64, bins=10, seed=21, cutoff=None),
+    'md_hot_cut3': dict(n=150000, height=24, width=32, bins=10, seed=22, cutoff=3, hot_fraction=0.4, hot_pixels=2),
+    'md_wrap': dict(n=60000, height=4, width=4, bins=4, seed=23, cutoff=None, hot_fraction=0.9, hot_pixels=1),   # int8 wrap-around
+    'md_single': dict(n=1, height=6, width=8, bins=10, seed=24, cutoff=5),
+    'md_same_ts': dict(n=2000, height=8, width=8, bins=10, seed=25, cutoff=None, same_timestamp=True),
+    'md_empty': dict(n=0, height=8, width=8, bins=10, seed=26, cutoff=None),
+    'md_bins1': dict(n=5000, height=8, width=8, bins=1, seed=27, cutoff=7),
+}
+
+
+def make_time_glitched(seed: int, n: int):
+    """sorted timestamps with backwards glitches (what H5Reader._correct_time repairs)"""
+    rs = np.random.RandomState(seed)
+    t = np.sort(rs.randint(0, 1_000_000, n).astype(np.int64))
+    bad = rs.uniform(size=n) < 0.02
+    t = np.where(bad, t - rs.randint(1, 5000, n), t)
+    t[0] = abs(t[0])
+    return np.where(t < 0, 0, t)

@@ -89,3 +89,28 @@ def test_backbone_oracle_gradients_match_reference_golden(name):
         got = p.grad.contiguous().reshape(-1)[::grad_sub(name)]
         assert float((got - ref).norm()) <= 1e-4 * float(gold['n.' + k]) + 1e-12, k
         assert abs(float(p.grad.double().norm()) - float(gold['n.' + k])) <= 1e-4 * float(gold['n.' + k]) + 1e-12, k
+
+
+def test_neighbour_oracles_match_reference_golden():
+    """downsample_ev_repr, _correct_time, window indices, MixedDensityEventStack restatements vs the
+    REFERENCE's outputs (tests/golden/neigh.npz, minted by oracle/make_golden.py from the reference's own code)."""
+    import numpy as np
+    from oracle import neighbours_oracle as no
+    from oracle import voxel_oracle as vo
+    from tests.golden_configs import MIXED_DENSITY_CASES, VOXEL_CASES, make_time_glitched, make_voxel_events
+    from tests.helpers import GOLD
+    gold = np.load(os.path.join(GOLD, 'neigh.npz'))
+    c = VOXEL_CASES['uniform']
+    x, y, p, t = make_voxel_events(c)
+    sh = vo.stacked_histogram(x, y, p, t, c['bins'], c['height'], c['width'], 10, True)
+    assert np.array_equal(no.downsample_ev_repr(sh), gold['ds_u8'])
+    assert np.array_equal(no.downsample_ev_repr(gold['ds_odd_in']), gold['ds_odd'])
+    assert np.array_equal(no.correct_time(make_time_glitched(31, 20000)), gold['ct'])
+    ts = np.sort(np.random.RandomState(32).randint(0, 2_000_000, 50000).astype(np.int64))
+    q = np.arange(50_000, 2_000_000, 50_000, dtype=np.int64)
+    s_d, e_d = no.event_window_indices(ts, q, None, 50)
+    s_n, _ = no.event_window_indices(ts, q, 3000, None)
+    assert np.array_equal(s_d, gold['win_start_dt']) and np.array_equal(e_d, gold['win_end']) and np.array_equal(s_n, gold['win_start_n'])
+    for name, c in MIXED_DENSITY_CASES.items():
+        x, y, p, t = make_voxel_events(c)
+        assert np.array_equal(no.mixed_density_stack(x, y, p, t, c['bins'], c['height'], c['width'], c['cutoff']), gold[name]), name
