@@ -228,6 +228,30 @@ int rvt_mixed_density_stack(const int64_t* x, const int64_t* y, const int64_t* p
                             int height, int width, int count_cutoff, float t_lo, float t_hi, const float* thresholds,
                             int32_t* counts, int8_t* out, int* err_flag, void* stream);
 
+/* ---- f2: YOLOPAFPN + YOLOXHead inference + postprocess (the step right after the backbone) -------------
+ * (models/detection/yolox_extension/models/yolo_pafpn.py:109-139, yolox/models/yolo_head.py:165-290, yolox/utils/boxes.py:32-76)
+ * BaseConv = Conv2d(bias=False) + BatchNorm2d + SiLU (network_blocks.py:29-51) as ONE implicit-GEMM launch: BatchNorm folded
+ * into w_packed (packing.pack_conv_weight of the scaled kernel, K order (ky, kx, ci)) + bias.  Tensors are channels-last
+ * f16 with a pixel pitch, so th.cat along channels is writing channel slices of one buffer.  in: [B,Hin,Win] pixels of `cin`
+ * channels, pitch in_pitch; out: [round_up(B*Hout*Wout,128)] pixels of cout_padded (multiple of 16) channels, pitch out_pitch.
+ * act: 0 none, 4 SiLU. */
+int rvt_conv2d_nhwc_f16(const void* in, int in_pitch, int batch, int cin, int hin, int win, int ksize, int stride, int pad, int hout,
+                        int wout, int cout_padded, const void* w_packed, const float* bias, int act, void* out, int out_pitch,
+                        void* stream);
+/* f32 [B,H,W,C] given by element strides (any layout) -> f16 channel slice dst (pixel pitch dst_pitch). */
+int rvt_cast_slice_f16(const float* src, int64_t sb, int64_t sy, int64_t sx, int64_t sc, int batch, int height, int width, int channels,
+                       void* dst, int dst_pitch, void* stream);
+/* F.interpolate(scale_factor=2, mode='nearest-exact') (yolo_pafpn.py:47) between f16 channel slices; src is [B,height,width]. */
+int rvt_upsample2_slice_f16(const void* src, int src_pitch, int batch, int height, int width, int channels, void* dst, int dst_pitch,
+                            void* stream);
+/* One head level: [reg(4)|obj(1)] and [cls(nc)] f16 rows -> decoded f32 out[b, anchor_offset + y*W + x, 5+nc] (yolo_head.py:228-232,271-290). */
+int rvt_yolox_decode(const void* regobj, int regobj_pitch, const void* cls, int cls_pitch, int batch, int height, int width,
+                     int num_classes, float stride_px, int anchor_offset, int anchors_total, float* out, void* stream);
+/* postprocess (boxes.py:32-76): prediction f32 [B, anchors, 5+nc] (cx, cy, w, h, obj, cls..) -> detections f32 [B, anchors, 7]
+ * (x1, y1, x2, y2, obj_conf, class_conf, class_pred), the first counts[b] rows of image b valid, in score order. anchors <= 8192. */
+int rvt_yolox_postprocess(const float* prediction, int batch, int anchors, int num_classes, float conf_thre, float nms_thre,
+                          float* detections, int* counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

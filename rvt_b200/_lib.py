@@ -56,6 +56,11 @@ SIGNATURES = {
     'rvt_cummax_scratch_elems': (_i64, [_i64]),
     'rvt_cummax_i64': (_i, [_vp, _i64, _i64, _vp, _vp]),
     'rvt_searchsorted_i64': (_i, [_vp, _i64, _vp, _i64, _i, _vp, _vp]),
+    'rvt_conv2d_nhwc_f16': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp]),
+    'rvt_cast_slice_f16': (_i, [_vp, _i64, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _i, _vp]),
+    'rvt_upsample2_slice_f16': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    'rvt_yolox_decode': (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _vp, _vp]),
+    'rvt_yolox_postprocess': (_i, [_vp, _i, _i, _i, _f, _f, _vp, _vp, _vp]),
     'rvt_mixed_density_stack': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp]),
 }
 

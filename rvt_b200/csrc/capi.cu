@@ -15,6 +15,7 @@
 #include "mlp_v2.cuh"
 #include "voxel.cuh"
 #include "neighbours.cuh"
+#include "det.cuh"
 #include "train.cuh"
 
 using namespace rvt;
@@ -1103,6 +1104,72 @@ int rvt_mixed_density_stack(const int64_t* x, const int64_t* y, const int64_t* p
     if (e != cudaSuccess) return static_cast<int>(e);
   }
   mixed_density_finalize_kernel<<<static_cast<unsigned>((hw + 255) / 256), 256, 0, st>>>(counts, out, bins, hw, count_cutoff);
+  return static_cast<int>(cudaGetLastError());
+}
+
+
+// ======================================================================================
+// YOLOPAFPN + YOLOXHead inference + postprocess (det.cuh; convs on the gemm_fused family)
+// ======================================================================================
+int rvt_conv2d_nhwc_f16(const void* in, int in_pitch, int batch, int cin, int hin, int win, int ksize, int stride, int pad, int hout,
+                        int wout, int cout_padded, const void* w_packed, const float* bias, int act, void* out, int out_pitch,
+                        void* stream) {
+  if (!in || !w_packed || !out || batch < 1 || cin % 8 != 0 || cout_padded % 16 != 0 || in_pitch % 8 != 0 || out_pitch % 8 != 0)
+    return kErrBadArg;
+  if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) return kErrBadArg;
+  GemmArgs a{};
+  const int64_t n_tok = static_cast<int64_t>(batch) * hout * wout;
+  a.K = cin * ksize * ksize;
+  a.BN = rvt_tile_n(cout_padded, a.K);
+  if (a.BN < 0) return kErrUnsupported;
+  a.Wp = static_cast<const __half*>(w_packed); a.bias = bias;
+  a.map = identity_map(n_tok, hout, wout);
+  a.Hout = hout; a.Wout = wout;
+  a.cin = in; a.in_dtype = 2; a.in_nchw = 0; a.in_pitch = in_pitch;
+  a.Cin = cin; a.Hin = hin; a.Win = win; a.KSy = a.KSx = ksize; a.sy = a.sx = stride; a.pady = a.padx = pad;
+  a.o16 = static_cast<__half*>(out); a.ldo = out_pitch; a.act = act;
+  return launch_gemm<LD_CONV, EP_F16>(a, cdiv(n_tok, 128), cout_padded / a.BN, static_cast<cudaStream_t>(stream));
+}
+
+int rvt_cast_slice_f16(const float* src, int64_t sb, int64_t sy, int64_t sx, int64_t sc, int batch, int height, int width, int channels,
+                       void* dst, int dst_pitch, void* stream) {
+  if (!src || !dst || batch < 1 || channels < 1) return kErrBadArg;
+  const int64_t total = static_cast<int64_t>(batch) * height * width * channels;
+  cast_slice_f16_kernel<<<stream_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, sb, sy, sx, sc, batch, height, width,
+                                                                                            channels, static_cast<__half*>(dst), dst_pitch);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int rvt_upsample2_slice_f16(const void* src, int src_pitch, int batch, int height, int width, int channels, void* dst, int dst_pitch,
+                            void* stream) {
+  if (!src || !dst || channels % 8 != 0 || src_pitch % 8 != 0 || dst_pitch % 8 != 0) return kErrBadArg;
+  if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) return kErrBadArg;
+  const int64_t total = static_cast<int64_t>(batch) * 4 * height * width * (channels / 8);
+  upsample2_slice_f16_kernel<<<stream_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(src), src_pitch, batch, height, width, channels, static_cast<__half*>(dst), dst_pitch);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int rvt_yolox_decode(const void* regobj, int regobj_pitch, const void* cls, int cls_pitch, int batch, int height, int width,
+                     int num_classes, float stride_px, int anchor_offset, int anchors_total, float* out, void* stream) {
+  if (!regobj || !cls || !out || num_classes < 1 || regobj_pitch < 5 || cls_pitch < num_classes) return kErrBadArg;
+  const int64_t total = static_cast<int64_t>(batch) * height * width;
+  yolox_decode_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(regobj), regobj_pitch, static_cast<const __half*>(cls), cls_pitch, batch, height, width, num_classes,
+      stride_px, anchor_offset, anchors_total, out);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int rvt_yolox_postprocess(const float* prediction, int batch, int anchors, int num_classes, float conf_thre, float nms_thre,
+                          float* detections, int* counts, void* stream) {
+  if (!prediction || !detections || !counts || batch < 0 || num_classes < 1) return kErrBadArg;
+  if (anchors > kNmsMax) return kErrUnsupported;
+  if (batch == 0) return 0;
+  const int smem = kNmsMax * 8 + kNmsMax;
+  static DevOnce once;
+  if (cudaError_t e = ensure_smem_attr(once, yolox_postprocess_kernel, smem); e != cudaSuccess) return static_cast<int>(e);
+  yolox_postprocess_kernel<<<batch, 1024, smem, static_cast<cudaStream_t>(stream)>>>(prediction, anchors, num_classes, conf_thre, nms_thre,
+                                                                                    detections, counts);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -88,6 +88,7 @@ struct GemmArgs {
   const float* hprev; const float* dw_w; const float* dw_b; int dws_mode; int dws_ks;
   // LD_CONV (rectangular kernel / stride / pad so the space-to-depth stem maps onto it)
   const void* cin; int in_dtype; int in_nchw; int Cin, Hin, Win, KSy, KSx, sy, sx, pady, padx, Hout, Wout;
+  int in_pitch;        // channels-last input: elements between consecutive pixels (0 = Cin; > Cin reads a channel slice of a wider buffer)
   // EP_F16
   __half* o16; int ldo; int act;
   __half* o16_pre;                     // optional second store: the pre-activation (bias added), same ld (training forward)
@@ -424,7 +425,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_fused_kernel(const __gri
           for (int i = 0; i < 4; ++i) {
             const int iy = ciy[i] + ky, ix = cix[i] + kx;
             const bool ok = kv && tok[i] >= 0 && iy >= 0 && iy < Hin && ix >= 0 && ix < Win;
-            const size_t off = ok ? (static_cast<size_t>(cb[i] * Hin + iy) * Win + ix) * Cin + ci : 0;
+            const size_t off = ok ? (static_cast<size_t>(cb[i] * Hin + iy) * Win + ix) * (a.in_pitch > 0 ? a.in_pitch : Cin) + ci : 0;
             if (a.in_dtype == 2) {
               uint4 o = make_uint4(0, 0, 0, 0);
               if (ok) o = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.cin) + off));
@@ -614,6 +615,9 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_fused_kernel(const __gri
         if (a.act == 1) {
 #pragma unroll
           for (int e = 0; e < 16; ++e) v[e] = gelu_erf(v[e]);
+        } else if (a.act == 4) {     // SiLU (yolox network_blocks.py:29-51 BaseConv act)
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = v[e] * sigmoid_acc(v[e]);
         } else if (a.act == 2) {
           const __half* ap = a.aux16 + static_cast<size_t>(row) * a.ldaux + nt * BN + c0;
           const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(ap)), a1 = __ldg(reinterpret_cast<const uint4*>(ap + 8));
