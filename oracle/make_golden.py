@@ -25,6 +25,8 @@ from oracle import voxel_oracle as vo  # noqa: E402
 from tests.golden_configs import (BACKBONE_CASES, MIXED_DENSITY_CASES, VOXEL_CASES, make_time_glitched, make_voxel_events,  # noqa: E402
                                   spec_of)
 from oracle import neighbours_oracle as no  # noqa: E402
+from oracle import detection_oracle as do  # noqa: E402
+from tests.golden_configs import DETECTION_CASES, POSTPROCESS_CASES, detection_inputs  # noqa: E402
 from tests.helpers import GRAD_CASES, grad_sub, case_inputs, train_loss  # noqa: E402
 
 from models.detection.recurrent_backbone import build_recurrent_backbone  # noqa: E402
@@ -169,6 +171,50 @@ def _reference_function(path, name, extra_globals):
     raise KeyError(name)
 
 
+def run_detection_cases():
+    """oracle.detection_oracle vs the reference's YOLOPAFPN / YOLOXHead / postprocess; the REFERENCE's outputs
+    are committed (tests/golden/det.npz)."""
+    from models.detection.yolox_extension.models.yolo_pafpn import YOLOPAFPN
+    from models.detection.yolox.models.yolo_head import YOLOXHead
+    from models.detection.yolox.utils.boxes import postprocess
+    out = {}
+    for name, c in DETECTION_CASES.items():
+        torch.manual_seed(0)
+        fpn = YOLOPAFPN(depth=c['depth'], in_stages=(2, 3, 4), in_channels=c['in_channels']).eval()
+        head = YOLOXHead(num_classes=c['num_classes'], strides=(8, 16, 32), in_channels=c['in_channels']).eval()
+        sd_f = do.synth_state({k: tuple(v.shape) for k, v in fpn.state_dict().items()}, c['seed'])
+        sd_h = do.synth_state({k: tuple(v.shape) for k, v in head.state_dict().items()}, c['seed'] + 1)
+        fpn.load_state_dict(sd_f, strict=True)
+        head.load_state_dict(sd_h, strict=True)
+        feats = {k: torch.from_numpy(v) for k, v in detection_inputs(c).items()}
+        with torch.no_grad():
+            r = fpn(feats)
+            ro, losses = head(r)
+            o = do.pafpn_forward(feats, sd_f, depth=c['depth'])
+            oo = do.head_forward(o, sd_h)
+        assert losses is None
+        w1 = max(float((a - b).abs().max()) for a, b in zip(r, o))
+        w2 = float(((ro - oo).abs() / ro.abs().clamp_min(1.0)).max())
+        assert w1 < 1e-5 and w2 < 1e-5, (name, w1, w2)
+        for i, t in enumerate(r):
+            out[f'{name}_fpn{i}'] = t.numpy()
+        out[f'{name}_head'] = ro.numpy()
+        print(f'detection {name}: oracle-vs-reference fpn {w1:.1e}, head {w2:.1e}; head out {tuple(ro.shape)}')
+    for name, c in POSTPROCESS_CASES.items():
+        pred = do.synth_predictions(c['seed'], c['batch'], c['anchors'], c['num_classes'])
+        ref = postprocess(torch.from_numpy(pred.copy()), c['num_classes'], c['conf'], c['nms'])
+        mine = do.postprocess(pred, c['num_classes'], c['conf'], c['nms'])
+        for i, (a, b) in enumerate(zip(ref, mine)):
+            assert (a is None) == (b is None), name
+            if a is not None:
+                assert a.shape == b.shape and np.array_equal(a.numpy(), b), (name, i)
+                out[f'{name}_img{i}'] = a.numpy()
+            else:
+                out[f'{name}_img{i}'] = np.zeros((0, 7), np.float32)
+        print(f'postprocess {name}: oracle == reference (torchvision batched_nms), {[0 if a is None else len(a) for a in ref]} detections')
+    np.savez_compressed(os.path.join(GOLD, 'det.npz'), **out)
+
+
 def run_neighbour_cases():
     """oracle.neighbours_oracle vs the reference's own code; the REFERENCE's outputs go to tests/golden/neigh.npz"""
     out = {}
@@ -220,6 +266,8 @@ if __name__ == '__main__':
     want = lambda n: only is None or n in only
     if '--grads-only' not in sys.argv and want('neigh'):
         run_neighbour_cases()
+    if '--grads-only' not in sys.argv and want('det'):
+        run_detection_cases()
     if '--grads-only' not in sys.argv:
         for n, c in VOXEL_CASES.items():
             if want(n):

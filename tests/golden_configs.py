@@ -95,3 +95,24 @@ def make_time_glitched(seed: int, n: int):
     t = np.where(bad, t - rs.randint(1, 5000, n), t)
     t[0] = abs(t[0])
     return np.where(t < 0, 0, t)
+
+
+# ---- PAFPN + YOLOX head + postprocess ----------------------------------------------------------------
+DETECTION_CASES = {
+    # RVT-Base gen4 (1Mpx): stages 2-4 dims (128, 256, 512), depth 0.67, 3 classes; small spatial sizes
+    'det_b_gen4': dict(in_channels=(128, 256, 512), depth=0.67, num_classes=3, batch=2, hw8=(12, 20), seed=51),
+    # RVT-Tiny gen1: dims (64, 128, 256), depth 0.33, 2 classes
+    'det_t_gen1': dict(in_channels=(64, 128, 256), depth=0.33, num_classes=2, batch=1, hw8=(16, 20), seed=52),
+}
+POSTPROCESS_CASES = {
+    'pp_gen4': dict(seed=5, batch=3, anchors=5040, num_classes=3, conf=0.1, nms=0.45),
+    'pp_small': dict(seed=6, batch=2, anchors=300, num_classes=2, conf=0.3, nms=0.45),
+}
+
+
+def detection_inputs(case):
+    rs = np.random.RandomState(case['seed'] + 100)
+    h, w = case['hw8']
+    b = case['batch']
+    return {st: (rs.normal(0, 0.3, (b, c, h >> i, w >> i))).astype(np.float32)
+            for i, (st, c) in enumerate(zip((2, 3, 4), case['in_channels']))}

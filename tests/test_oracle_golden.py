@@ -114,3 +114,33 @@ def test_neighbour_oracles_match_reference_golden():
     for name, c in MIXED_DENSITY_CASES.items():
         x, y, p, t = make_voxel_events(c)
         assert np.array_equal(no.mixed_density_stack(x, y, p, t, c['bins'], c['height'], c['width'], c['cutoff']), gold[name]), name
+
+
+def test_detection_oracles_match_reference_golden():
+    """PAFPN / YOLOX head / postprocess restatements vs the REFERENCE's outputs (tests/golden/det.npz)."""
+    import numpy as np
+    from oracle import detection_oracle as do
+    from tests.golden_configs import DETECTION_CASES, POSTPROCESS_CASES, detection_inputs
+    from tests.helpers import GOLD
+    import rvt_b200.detection as det
+    gold = np.load(os.path.join(GOLD, 'det.npz'))
+    for name, c in DETECTION_CASES.items():
+        fpn = det.YOLOPAFPN(depth=c['depth'], in_stages=(2, 3, 4), in_channels=c['in_channels'])
+        head = det.YOLOXHead(num_classes=c['num_classes'], strides=(8, 16, 32), in_channels=c['in_channels'])
+        sd_f = do.synth_state({k: tuple(v.shape) for k, v in fpn.state_dict().items()}, c['seed'])
+        sd_h = do.synth_state({k: tuple(v.shape) for k, v in head.state_dict().items()}, c['seed'] + 1)
+        fpn.load_state_dict(sd_f, strict=True)          # the mirror's state_dict keys / shapes are the reference's
+        head.load_state_dict(sd_h, strict=True)
+        feats = {k: torch.from_numpy(v) for k, v in detection_inputs(c).items()}
+        with torch.no_grad():
+            o = do.pafpn_forward(feats, sd_f, depth=c['depth'])
+            oo = do.head_forward(o, sd_h)
+        for i, t in enumerate(o):
+            assert float((t - torch.from_numpy(gold[f'{name}_fpn{i}'])).abs().max()) < 1e-5
+        ref = torch.from_numpy(gold[f'{name}_head'])
+        assert float(((oo - ref).abs() / ref.abs().clamp_min(1.0)).max()) < 1e-5
+    for name, c in POSTPROCESS_CASES.items():
+        pred = do.synth_predictions(c['seed'], c['batch'], c['anchors'], c['num_classes'])
+        for i, d in enumerate(do.postprocess(pred, c['num_classes'], c['conf'], c['nms'])):
+            g = gold[f'{name}_img{i}']
+            assert (d is None and len(g) == 0) or np.array_equal(d, g)
