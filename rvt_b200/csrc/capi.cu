@@ -13,6 +13,7 @@
 #include "attn_fused.cuh"
 #include "attn_v2.cuh"
 #include "mlp_v2.cuh"
+#include "lstm_v2.cuh"
 #include "voxel.cuh"
 #include "neighbours.cuh"
 #include "det.cuh"
@@ -187,6 +188,12 @@ int persistent_sms() {
   return (cached > 0 && cached < sms) ? cached : sms;
 }
 
+int v2_cta_cap() {          // experiment knob: total CTAs of the persistent kernels (0 = SMs x CTAs/SM)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("RVT_V2_CTAS"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
 template <int NH, int KC1>
 int launch_attn_v2(const AttnV2Args& a, const CUtensorMap& tm, cudaStream_t st) {
   using Cfg = AttnV2Cfg<NH, KC1>;
@@ -195,6 +202,7 @@ int launch_attn_v2(const AttnV2Args& a, const CUtensorMap& tm, cudaStream_t st) 
   if (cudaError_t e = ensure_smem_attr(once, attn_v2_kernel<NH, KC1>, static_cast<int>(Cfg::SMEM)); e != cudaSuccess)
     return static_cast<int>(e);
   int grid = persistent_sms() * Cfg::CTAS_PER_SM;
+  if (v2_cta_cap() > 0) grid = v2_cta_cap();
   if (grid > a.n_tiles) grid = a.n_tiles;
   if (grid <= 0) return 0;
   attn_v2_kernel<NH, KC1><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(a, tm);
@@ -225,9 +233,28 @@ int launch_mlp_v2(const MlpV2Args& a, const CUtensorMap& tm, cudaStream_t st) {
   static DevOnce once;
   if (cudaError_t e = ensure_smem_attr(once, mlp_v2_kernel<H2>, static_cast<int>(kMv2Smem)); e != cudaSuccess) return static_cast<int>(e);
   int grid = persistent_sms();
+  if (v2_cta_cap() > 0) grid = v2_cta_cap();
   if (grid > a.n_tiles) grid = a.n_tiles;
   if (grid <= 0) return 0;
   mlp_v2_kernel<H2><<<grid, kMv2Threads, kMv2Smem, st>>>(a, tm);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int lstm_v2_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("RVT_LSTM_V2"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
+int launch_lstm_v2(const LstmV2Args& a, const CUtensorMap& tx, const CUtensorMap& th, cudaStream_t st) {
+  static_assert(kLv2Smem <= kMaxSmem, "lstm_v2 shared memory");
+  static DevOnce once;
+  if (cudaError_t e = ensure_smem_attr(once, lstm_v2_kernel, static_cast<int>(kLv2Smem)); e != cudaSuccess) return static_cast<int>(e);
+  int grid = persistent_sms();
+  if (v2_cta_cap() > 0) grid = v2_cta_cap();
+  if (grid > a.n_tiles) grid = a.n_tiles;
+  if (grid <= 0) return 0;
+  lstm_v2_kernel<<<grid, kLv2Threads, kLv2Smem, st>>>(a, tx, th);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -684,6 +711,18 @@ static int dws_conv_lstm_impl(const float* x, const float* h_prev, const float* 
   a.gates16 = static_cast<__half*>(gates16);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int n_mtiles = cdiv(n_tok, 128);
+  if (lstm_v2_enabled() && dws_mode == 0 && dim <= 64 && cw == dim && !gates16 && n_mtiles > 0) {
+    // persistent kernel, resident gate weight, TMA-staged x / h tiles, double-buffered accumulators (lstm_v2.cuh)
+    alignas(64) CUtensorMap tx, th;
+    if (make_tmap_f32_rows(x, n_tok, dim, &tx) && (!h_prev || make_tmap_f32_rows(h_prev, n_tok, dim, &th))) {
+      if (!h_prev) th = tx;
+      LstmV2Args la{};
+      la.cprev = c_prev; la.hout = h_out; la.cout = c_out; la.hout16 = static_cast<__half*>(h_out_f16);
+      la.n_tokens = static_cast<int>(n_tok); la.C = dim; la.n_tiles = n_mtiles; la.has_h = h_prev != nullptr;
+      la.w = static_cast<const __half*>(w_packed); la.bias = bias_tiled;
+      return launch_lstm_v2(la, tx, th, st);
+    }
+  }
   if (dws_mode == 0 && dim >= kWideDim && scratch_xh != nullptr) {
     // wide stage, plain 1x1 cell: cast [x|h] once, then a TMA-fed mainloop (no per-N-tile A rebuild)
     const int n_rows = n_mtiles * 128;
