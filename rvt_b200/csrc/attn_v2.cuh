@@ -42,6 +42,7 @@ struct AttnV2Args {
   const float* bproj;        // [C] or null
   const float* gamma;        // [C] or null
   float scale_log2e;
+  int fast_ln;               // 1: C == 32 * nh and the x tile arrives as nh 32-channel SW128 half tiles (thread-per-row LayerNorm)
 };
 
 constexpr int kAv2Stages = 3;
@@ -58,7 +59,7 @@ struct AttnV2Cfg {
   static constexpr uint32_t SLOT = KC1 * 96 * 128;          // >= proj K-atom (C * 128 <= 64 * KC1 * 128)
   static constexpr int CHUNKS = NH + KC1;                   // weight chunks per tile
   static constexpr bool RESIDENT = CHUNKS <= kAv2Stages;
-  static constexpr uint32_t PAR_FLOATS = NH * 96 + 4 * 64 * KC1;
+  static constexpr uint32_t PAR_FLOATS = NH * 96 + 4 * 64 * KC1 + NH * 256;     // + per-row LayerNorm partial sums
   static constexpr uint32_t SMEM = 1024 + R1 + R2 + R3 + kAv2Stages * SLOT + PAR_FLOATS * 4 + 64 * 4 + 4 * 4 + 32 * 8 + 16;
   static constexpr int TMEM_COLS = 128 * NH;
   static constexpr int CTAS_PER_SM = NH <= 2 ? 2 : 1;
@@ -68,6 +69,54 @@ struct AttnV2Cfg {
 __device__ __forceinline__ void lds8(const float* p, float* v) {
   const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// Thread-per-row LayerNorm on a [128 rows x 32 fp32] half tile that TMA wrote with SWIZZLE_128B (row r's 16-byte chunk c
+// sits at r*128 + ((c ^ (r & 7)) << 4): the 8 lanes of a quarter warp hit 8 different bank groups, conflict free).  `part`
+// exchanges the per-row partial sums between the NWG warpgroups that share a row; one named barrier (id `bar_id`, NWG*128
+// threads).  The result goes to 16-byte chunks [4*wg, 4*wg+4) of the row's 128-byte operand row, i.e. K columns [32*wg, +32).
+template <int NWG>
+__device__ __forceinline__ void ln_row32_to_operand(uint32_t half_tile, int row, int wg, bool valid, bool do_ln, int C, float eps,
+                                                    const float* s_lnw, const float* s_lnb, float* part, int bar_id,
+                                                    uint32_t a_tile_base) {
+  float v[32];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint32_t src = half_tile + sw128_offset(row, c);
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[4 * c]), "=f"(v[4 * c + 1]), "=f"(v[4 * c + 2]), "=f"(v[4 * c + 3]) : "r"(src));
+  }
+  if (!valid) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] = 0.f;
+  }
+  if (do_ln) {
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) { s1 += v[e]; s2 = fmaf(v[e], v[e], s2); }
+    if (NWG > 1) {
+      part[(wg * 128 + row) * 2] = s1;
+      part[(wg * 128 + row) * 2 + 1] = s2;
+      named_bar_sync(bar_id, NWG * 128);
+      s1 = 0.f; s2 = 0.f;
+#pragma unroll
+      for (int w = 0; w < NWG; ++w) { s1 += part[(w * 128 + row) * 2]; s2 += part[(w * 128 + row) * 2 + 1]; }
+    }
+    const float mean = s1 / C;
+    const float rstd = rsqrtf(fmaxf(s2 / C - mean * mean, 0.f) + eps);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float g[8], bb[8];
+      lds8(s_lnw + 32 * wg + 8 * c, g);
+      lds8(s_lnb + 32 * wg + 8 * c, bb);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[8 * c + e] = valid ? fmaf((v[8 * c + e] - mean) * rstd, g[e], bb[e]) : 0.f;
+    }
+  }
+  const uint32_t dst = a_tile_base + ((32 * wg) >> 6) * kAv2Tile;
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    st_smem_16B(dst + sw128_offset(row, (wg & 1) * 4 + c), pack_h2(v[8 * c], v[8 * c + 1]), pack_h2(v[8 * c + 2], v[8 * c + 3]),
+                pack_h2(v[8 * c + 4], v[8 * c + 5]), pack_h2(v[8 * c + 6], v[8 * c + 7]));
 }
 
 template <int NH, int KC1>
@@ -95,7 +144,8 @@ attn_v2_kernel(const __grid_constant__ AttnV2Args a, const __grid_constant__ CUt
   float* s_gamma = s_bproj + 64 * KC1;
   float* s_lnw = s_gamma + 64 * KC1;
   float* s_lnb = s_lnw + 64 * KC1;
-  int* s_lut = reinterpret_cast<int*>(s_lnb + 64 * KC1);     // [64] token offset of position p inside its group
+  float* s_part = s_lnb + 64 * KC1;                          // [NH][128][2] LayerNorm partial sums (fast_ln)
+  int* s_lut = reinterpret_cast<int*>(s_part + NH * 256);    // [64] token offset of position p inside its group
   int* s_tbase = s_lut + 64;                                 // [2 parities][2 groups] first token of the group, -1 = no group
   uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_tbase + 4) + 7) & ~static_cast<uintptr_t>(7));
   uint64_t* x_full = bars + 0;        // tx
@@ -156,6 +206,9 @@ attn_v2_kernel(const __grid_constant__ AttnV2Args a, const __grid_constant__ CUt
       // ---------------- LayerNorm of the x tile -> A operand (8 lanes per row) ----------------
       mbar_wait(x_full, par);
       const int* tb = s_tbase + 2 * par;
+      if (a.fast_ln) {
+        ln_row32_to_operand<NH>(sR1 + h * kAv2Tile, row, h, pos < P && tb[grp] >= 0, a.do_ln != 0, C, a.eps, s_lnw, s_lnb, s_part, 1, sA);
+      } else
       for (int r = tid >> 3; r < 128; r += NW / 8) {
         const bool valid = (r & 63) < P && tb[r >> 6] >= 0;
         float v[KC1][8];
@@ -409,8 +462,15 @@ attn_v2_kernel(const __grid_constant__ AttnV2Args a, const __grid_constant__ CUt
           }
         }
         mbar_arrive_expect_tx(x_full, nv * grp_bytes);
-        for (int g = 0; g < 2; ++g)
-          if (tb[g] >= 0) tma_load_5d(sR1 + g * 64 * C * 4, &tmap_x, 0, c1[g], c2[g], c3[g], c4[g], x_full);
+        for (int g = 0; g < 2; ++g) {
+          if (tb[g] < 0) continue;
+          if (a.fast_ln) {           // NH half tiles of 32 channels, each [128 rows x 128 B] with the 128-byte swizzle
+            for (int j = 0; j < NH; ++j)
+              tma_load_5d(sR1 + j * kAv2Tile + g * 64 * 128, &tmap_x, 32 * j, c1[g], c2[g], c3[g], c4[g], x_full);
+          } else {
+            tma_load_5d(sR1 + g * 64 * C * 4, &tmap_x, 0, c1[g], c2[g], c3[g], c4[g], x_full);
+          }
+        }
       }
     }
     __syncwarp();

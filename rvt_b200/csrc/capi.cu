@@ -157,7 +157,8 @@ int launch_ln_rows_any_f16(const float* x, const RowMap& map, int64_t n_rows, in
 // (reference maxvit.py:273-304):
 //   window: dims (C, pw, nx, ph, B*ny), box (C, pw, 1, ph, 1) at (0, 0, gx, 0, b*ny + gy)
 //   grid  : dims (C, nx, pw, ny, B*ph), box (C, 1, pw, 1, ph) at (0, gx, 0, gy, b*ph)
-bool make_tmap_partition_f32(const float* x, int batch, int H, int W, int C, int ph, int pw, int grid, CUtensorMap* out) {
+bool make_tmap_partition_f32(const float* x, int batch, int H, int W, int C, int ph, int pw, int grid, CUtensorMap* out,
+                             int box_c = 0) {   // box_c = 32: 32-channel boxes with the 128-byte swizzle (thread-per-row LayerNorm)
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn || (reinterpret_cast<uintptr_t>(x) & 15) || C % 4 != 0 || C > 256 || pw > 256 || ph > 256) return false;
   const cuuint64_t ny = H / ph, nx = W / pw, cb = static_cast<cuuint64_t>(C) * 4;
@@ -166,15 +167,16 @@ bool make_tmap_partition_f32(const float* x, int batch, int H, int W, int C, int
   if (!grid) {
     gdim[0] = C; gdim[1] = pw; gdim[2] = nx; gdim[3] = ph; gdim[4] = static_cast<cuuint64_t>(batch) * ny;
     gstride[0] = cb; gstride[1] = pw * cb; gstride[2] = W * cb; gstride[3] = static_cast<cuuint64_t>(ph) * W * cb;
-    box[0] = C; box[1] = pw; box[2] = 1; box[3] = ph; box[4] = 1;
+    box[0] = box_c ? box_c : C; box[1] = pw; box[2] = 1; box[3] = ph; box[4] = 1;
   } else {
     gdim[0] = C; gdim[1] = nx; gdim[2] = pw; gdim[3] = ny; gdim[4] = static_cast<cuuint64_t>(batch) * ph;
     gstride[0] = cb; gstride[1] = nx * cb; gstride[2] = W * cb; gstride[3] = ny * W * cb;
-    box[0] = C; box[1] = 1; box[2] = pw; box[3] = 1; box[4] = ph;
+    box[0] = box_c ? box_c : C; box[1] = 1; box[2] = pw; box[3] = 1; box[4] = ph;
   }
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(x), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 int persistent_sms() {
@@ -210,15 +212,16 @@ int launch_attn_v2(const AttnV2Args& a, const CUtensorMap& tm, cudaStream_t st) 
 }
 
 // fp32 row-major [rows, cols] -> box of all `cols` columns x 128 rows, no swizzle (token tiles of the residual stream)
-bool make_tmap_f32_rows(const float* base, int64_t rows, int cols, CUtensorMap* out) {
+bool make_tmap_f32_rows(const float* base, int64_t rows, int cols, CUtensorMap* out, int box_c = 0) {   // box_c = 32: SW128 half tiles
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn || (reinterpret_cast<uintptr_t>(base) & 15) || cols % 4 != 0 || cols > 256) return false;
   const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * 4};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(cols), 128};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_c ? box_c : cols), 128};
   const cuuint32_t estr[2] = {1, 1};
   return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 int mlp_v2_enabled() {
@@ -509,8 +512,12 @@ static int partition_attention_impl(const float* x, float* x_out, int force_unfu
     if (attn_v2_enabled() && P <= 64 && ((nh <= 2 && dim <= 64) || (nh == 4 && dim > 64)) && dim % 16 == 0 && (dim / nh) % 8 == 0) {
       // persistent, head-parallel kernel with TMA-staged partition tiles (attn_v2.cuh)
       alignas(64) CUtensorMap tm;
-      if (make_tmap_partition_f32(x_out, batch, height, width, dim, ph, pw, grid, &tm)) {
+      static int fast_env = -1;
+      if (fast_env < 0) { const char* e = getenv("RVT_V2_FAST_LN"); fast_env = e ? atoi(e) : 1; }
+      const int fast_ln = (fast_env && dim == 32 * nh) ? 1 : 0;
+      if (make_tmap_partition_f32(x_out, batch, height, width, dim, ph, pw, grid, &tm, fast_ln ? 32 : 0)) {
         AttnV2Args va{};
+        va.fast_ln = fast_ln;
         va.x = x_out; va.map = m; va.C = dim; va.dh = dim_head; va.nh = nh; va.n_tiles = n_mtiles;
         va.ln_w = n1_w; va.ln_b = n1_b; va.eps = eps; va.do_ln = n1_w != nullptr;
         va.wqkv = fa.wqkv; va.bqkv = bqkv; va.wproj = fa.wproj; va.bproj = bproj; va.gamma = gamma1;
@@ -616,8 +623,12 @@ static int mlp_block_impl(const float* x, float* x_out, int force_unfused, void*
     if (mlp_v2_enabled() && dim <= 64 && hidden <= 256 && n_mtiles > 0) {
       // persistent kernel, resident weights, TMA-staged token tiles (mlp_v2.cuh)
       alignas(64) CUtensorMap tm;
-      if (make_tmap_f32_rows(x_out, n_tokens, dim, &tm)) {
+      static int fast_env = -1;
+      if (fast_env < 0) { const char* e = getenv("RVT_V2_FAST_LN"); fast_env = e ? atoi(e) : 1; }
+      const int fast_ln = (fast_env && (dim == 32 || dim == 64)) ? 1 : 0;
+      if (make_tmap_f32_rows(x_out, n_tokens, dim, &tm, fast_ln ? 32 : 0)) {
         MlpV2Args va{};
+        va.fast_ln = fast_ln;
         va.x = x_out; va.n_tokens = static_cast<int>(n_tokens); va.C = dim; va.hidden = hidden; va.n_tiles = n_mtiles;
         va.ln_w = n2_w; va.ln_b = n2_b; va.eps = eps; va.w1p = ma.w1p; va.b1 = b1; va.w2p = ma.w2p; va.b2 = b2; va.gamma = gamma2;
         return ma.gelu_f16x2 ? launch_mlp_v2<true>(va, tm, st) : launch_mlp_v2<false>(va, tm, st);

@@ -28,13 +28,14 @@ struct MlpV2Args {
   const __half* w2p;        // pack_linear_weight(W2[C, hidden], bn = C):  [1][hidden/64][C x 64]
   const float* b2;
   const float* gamma;       // LayerScale or null
+  int fast_ln;              // 1: C in {32, 64}: x tiles arrive as 32-channel SW128 half tiles, thread-per-row LayerNorm
 };
 
 constexpr int kMv2Workers = 512;
 constexpr int kMv2Threads = kMv2Workers + 64;          // + MMA warp + producer warp
 constexpr uint32_t kMv2XBuf = 128 * 64 * 4;            // one fp32 x tile (C <= 64)
 constexpr uint32_t kMv2Smem = 1024 + 2 * kMv2XBuf + kAv2Tile /*A*/ + 4 * kAv2Tile /*H*/ + 4 * 8192 /*W1*/ + 4 * 8192 /*W2*/ +
-                              (256 + 4 * 64) * 4 + 24 * 8 + 16;
+                              (256 + 4 * 64 + 2 * 256) * 4 + 24 * 8 + 16;
 
 template <bool GELU_H2>
 __global__ void __launch_bounds__(kMv2Threads, 1)
@@ -56,7 +57,8 @@ mlp_v2_kernel(const __grid_constant__ MlpV2Args a, const __grid_constant__ CUten
   float* s_gamma = s_b2 + 64;
   float* s_lnw = s_gamma + 64;
   float* s_lnb = s_lnw + 64;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_lnb + 64);
+  float* s_part = s_lnb + 64;                                                // [2][128][2] LayerNorm partial sums (fast_ln)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 2 * 256);
   uint64_t* x_full = bars + 0;        // [2] tx
   uint64_t* x_free = bars + 2;        // [2] 512
   uint64_t* a_full = bars + 4;        // 512
@@ -103,6 +105,12 @@ mlp_v2_kernel(const __grid_constant__ MlpV2Args a, const __grid_constant__ CUten
       mbar_wait(&x_full[b], (it >> 1) & 1);
       const uint32_t xb = sX + b * kMv2XBuf;
       const int k0 = j8 * 8;
+      if (a.fast_ln) {
+        if (32 * wg < C) {
+          if (C == 64) ln_row32_to_operand<2>(xb + wg * kAv2Tile, row, wg, true, true, C, a.eps, s_lnw, s_lnb, s_part, 1, sA);
+          else ln_row32_to_operand<1>(xb + wg * kAv2Tile, row, wg, true, true, C, a.eps, s_lnw, s_lnb, s_part, 1, sA);
+        }
+      } else
       for (int r = tid >> 3; r < 128; r += kMv2Workers / 8) {
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (k0 < C) {
@@ -244,7 +252,11 @@ mlp_v2_kernel(const __grid_constant__ MlpV2Args a, const __grid_constant__ CUten
         const int b = it & 1;
         mbar_wait(&x_free[b], ((it >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&x_full[b], x_bytes);
-        tma_load_2d(sX + b * kMv2XBuf, &tmap_x, 0, tile * 128, &x_full[b]);
+        if (a.fast_ln) {
+          for (int j = 0; 32 * j < C; ++j) tma_load_2d(sX + b * kMv2XBuf + j * kAv2Tile, &tmap_x, 32 * j, tile * 128, &x_full[b]);
+        } else {
+          tma_load_2d(sX + b * kMv2XBuf, &tmap_x, 0, tile * 128, &x_full[b]);
+        }
       }
     }
     __syncwarp();

@@ -46,9 +46,11 @@ def check_against_golden(name, case, step_fn, tol, device='cpu', input_dtype=tor
     stride = case.get('sub', 1)
     save_steps = case.get('save_steps', [case['steps'] - 1])
     worst = 0.0
+    tol_fn = tol if callable(tol) else (lambda _step: tol)
     for step, feats, states in replay_case(case, step_fn, device, input_dtype):
         if step not in save_steps:
             continue
+        tol = tol_fn(step)
         for s in range(4):
             hh, cc = states[s]
             assert feats[s + 1].shape == hh.shape
