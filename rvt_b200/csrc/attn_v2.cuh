@@ -299,9 +299,14 @@ attn_v2_kernel(const __grid_constant__ AttnV2Args a, const __grid_constant__ CUt
         float v[16];
         tmem_ld_x16(ts + k0, v);
         tmem_ld_wait();
+        if (k0 + 16 <= P) {                  // full chunk: no masking (P = 60: three of the four chunks)
 #pragma unroll
-        for (int e = 0; e < 16; ++e)
-          if (k0 + e < P) mx = fmaxf(mx, v[e]);
+          for (int e = 0; e < 16; ++e) mx = fmaxf(mx, v[e]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (k0 + e < P) mx = fmaxf(mx, v[e]);
+        }
       }
       const float mxs = mx * a.scale_log2e;
       float sum = 0.f;
@@ -309,11 +314,16 @@ attn_v2_kernel(const __grid_constant__ AttnV2Args a, const __grid_constant__ CUt
         float v[16];
         tmem_ld_x16(ts + k0, v);
         tmem_ld_wait();
+        if (k0 + 16 <= P) {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float p = (k0 + e < P) ? ex2_approx(fmaf(v[e], a.scale_log2e, -mxs)) : 0.f;
-          sum += p;
-          v[e] = p;
+          for (int e = 0; e < 16; ++e) { v[e] = ex2_approx(fmaf(v[e], a.scale_log2e, -mxs)); sum += v[e]; }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float p = (k0 + e < P) ? ex2_approx(fmaf(v[e], a.scale_log2e, -mxs)) : 0.f;
+            sum += p;
+            v[e] = p;
+          }
         }
         st_smem_16B(sP + sw128_offset(row, k0 >> 3), pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
         st_smem_16B(sP + sw128_offset(row, (k0 >> 3) + 1), pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]),
