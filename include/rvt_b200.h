@@ -252,6 +252,10 @@ int rvt_yolox_decode(const void* regobj, int regobj_pitch, const void* cls, int 
 int rvt_yolox_postprocess(const float* prediction, int batch, int anchors, int num_classes, float conf_thre, float nms_thre,
                           float* detections, int* counts, void* stream);
 
+/* Profiling aid, not part of the reference boundary: device buffer int64 [grid][8][12] the persistent kernels fill with
+ * %globaltimer stamps of their phase boundaries (profiles/trace_v2.py); NULL disables. */
+int rvt_debug_set_trace(void* buf);
+
 #ifdef __cplusplus
 }
 #endif

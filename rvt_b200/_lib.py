@@ -61,6 +61,7 @@ SIGNATURES = {
     'rvt_upsample2_slice_f16': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     'rvt_yolox_decode': (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _vp, _vp]),
     'rvt_yolox_postprocess': (_i, [_vp, _i, _i, _i, _f, _f, _vp, _vp, _vp]),
+    'rvt_debug_set_trace': (_i, [_vp]),
     'rvt_mixed_density_stack': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp]),
 }
 

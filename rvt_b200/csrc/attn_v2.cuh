@@ -42,8 +42,13 @@ struct AttnV2Args {
   const float* bproj;        // [C] or null
   const float* gamma;        // [C] or null
   float scale_log2e;
+  long long* trace;          // optional [grid][kTraceTiles][kTracePts] globaltimer stamps of warp 0 lane 0 (profiling aid)
   int fast_ln;               // 1: C == 32 * nh and the x tile arrives as nh 32-channel SW128 half tiles (thread-per-row LayerNorm)
 };
+
+constexpr int kTraceTiles = 8, kTracePts = 12;
+__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define RVT_TRACE(args, it, pt) do { if ((args).trace && tid == 0 && (it) < kTraceTiles) (args).trace[(static_cast<long long>(blockIdx.x) * kTraceTiles + (it)) * kTracePts + (pt)] = gtime(); } while (0)
 
 constexpr int kAv2Stages = 3;
 constexpr uint32_t kAv2Tile = 16384;     // one [128 x 64] fp16 operand atom
@@ -204,7 +209,9 @@ attn_v2_kernel(const __grid_constant__ AttnV2Args a, const __grid_constant__ CUt
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t par = it & 1;
       // ---------------- LayerNorm of the x tile -> A operand (8 lanes per row) ----------------
+      RVT_TRACE(a, it, 0);
       mbar_wait(x_full, par);
+      RVT_TRACE(a, it, 1);
       const int* tb = s_tbase + 2 * par;
       if (a.fast_ln) {
         ln_row32_to_operand<NH>(sR1 + h * kAv2Tile, row, h, pos < P && tb[grp] >= 0, a.do_ln != 0, C, a.eps, s_lnw, s_lnb, s_part, 1, sA);
@@ -258,6 +265,7 @@ attn_v2_kernel(const __grid_constant__ AttnV2Args a, const __grid_constant__ CUt
       fence_proxy_async_smem();
       tc_fence_before();            // orders this thread's TMEM reads of the previous tile before the MMAs that follow a_full
       mbar_arrive(a_full);
+      RVT_TRACE(a, it, 2);
 
       // residual row segment of this thread, fetched early (the latency hides behind the whole attention chain)
       const int gbase = tb[grp];
@@ -266,6 +274,7 @@ attn_v2_kernel(const __grid_constant__ AttnV2Args a, const __grid_constant__ CUt
 
       // ---------------- QKV_h accumulators + bias -> Q_h | K_h | V_h operand tiles ----------------
       mbar_wait(&qkv_full[h], par);
+      RVT_TRACE(a, it, 3);
       tc_fence_after();
 #pragma unroll
       for (int part = 0; part < 3; ++part) {
@@ -289,9 +298,11 @@ attn_v2_kernel(const __grid_constant__ AttnV2Args a, const __grid_constant__ CUt
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(qk_ready);
+      RVT_TRACE(a, it, 4);
 
       // ---------------- masked softmax of S_h over the row's own group ----------------
       mbar_wait(s_full, par);
+      RVT_TRACE(a, it, 5);
       tc_fence_after();
       const uint32_t ts = tmem + lane_off + 128 * h + 64 * grp;
       float mx = -INFINITY;
@@ -333,9 +344,11 @@ attn_v2_kernel(const __grid_constant__ AttnV2Args a, const __grid_constant__ CUt
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_full[h]);
+      RVT_TRACE(a, it, 6);
 
       // ---------------- O_h / rowsum -> column block h of the proj A operand ----------------
       mbar_wait(&o_full[h], par);
+      RVT_TRACE(a, it, 7);
       tc_fence_after();
       {
         float v[32];
@@ -353,6 +366,7 @@ attn_v2_kernel(const __grid_constant__ AttnV2Args a, const __grid_constant__ CUt
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(so_full);
+      RVT_TRACE(a, it, 8);
 
       // ---------------- proj epilogue: + bias, * gamma, + residual, scatter (= partition reverse) ----------------
       float res[32];
@@ -361,6 +375,7 @@ attn_v2_kernel(const __grid_constant__ AttnV2Args a, const __grid_constant__ CUt
       for (int c8 = 0; c8 < 4; ++c8)
         if (live && c8 * 8 < cw) load8(xrow + c8 * 8, res + c8 * 8);
       mbar_wait(out_full, par);
+      RVT_TRACE(a, it, 9);
       tc_fence_after();
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8) {
@@ -379,6 +394,7 @@ attn_v2_kernel(const __grid_constant__ AttnV2Args a, const __grid_constant__ CUt
           *reinterpret_cast<float4*>(xrow + c8 * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
         }
       }
+      RVT_TRACE(a, it, 10);
     }
   } else if (warp == NH * 4) {
     // =============================================== MMA issuer ===============================================

@@ -190,6 +190,8 @@ int persistent_sms() {
   return (cached > 0 && cached < sms) ? cached : sms;
 }
 
+long long* g_v2_trace = nullptr;     // profiling aid: rvt_debug_set_trace()
+
 int v2_cta_cap() {          // experiment knob: total CTAs of the persistent kernels (0 = SMs x CTAs/SM)
   static int v = -1;
   if (v < 0) { const char* e = getenv("RVT_V2_CTAS"); v = e ? atoi(e) : 0; }
@@ -517,7 +519,7 @@ static int partition_attention_impl(const float* x, float* x_out, int force_unfu
       const int fast_ln = (fast_env && dim == 32 * nh) ? 1 : 0;
       if (make_tmap_partition_f32(x_out, batch, height, width, dim, ph, pw, grid, &tm, fast_ln ? 32 : 0)) {
         AttnV2Args va{};
-        va.fast_ln = fast_ln;
+        va.fast_ln = fast_ln; va.trace = g_v2_trace;
         va.x = x_out; va.map = m; va.C = dim; va.dh = dim_head; va.nh = nh; va.n_tiles = n_mtiles;
         va.ln_w = n1_w; va.ln_b = n1_b; va.eps = eps; va.do_ln = n1_w != nullptr;
         va.wqkv = fa.wqkv; va.bqkv = bqkv; va.wproj = fa.wproj; va.bproj = bproj; va.gamma = gamma1;
@@ -628,7 +630,7 @@ static int mlp_block_impl(const float* x, float* x_out, int force_unfused, void*
       const int fast_ln = (fast_env && (dim == 32 || dim == 64)) ? 1 : 0;
       if (make_tmap_f32_rows(x_out, n_tokens, dim, &tm, fast_ln ? 32 : 0)) {
         MlpV2Args va{};
-        va.fast_ln = fast_ln;
+        va.fast_ln = fast_ln; va.trace = g_v2_trace;
         va.x = x_out; va.n_tokens = static_cast<int>(n_tokens); va.C = dim; va.hidden = hidden; va.n_tiles = n_mtiles;
         va.ln_w = n2_w; va.ln_b = n2_b; va.eps = eps; va.w1p = ma.w1p; va.b1 = b1; va.w2p = ma.w2p; va.b2 = b2; va.gamma = gamma2;
         return ma.gelu_f16x2 ? launch_mlp_v2<true>(va, tm, st) : launch_mlp_v2<false>(va, tm, st);
@@ -1222,5 +1224,9 @@ int rvt_yolox_postprocess(const float* prediction, int batch, int anchors, int n
                                                                                     detections, counts);
   return static_cast<int>(cudaGetLastError());
 }
+
+/* profiling aid (not part of the reference boundary): device buffer int64 [grid][8][12] that the persistent v2 kernels fill
+ * with %globaltimer stamps of their phase boundaries; NULL disables. */
+int rvt_debug_set_trace(void* buf) { g_v2_trace = static_cast<long long*>(buf); return 0; }
 
 }  // extern "C"

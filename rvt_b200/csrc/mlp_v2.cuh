@@ -28,6 +28,7 @@ struct MlpV2Args {
   const __half* w2p;        // pack_linear_weight(W2[C, hidden], bn = C):  [1][hidden/64][C x 64]
   const float* b2;
   const float* gamma;       // LayerScale or null
+  long long* trace;         // optional [grid][kTraceTiles][kTracePts] globaltimer stamps (profiling aid)
   int fast_ln;              // 1: C in {32, 64}: x tiles arrive as 32-channel SW128 half tiles, thread-per-row LayerNorm
 };
 
@@ -147,8 +148,10 @@ mlp_v2_kernel(const __grid_constant__ MlpV2Args a, const __grid_constant__ CUten
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t par = it & 1;
+      RVT_TRACE(a, it, 0);
       // ---------------- GELU(it): hidden chunk wg -> fp16 operand chunk of fc2 ----------------
       mbar_wait(hid_full, par);                // everybody: fc1(it) has finished reading the A operand
+      RVT_TRACE(a, it, 1);
       tc_fence_after();
       if (wg < nch) {
         const uint32_t dst = sH + wg * kAv2Tile;
@@ -177,8 +180,10 @@ mlp_v2_kernel(const __grid_constant__ MlpV2Args a, const __grid_constant__ CUten
         tc_fence_before();
         mbar_arrive(&sh_full[wg]);
       }
+      RVT_TRACE(a, it, 2);
       // ---------------- LN(it + 1): the next tile's A operand (fc1(it+1) overlaps the epilogue below) ----------------
       if (tile + static_cast<int>(gridDim.x) < n_tiles) layer_norm(it + 1);
+      RVT_TRACE(a, it, 3);
       // ---------------- EPI(it): + b2, * gamma2, + residual -> x ----------------
       const int tok = tile * 128 + row;
       const bool live = tok < a.n_tokens;
@@ -190,6 +195,7 @@ mlp_v2_kernel(const __grid_constant__ MlpV2Args a, const __grid_constant__ CUten
         if (live && c8 * 8 < C) load8(xrow + c8 * 8, res + q * 8);
       }
       mbar_wait(out_full, par);
+      RVT_TRACE(a, it, 4);
       tc_fence_after();
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
@@ -210,6 +216,7 @@ mlp_v2_kernel(const __grid_constant__ MlpV2Args a, const __grid_constant__ CUten
       }
       tc_fence_before();
       mbar_arrive(out_free);
+      RVT_TRACE(a, it, 5);
     }
   } else if (warp == 16) {
     // =============================================== MMA issuer ===============================================
