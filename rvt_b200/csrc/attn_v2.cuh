@@ -65,7 +65,7 @@ struct AttnV2Cfg {
   static constexpr int CHUNKS = NH + KC1;                   // weight chunks per tile
   static constexpr bool RESIDENT = CHUNKS <= kAv2Stages;
   static constexpr uint32_t PAR_FLOATS = NH * 96 + 4 * 64 * KC1 + NH * 256;     // + per-row LayerNorm partial sums
-  static constexpr uint32_t SMEM = 1024 + R1 + R2 + R3 + kAv2Stages * SLOT + PAR_FLOATS * 4 + 64 * 4 + 4 * 4 + 32 * 8 + 16;
+  static constexpr uint32_t SMEM = 1024 + R1 + R2 + R3 + kAv2Stages * SLOT + PAR_FLOATS * 4 + 64 * 4 + 4 * 4 + 128 * 4 + 32 * 8 + 16;
   static constexpr int TMEM_COLS = 128 * NH;
   static constexpr int CTAS_PER_SM = NH <= 2 ? 2 : 1;
 };
@@ -152,7 +152,8 @@ attn_v2_kernel(const __grid_constant__ AttnV2Args a, const __grid_constant__ CUt
   float* s_part = s_lnb + 64 * KC1;                          // [NH][128][2] LayerNorm partial sums (fast_ln)
   int* s_lut = reinterpret_cast<int*>(s_part + NH * 256);    // [64] token offset of position p inside its group
   int* s_tbase = s_lut + 64;                                 // [2 parities][2 groups] first token of the group, -1 = no group
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_tbase + 4) + 7) & ~static_cast<uintptr_t>(7));
+  int* s_tok = s_tbase + 4;                                  // [128] token of every tile row (-1 = padding), for the coalesced epilogue
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_tok + 128) + 7) & ~static_cast<uintptr_t>(7));
   uint64_t* x_full = bars + 0;        // tx
   uint64_t* x_free = bars + 1;        // commit (PV done: R1 may be overwritten)
   uint64_t* a_full = bars + 2;        // NW
@@ -369,6 +370,61 @@ attn_v2_kernel(const __grid_constant__ AttnV2Args a, const __grid_constant__ CUt
       RVT_TRACE(a, it, 8);
 
       // ---------------- proj epilogue: + bias, * gamma, + residual, scatter (= partition reverse) ----------------
+      if (C % 32 == 0) {
+        // Coalesced version.  A thread owns a ROW of the accumulator (TMEM lane), but row-per-thread global accesses touch 32
+        // different 128-byte lines per instruction (the first profile's top cost: 3.5 us per tile).  So: (1) acc + bias, * gamma
+        // -> fp32 staging tile in shared memory (the A/O and V regions, dead by now; 16-byte chunks XOR-swizzled with row & 7),
+        // (2) the workers re-map to (row, 16-byte column chunk) so that the lanes of a warp cover whole 128-byte lines of x for
+        // the residual read and the store.
+        if (h == 0) s_tok[row] = tok;
+        mbar_wait(out_full, par);
+        RVT_TRACE(a, it, 9);
+        tc_fence_after();
+        const int nch = C >> 2;                                   // 16-byte chunks per row
+        const uint32_t srow = sA + static_cast<uint32_t>(row) * C * 4;
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          if (c8 * 8 >= cw) break;
+          float v[8];
+          tmem_ld_x8(tmem + lane_off + h * cw + c8 * 8, v);
+          tmem_ld_wait();
+          const int col = h * cw + c8 * 8;
+          float bv[8], gv[8];
+          lds8(s_bproj + col, bv);
+          lds8(s_gamma + col, gv);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = (v[e] + bv[e]) * gv[e];
+          const int ch = col >> 2;
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (((ch) ^ (row & 7)) << 4)), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (((ch + 1) ^ (row & 7)) << 4)), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+        }
+        tc_fence_before();
+        named_bar_sync(2, NW);
+        {
+          const int ch = tid % nch, r0 = tid / nch, rstep = NW / nch;
+          constexpr int kPass = 4;                                // rows in flight per thread (independent loads first)
+          for (int rb = r0; rb < 128; rb += rstep * kPass) {
+            float4 xr[kPass], sv[kPass];
+            int tk[kPass];
+#pragma unroll
+            for (int q = 0; q < kPass; ++q) {
+              const int r = rb + q * rstep;
+              tk[q] = r < 128 ? s_tok[r] : -1;
+              if (tk[q] >= 0) xr[q] = *reinterpret_cast<const float4*>(a.x + static_cast<size_t>(tk[q]) * C + ch * 4);
+            }
+#pragma unroll
+            for (int q = 0; q < kPass; ++q) {
+              const int r = rb + q * rstep;
+              if (tk[q] < 0) continue;
+              const uint32_t src = sA + static_cast<uint32_t>(r) * C * 4 + ((ch ^ (r & 7)) << 4);
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sv[q].x), "=f"(sv[q].y), "=f"(sv[q].z), "=f"(sv[q].w) : "r"(src));
+              *reinterpret_cast<float4*>(a.x + static_cast<size_t>(tk[q]) * C + ch * 4) =
+                  make_float4(xr[q].x + sv[q].x, xr[q].y + sv[q].y, xr[q].z + sv[q].z, xr[q].w + sv[q].w);
+            }
+          }
+        }
+        named_bar_sync(3, NW);                                    // the staging tile is the next tile's A operand / V
+      } else {
       float res[32];
       float* xrow = a.x + static_cast<size_t>(tok < 0 ? 0 : tok) * C + h * cw;
 #pragma unroll
@@ -393,6 +449,7 @@ attn_v2_kernel(const __grid_constant__ AttnV2Args a, const __grid_constant__ CUt
           *reinterpret_cast<float4*>(xrow + c8 * 8) = make_float4(v[0], v[1], v[2], v[3]);
           *reinterpret_cast<float4*>(xrow + c8 * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
         }
+      }
       }
       RVT_TRACE(a, it, 10);
     }

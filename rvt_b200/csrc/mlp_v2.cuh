@@ -185,6 +185,62 @@ mlp_v2_kernel(const __grid_constant__ MlpV2Args a, const __grid_constant__ CUten
       if (tile + static_cast<int>(gridDim.x) < n_tiles) layer_norm(it + 1);
       RVT_TRACE(a, it, 3);
       // ---------------- EPI(it): + b2, * gamma2, + residual -> x ----------------
+      if (C % 32 == 0) {
+        // coalesced version (see attn_v2.cuh): (acc + b2) * gamma -> swizzled fp32 staging tile in the (now idle) fc2 operand
+        // region, then (row, 16-byte chunk) threads read x / write x as whole 128-byte lines
+        mbar_wait(out_full, par);
+        RVT_TRACE(a, it, 4);
+        tc_fence_after();
+        const uint32_t srow = sH + static_cast<uint32_t>(row) * C * 4;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int c8 = wg + 4 * q;
+          if (c8 * 8 >= C) break;
+          float v[8];
+          tmem_ld_x8(t_out + lane_off + c8 * 8, v);
+          tmem_ld_wait();
+          float bv[8], gv[8];
+          lds8(s_b2 + c8 * 8, bv);
+          lds8(s_gamma + c8 * 8, gv);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = (v[e] + bv[e]) * gv[e];
+          const int ch = c8 * 2;
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((ch ^ (row & 7)) << 4)), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (((ch + 1) ^ (row & 7)) << 4)), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+        }
+        tc_fence_before();
+        mbar_arrive(out_free);                                    // the out accumulator is drained (fc2 of the next tile may start)
+        named_bar_sync(2, kMv2Workers);
+        {
+          const int nch = C >> 2;
+          const int ch = tid % nch, r0 = tid / nch, rstep = kMv2Workers / nch;
+          constexpr int kPass = 4;
+          for (int rb = r0; rb < 128; rb += rstep * kPass) {
+            float4 xr[kPass];
+            bool ok[kPass];
+#pragma unroll
+            for (int q = 0; q < kPass; ++q) {
+              const int r = rb + q * rstep;
+              ok[q] = r < 128 && tile * 128 + r < a.n_tokens;
+              if (ok[q]) xr[q] = *reinterpret_cast<const float4*>(a.x + static_cast<size_t>(tile * 128 + r) * C + ch * 4);
+            }
+#pragma unroll
+            for (int q = 0; q < kPass; ++q) {
+              const int r = rb + q * rstep;
+              if (!ok[q]) continue;
+              float4 sv;
+              const uint32_t src = sH + static_cast<uint32_t>(r) * C * 4 + ((ch ^ (r & 7)) << 4);
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sv.x), "=f"(sv.y), "=f"(sv.z), "=f"(sv.w) : "r"(src));
+              *reinterpret_cast<float4*>(a.x + static_cast<size_t>(tile * 128 + r) * C + ch * 4) =
+                  make_float4(xr[q].x + sv.x, xr[q].y + sv.y, xr[q].z + sv.z, xr[q].w + sv.w);
+            }
+          }
+        }
+        named_bar_sync(3, kMv2Workers);                           // the staging tile is the next tile's fc2 operand
+        RVT_TRACE(a, it, 5);
+        continue;
+      }
+      // ---------------- EPI(it): + b2, * gamma2, + residual -> x ----------------
       const int tok = tile * 128 + row;
       const bool live = tok < a.n_tokens;
       float* xrow = a.x + static_cast<size_t>(live ? tok : 0) * C;
