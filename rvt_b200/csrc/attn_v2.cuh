@@ -272,6 +272,7 @@ attn_v2_kernel(const __grid_constant__ AttnV2Args a, const __grid_constant__ CUt
       const int gbase = tb[grp];
       const bool live = pos < P && gbase >= 0;
       const int tok = live ? gbase + s_lut[pos] : -1;
+      if (h == 0) s_tok[row] = tok;                      // read by the coalesced epilogue (all workers) much later
 
       // ---------------- QKV_h accumulators + bias -> Q_h | K_h | V_h operand tiles ----------------
       mbar_wait(&qkv_full[h], par);
@@ -376,11 +377,22 @@ attn_v2_kernel(const __grid_constant__ AttnV2Args a, const __grid_constant__ CUt
         // -> fp32 staging tile in shared memory (the A/O and V regions, dead by now; 16-byte chunks XOR-swizzled with row & 7),
         // (2) the workers re-map to (row, 16-byte column chunk) so that the lanes of a warp cover whole 128-byte lines of x for
         // the residual read and the store.
-        if (h == 0) s_tok[row] = tok;
+        // residual prefetch in the coalesced (row, chunk) mapping, issued BEFORE the accumulator wait: the L2 latency of these
+        // loads hides behind the proj MMA (s_tok was published by the row threads at the top of the tile; the qk_ready / s_full
+        // hand-offs in between order those writes before these reads)
+        const int nch = C >> 2;                                   // 16-byte chunks per row
+        const int ech = tid % nch, er0 = tid / nch, erstep = NW / nch;
+        constexpr int kRows = 8;                                  // 128 rows * nch chunks / NW threads
+        float4 xr[kRows];
+        int tk[kRows];
+#pragma unroll
+        for (int q = 0; q < kRows; ++q) {
+          tk[q] = s_tok[er0 + q * erstep];
+          if (tk[q] >= 0) xr[q] = *reinterpret_cast<const float4*>(a.x + static_cast<size_t>(tk[q]) * C + ech * 4);
+        }
         mbar_wait(out_full, par);
         RVT_TRACE(a, it, 9);
         tc_fence_after();
-        const int nch = C >> 2;                                   // 16-byte chunks per row
         const uint32_t srow = sA + static_cast<uint32_t>(row) * C * 4;
 #pragma unroll
         for (int c8 = 0; c8 < 4; ++c8) {
@@ -400,28 +412,15 @@ attn_v2_kernel(const __grid_constant__ AttnV2Args a, const __grid_constant__ CUt
         }
         tc_fence_before();
         named_bar_sync(2, NW);
-        {
-          const int ch = tid % nch, r0 = tid / nch, rstep = NW / nch;
-          constexpr int kPass = 4;                                // rows in flight per thread (independent loads first)
-          for (int rb = r0; rb < 128; rb += rstep * kPass) {
-            float4 xr[kPass], sv[kPass];
-            int tk[kPass];
 #pragma unroll
-            for (int q = 0; q < kPass; ++q) {
-              const int r = rb + q * rstep;
-              tk[q] = r < 128 ? s_tok[r] : -1;
-              if (tk[q] >= 0) xr[q] = *reinterpret_cast<const float4*>(a.x + static_cast<size_t>(tk[q]) * C + ch * 4);
-            }
-#pragma unroll
-            for (int q = 0; q < kPass; ++q) {
-              const int r = rb + q * rstep;
-              if (tk[q] < 0) continue;
-              const uint32_t src = sA + static_cast<uint32_t>(r) * C * 4 + ((ch ^ (r & 7)) << 4);
-              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sv[q].x), "=f"(sv[q].y), "=f"(sv[q].z), "=f"(sv[q].w) : "r"(src));
-              *reinterpret_cast<float4*>(a.x + static_cast<size_t>(tk[q]) * C + ch * 4) =
-                  make_float4(xr[q].x + sv[q].x, xr[q].y + sv[q].y, xr[q].z + sv[q].z, xr[q].w + sv[q].w);
-            }
-          }
+        for (int q = 0; q < kRows; ++q) {
+          if (tk[q] < 0) continue;
+          const int r = er0 + q * erstep;
+          float4 sv;
+          const uint32_t src = sA + static_cast<uint32_t>(r) * C * 4 + ((ech ^ (r & 7)) << 4);
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sv.x), "=f"(sv.y), "=f"(sv.z), "=f"(sv.w) : "r"(src));
+          *reinterpret_cast<float4*>(a.x + static_cast<size_t>(tk[q]) * C + ech * 4) =
+              make_float4(xr[q].x + sv.x, xr[q].y + sv.y, xr[q].z + sv.z, xr[q].w + sv.w);
         }
         named_bar_sync(3, NW);                                    // the staging tile is the next tile's A operand / V
       } else {

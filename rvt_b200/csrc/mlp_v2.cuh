@@ -188,6 +188,19 @@ mlp_v2_kernel(const __grid_constant__ MlpV2Args a, const __grid_constant__ CUten
       if (C % 32 == 0) {
         // coalesced version (see attn_v2.cuh): (acc + b2) * gamma -> swizzled fp32 staging tile in the (now idle) fc2 operand
         // region, then (row, 16-byte chunk) threads read x / write x as whole 128-byte lines
+        // residual prefetch in the coalesced (row, chunk) mapping BEFORE the accumulator wait (its latency hides behind fc2)
+        const int nch = C >> 2;
+        const int ech = tid % nch, er0 = tid / nch, erstep = kMv2Workers / nch;
+        constexpr int kRows = 4;                                  // 128 rows * nch chunks / 512 threads: 4 (C = 64), 2 (C = 32)
+        const int nrows = 128 / erstep;
+        float4 xr[kRows];
+        bool ok[kRows];
+#pragma unroll
+        for (int q = 0; q < kRows; ++q) {
+          const int r = er0 + q * erstep;
+          ok[q] = q < nrows && tile * 128 + r < a.n_tokens;
+          if (ok[q]) xr[q] = *reinterpret_cast<const float4*>(a.x + static_cast<size_t>(tile * 128 + r) * C + ech * 4);
+        }
         mbar_wait(out_full, par);
         RVT_TRACE(a, it, 4);
         tc_fence_after();
@@ -211,30 +224,15 @@ mlp_v2_kernel(const __grid_constant__ MlpV2Args a, const __grid_constant__ CUten
         tc_fence_before();
         mbar_arrive(out_free);                                    // the out accumulator is drained (fc2 of the next tile may start)
         named_bar_sync(2, kMv2Workers);
-        {
-          const int nch = C >> 2;
-          const int ch = tid % nch, r0 = tid / nch, rstep = kMv2Workers / nch;
-          constexpr int kPass = 4;
-          for (int rb = r0; rb < 128; rb += rstep * kPass) {
-            float4 xr[kPass];
-            bool ok[kPass];
 #pragma unroll
-            for (int q = 0; q < kPass; ++q) {
-              const int r = rb + q * rstep;
-              ok[q] = r < 128 && tile * 128 + r < a.n_tokens;
-              if (ok[q]) xr[q] = *reinterpret_cast<const float4*>(a.x + static_cast<size_t>(tile * 128 + r) * C + ch * 4);
-            }
-#pragma unroll
-            for (int q = 0; q < kPass; ++q) {
-              const int r = rb + q * rstep;
-              if (!ok[q]) continue;
-              float4 sv;
-              const uint32_t src = sH + static_cast<uint32_t>(r) * C * 4 + ((ch ^ (r & 7)) << 4);
-              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sv.x), "=f"(sv.y), "=f"(sv.z), "=f"(sv.w) : "r"(src));
-              *reinterpret_cast<float4*>(a.x + static_cast<size_t>(tile * 128 + r) * C + ch * 4) =
-                  make_float4(xr[q].x + sv.x, xr[q].y + sv.y, xr[q].z + sv.z, xr[q].w + sv.w);
-            }
-          }
+        for (int q = 0; q < kRows; ++q) {
+          if (!ok[q]) continue;
+          const int r = er0 + q * erstep;
+          float4 sv;
+          const uint32_t src = sH + static_cast<uint32_t>(r) * C * 4 + ((ech ^ (r & 7)) << 4);
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sv.x), "=f"(sv.y), "=f"(sv.z), "=f"(sv.w) : "r"(src));
+          *reinterpret_cast<float4*>(a.x + static_cast<size_t>(tile * 128 + r) * C + ech * 4) =
+              make_float4(xr[q].x + sv.x, xr[q].y + sv.y, xr[q].z + sv.z, xr[q].w + sv.w);
         }
         named_bar_sync(3, kMv2Workers);                           // the staging tile is the next tile's fc2 operand
         RVT_TRACE(a, it, 5);
