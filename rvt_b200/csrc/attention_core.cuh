@@ -44,7 +44,9 @@ __global__ void __launch_bounds__(128) attention_core_kernel(const __grid_consta
 
   // zero V^T (rows d in [dh, dhp) and unused key columns must be exact zeros)
   for (int i = t; i < 16384 / 16; i += 128) st_smem_16B(sVt + i * 16, 0u, 0u, 0u, 0u);
+  pdl_trigger();
   __syncthreads();
+  pdl_wait();            // qkv is the previous kernel's output
 
   // ---- stage Q, K (row t) and V^T (column t) ----
   const __half* rowp = a.qkv + (static_cast<size_t>(mt) * 128 + t) * (3 * a.C) + h * 3 * dh;

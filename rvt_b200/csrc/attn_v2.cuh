@@ -189,10 +189,12 @@ attn_v2_kernel(const __grid_constant__ AttnV2Args a, const __grid_constant__ CUt
     const int py = p / a.map.pw, px = p - py * a.map.pw;
     s_lut[p] = a.map.mode == MAP_WINDOW ? py * a.map.W + px : py * a.map.ny * a.map.W + px * a.map.nx;
   }
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();            // x (TMA loads, residual reads) is the previous kernel's output; weights / bias vectors above are constants
 
   const int n_tiles = a.n_tiles;
   const int ks1 = C >> 4;                                // K steps of the C-wide contractions

@@ -45,6 +45,26 @@ cudaError_t ensure_smem_attr(DevOnce& once, F* fn, int bytes) {
   return cudaSuccess;
 }
 
+// Launch with (optional) programmatic dependent launch: the kernel may begin its prologue while the previous kernel of the
+// stream drains; it blocks in pdl_wait() (umma.cuh) before touching that kernel's output.  RVT_PDL=0 disables.
+int pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("RVT_PDL"); v = e ? atoi(e) : 0; }
+  return v;
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  if (pdl_enabled()) {
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- TMA tensor maps (driver entry point resolved at run time: no link-time libcuda dependency) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -101,8 +121,8 @@ int launch_gemm(GemmArgs a, int n_mtiles, int n_ntiles, cudaStream_t st, const C
   if (n_mtiles <= 0 || n_ntiles <= 0) return 0;
   alignas(64) CUtensorMap tm;
   if (tmap) tm = *tmap; else memset(&tm, 0, sizeof(tm));
-  gemm_fused_kernel<LOADER, EPI><<<dim3(n_mtiles, n_ntiles, a.kc_split > 0 ? cdiv(a.KC, a.kc_split) : 1), kGemmThreads, smem, st>>>(a, tm);
-  return static_cast<int>(cudaGetLastError());
+  return static_cast<int>(launch_pdl(gemm_fused_kernel<LOADER, EPI>, dim3(n_mtiles, n_ntiles, a.kc_split > 0 ? cdiv(a.KC, a.kc_split) : 1),
+                                     dim3(kGemmThreads), smem, st, a, tm));
 }
 
 // A = fp16 row-major scratch [a_rows, K]: TMA-fed mainloop when a tensor map can be built, else the
@@ -124,10 +144,8 @@ int launch_ln_rows(const float* x, const RowMap& map, int64_t n_rows, int C, int
                    long long split_stride = 0) {
   if (C % 128 != 0 || C > 512) return kErrUnsupported;
   if (n_rows <= 0) return 0;
-  ln_rows_kernel<OUT_F16><<<static_cast<unsigned>((n_rows + 7) / 8), 256, 0, st>>>(x, map, static_cast<int>(n_rows), C, do_ln, w,
-                                                                                  b, eps, out, mask, mask_token, n_splits,
-                                                                                  split_stride);
-  return static_cast<int>(cudaGetLastError());
+  return static_cast<int>(launch_pdl(ln_rows_kernel<OUT_F16>, dim3(static_cast<unsigned>((n_rows + 7) / 8)), dim3(256), 0, st, x, map,
+                                     static_cast<int>(n_rows), C, do_ln, w, b, eps, out, mask, mask_token, n_splits, split_stride));
 }
 
 // any C % 8 == 0 (training forward: the normalised fp16 operand is materialised once and kept for the backward)
@@ -209,8 +227,7 @@ int launch_attn_v2(const AttnV2Args& a, const CUtensorMap& tm, cudaStream_t st) 
   if (v2_cta_cap() > 0) grid = v2_cta_cap();
   if (grid > a.n_tiles) grid = a.n_tiles;
   if (grid <= 0) return 0;
-  attn_v2_kernel<NH, KC1><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(a, tm);
-  return static_cast<int>(cudaGetLastError());
+  return static_cast<int>(launch_pdl(attn_v2_kernel<NH, KC1>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM, st, a, tm));
 }
 
 // fp32 row-major [rows, cols] -> box of all `cols` columns x 128 rows, no swizzle (token tiles of the residual stream)
@@ -241,8 +258,7 @@ int launch_mlp_v2(const MlpV2Args& a, const CUtensorMap& tm, cudaStream_t st) {
   if (v2_cta_cap() > 0) grid = v2_cta_cap();
   if (grid > a.n_tiles) grid = a.n_tiles;
   if (grid <= 0) return 0;
-  mlp_v2_kernel<H2><<<grid, kMv2Threads, kMv2Smem, st>>>(a, tm);
-  return static_cast<int>(cudaGetLastError());
+  return static_cast<int>(launch_pdl(mlp_v2_kernel<H2>, dim3(grid), dim3(kMv2Threads), kMv2Smem, st, a, tm));
 }
 
 int lstm_v2_enabled() {
@@ -251,7 +267,7 @@ int lstm_v2_enabled() {
   return v;
 }
 
-int launch_lstm_v2(const LstmV2Args& a, const CUtensorMap& tx, const CUtensorMap& th, cudaStream_t st) {
+int launch_lstm_v2(const LstmV2Args& a, const CUtensorMap& tx, const CUtensorMap& th, const CUtensorMap& tc, cudaStream_t st) {
   static_assert(kLv2Smem <= kMaxSmem, "lstm_v2 shared memory");
   static DevOnce once;
   if (cudaError_t e = ensure_smem_attr(once, lstm_v2_kernel, static_cast<int>(kLv2Smem)); e != cudaSuccess) return static_cast<int>(e);
@@ -259,8 +275,7 @@ int launch_lstm_v2(const LstmV2Args& a, const CUtensorMap& tx, const CUtensorMap
   if (v2_cta_cap() > 0) grid = v2_cta_cap();
   if (grid > a.n_tiles) grid = a.n_tiles;
   if (grid <= 0) return 0;
-  lstm_v2_kernel<<<grid, kLv2Threads, kLv2Smem, st>>>(a, tx, th);
-  return static_cast<int>(cudaGetLastError());
+  return static_cast<int>(launch_pdl(lstm_v2_kernel, dim3(grid), dim3(kLv2Threads), kLv2Smem, st, a, tx, th, tc));
 }
 
 int attn_v2_enabled() {
@@ -571,8 +586,7 @@ static int partition_attention_impl(const float* x, float* x_out, int force_unfu
     at.ab_fmt = 0;
     static DevOnce once;
     if (cudaError_t e = ensure_smem_attr(once, attention_core_kernel, kAttnSmemBytes); e != cudaSuccess) return static_cast<int>(e);
-    attention_core_kernel<<<dim3(n_mtiles, at.nh), 128, kAttnSmemBytes, st>>>(at);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_pdl(attention_core_kernel, dim3(n_mtiles, at.nh), dim3(128), kAttnSmemBytes, st, at);
     if (e != cudaSuccess) return static_cast<int>(e);
   }
   // 3) x[token] += gamma1 * (proj(o) + b)  scattered back = partition reverse (maxvit.py:259-262,268,353)
@@ -728,23 +742,24 @@ static int dws_conv_lstm_impl(const float* x, const float* h_prev, const float* 
   const int n_mtiles = cdiv(n_tok, 128);
   if (lstm_v2_enabled() && dws_mode == 0 && dim <= 64 && cw == dim && !gates16 && n_mtiles > 0) {
     // persistent kernel, resident gate weight, TMA-staged x / h tiles, double-buffered accumulators (lstm_v2.cuh)
-    alignas(64) CUtensorMap tx, th;
-    if (make_tmap_f32_rows(x, n_tok, dim, &tx) && (!h_prev || make_tmap_f32_rows(h_prev, n_tok, dim, &th))) {
+    alignas(64) CUtensorMap tx, th, tc;
+    if (make_tmap_f32_rows(x, n_tok, dim, &tx) && (!h_prev || make_tmap_f32_rows(h_prev, n_tok, dim, &th)) &&
+        (!c_prev || dim % 32 != 0 || make_tmap_f32_rows(c_prev, n_tok, dim, &tc, 32))) {
       if (!h_prev) th = tx;
+      if (!c_prev || dim % 32 != 0) tc = tx;
       LstmV2Args la{};
       la.cprev = c_prev; la.hout = h_out; la.cout = c_out; la.hout16 = static_cast<__half*>(h_out_f16);
       la.n_tokens = static_cast<int>(n_tok); la.C = dim; la.n_tiles = n_mtiles; la.has_h = h_prev != nullptr;
       la.w = static_cast<const __half*>(w_packed); la.bias = bias_tiled;
-      return launch_lstm_v2(la, tx, th, st);
+      return launch_lstm_v2(la, tx, th, tc, st);
     }
   }
   if (dws_mode == 0 && dim >= kWideDim && scratch_xh != nullptr) {
     // wide stage, plain 1x1 cell: cast [x|h] once, then a TMA-fed mainloop (no per-N-tile A rebuild)
     const int n_rows = n_mtiles * 128;
     const int64_t items = static_cast<int64_t>(n_rows) * (2 * dim / 8);
-    cast_xh_kernel<<<static_cast<unsigned>((items + 255) / 256), 256, 0, st>>>(x, h_prev, static_cast<int>(n_tok), n_rows, dim,
-                                                                             static_cast<__half*>(scratch_xh));
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_pdl(cast_xh_kernel, dim3(static_cast<unsigned>((items + 255) / 256)), dim3(256), 0, st, x, h_prev,
+                               static_cast<int>(n_tok), n_rows, dim, static_cast<__half*>(scratch_xh));
     if (e != cudaSuccess) return static_cast<int>(e);
     a.a16 = static_cast<const __half*>(scratch_xh); a.lda = 2 * dim; a.a_rows = n_rows;
     return launch_gemm_f16<EP_LSTM>(a, n_mtiles, dim / cw, st);

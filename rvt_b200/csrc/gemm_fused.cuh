@@ -261,10 +261,12 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_fused_kernel(const __gri
     fence_mbar_init();
   }
   if (warp == 8) tmem_alloc(tmem_slot, a.tmem_cols);
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();            // everything below may read what the previous kernel in the stream wrote
 
   if (warp < 8) {
    if (LOADER != LD_TMA) {
@@ -859,6 +861,8 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* x, RowMap map
                                                       long long split_stride = 0) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_trigger();
+  pdl_wait();
   if (row >= n_rows) return;
   const int tok = row_to_token(map, row);
   const int ng = C >> 7;                       // float4 groups per lane (<= 4)
@@ -935,6 +939,8 @@ __global__ void __launch_bounds__(256) cast_xh_kernel(const float* __restrict__ 
                                                       int n_rows, int C, __half* __restrict__ out) {
   const int per_row = (2 * C) >> 3;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
   if (idx >= static_cast<int64_t>(n_rows) * per_row) return;
   const int row = static_cast<int>(idx / per_row), k0 = static_cast<int>(idx - static_cast<int64_t>(row) * per_row) * 8;
   float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};

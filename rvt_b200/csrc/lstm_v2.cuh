@@ -29,11 +29,12 @@ struct LstmV2Args {
 constexpr int kLv2Workers = 512;
 constexpr int kLv2Threads = kLv2Workers + 64;
 constexpr uint32_t kLv2XBuf = 128 * 64 * 4;
-constexpr uint32_t kLv2Smem = 1024 + 2 * kLv2XBuf /*x, h*/ + 2 * 2 * kAv2Tile /*A double buffered, 2 atoms*/ + 2 * 256 * 128 /*W*/ +
+constexpr uint32_t kLv2Smem = 1024 + 3 * kLv2XBuf /*x, h, c_prev*/ + 2 * 2 * kAv2Tile /*A double buffered, 2 atoms*/ + 2 * 256 * 128 /*W*/ +
                               256 * 4 + 16 * 8 + 16;
 
 __global__ void __launch_bounds__(kLv2Threads, 1)
-lstm_v2_kernel(const __grid_constant__ LstmV2Args a, const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_h) {
+lstm_v2_kernel(const __grid_constant__ LstmV2Args a, const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_h,
+               const __grid_constant__ CUtensorMap tmap_c) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -43,7 +44,8 @@ lstm_v2_kernel(const __grid_constant__ LstmV2Args a, const __grid_constant__ CUt
   const int C = a.C, N4 = 4 * C, K2 = 2 * C;
   const int kc_n = (K2 + 63) >> 6;                       // K atoms of [x | h]
   const uint32_t sX = base, sH = sX + kLv2XBuf;
-  const uint32_t sA = sH + kLv2XBuf;                     // 2 buffers x 2 atoms
+  const uint32_t sC = sH + kLv2XBuf;                     // c_prev tile: C/32 half tiles [128 rows x 32 fp32], 128-byte swizzle
+  const uint32_t sA = sC + kLv2XBuf;                     // 2 buffers x 2 atoms
   const uint32_t sW = sA + 4 * kAv2Tile;
   float* s_bias = reinterpret_cast<float*>(sm + (sW - base) + 2 * 256 * 128);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 256);
@@ -53,19 +55,24 @@ lstm_v2_kernel(const __grid_constant__ LstmV2Args a, const __grid_constant__ CUt
   uint64_t* acc_full = bars + 4;      // [2] commit
   uint64_t* acc_free = bars + 6;      // [2] 512
   uint64_t* w_full = bars + 8;        // tx
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* c_full = bars + 9;        // tx
+  uint64_t* c_free = bars + 10;       // 512
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   if (tid == 0) {
     mbar_init(xh_full, 1); mbar_init(xh_free, kLv2Workers); mbar_init(w_full, 1);
+    mbar_init(c_full, 1); mbar_init(c_free, kLv2Workers);
     for (int b = 0; b < 2; ++b) { mbar_init(&a_full[b], kLv2Workers); mbar_init(&acc_full[b], 1); mbar_init(&acc_free[b], kLv2Workers); }
     fence_mbar_init();
   }
   if (warp == 16) tmem_alloc(tmem_slot, 512);
   for (int i = tid; i < 256; i += kLv2Threads) s_bias[i] = i < N4 ? a.bias[i] : 0.f;
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();
   const int n_tiles = a.n_tiles;
 
   if (warp < 16) {
@@ -102,20 +109,47 @@ lstm_v2_kernel(const __grid_constant__ LstmV2Args a, const __grid_constant__ CUt
       const int b = it & 1;
       if (tile + static_cast<int>(gridDim.x) < n_tiles) build_a(it + 1);
       // ---------------- epilogue(it) ----------------
+      // Row-per-thread global accesses touch 32 different 128-byte lines per instruction (measured: the dominant cost of the
+      // first version), so c_prev comes in through TMA (swizzled half tiles) and c_t / h_t go out through a swizzled fp32
+      // staging tile -- the A-operand buffer of THIS tile, idle since its MMA finished -- from which (row, 16-byte chunk)
+      // threads write whole lines.
+      const bool coalesced = (C % 32 == 0);
       const int tok = tile * 128 + row;
       const bool live = tok < a.n_tokens;
       const size_t rbase = static_cast<size_t>(live ? tok : 0) * C;
       float cp[2][8];
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
-        const int c8 = wg + 4 * q;
 #pragma unroll
         for (int e = 0; e < 8; ++e) cp[q][e] = 0.f;
-        if (live && a.cprev && c8 * 8 < C) load8(a.cprev + rbase + c8 * 8, cp[q]);
+      }
+      if (a.cprev) {
+        if (coalesced) {
+          mbar_wait(c_full, it & 1);
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int j0 = (wg + 4 * q) * 8;
+            if (j0 < C) {
+              const uint32_t half = sC + (j0 >> 5) * kAv2Tile;
+              const uint32_t s0 = half + sw128_offset(row, (j0 & 31) >> 2), s1 = half + sw128_offset(row, ((j0 & 31) >> 2) + 1);
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(cp[q][0]), "=f"(cp[q][1]), "=f"(cp[q][2]), "=f"(cp[q][3]) : "r"(s0));
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(cp[q][4]), "=f"(cp[q][5]), "=f"(cp[q][6]), "=f"(cp[q][7]) : "r"(s1));
+            }
+          }
+          mbar_arrive(c_free);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int c8 = wg + 4 * q;
+            if (live && c8 * 8 < C) load8(a.cprev + rbase + c8 * 8, cp[q]);
+          }
+        }
       }
       mbar_wait(&acc_full[b], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t tacc = tmem + lane_off + b * 256;
+      const uint32_t stage = sA + b * 2 * kAv2Tile;            // fp32 [128 x C] staging tile (C = 64: 32 KB = the A buffer)
+      float hn[2][8], cn[2][8];
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const int c8 = wg + 4 * q;
@@ -127,33 +161,65 @@ lstm_v2_kernel(const __grid_constant__ LstmV2Args a, const __grid_constant__ CUt
         tmem_ld_x8(tacc + 2 * C + j0, og);
         tmem_ld_x8(tacc + 3 * C + j0, g);
         tmem_ld_wait();
-        if (live) {
-          float bv[8];
-          lds8(s_bias + j0, bv);
+        float bv[8];
+        lds8(s_bias + j0, bv);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] += bv[e];
-          lds8(s_bias + C + j0, bv);
+        for (int e = 0; e < 8; ++e) f[e] += bv[e];
+        lds8(s_bias + C + j0, bv);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) ig[e] += bv[e];
-          lds8(s_bias + 2 * C + j0, bv);
+        for (int e = 0; e < 8; ++e) ig[e] += bv[e];
+        lds8(s_bias + 2 * C + j0, bv);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) og[e] += bv[e];
-          lds8(s_bias + 3 * C + j0, bv);
+        for (int e = 0; e < 8; ++e) og[e] += bv[e];
+        lds8(s_bias + 3 * C + j0, bv);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) g[e] += bv[e];
-          float hn[8], cn[8];
+        for (int e = 0; e < 8; ++e) g[e] += bv[e];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            cn[e] = sigmoid_acc(f[e]) * cp[q][e] + sigmoid_acc(ig[e]) * tanh_acc(g[e]);
-            hn[e] = sigmoid_acc(og[e]) * tanh_acc(cn[e]);
-          }
-          *reinterpret_cast<float4*>(a.cout + rbase + j0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-          *reinterpret_cast<float4*>(a.cout + rbase + j0 + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
-          *reinterpret_cast<float4*>(a.hout + rbase + j0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-          *reinterpret_cast<float4*>(a.hout + rbase + j0 + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+        for (int e = 0; e < 8; ++e) {
+          cn[q][e] = sigmoid_acc(f[e]) * cp[q][e] + sigmoid_acc(ig[e]) * tanh_acc(g[e]);
+          hn[q][e] = sigmoid_acc(og[e]) * tanh_acc(cn[q][e]);
+        }
+        if (!coalesced && live) {
+          *reinterpret_cast<float4*>(a.cout + rbase + j0) = make_float4(cn[q][0], cn[q][1], cn[q][2], cn[q][3]);
+          *reinterpret_cast<float4*>(a.cout + rbase + j0 + 4) = make_float4(cn[q][4], cn[q][5], cn[q][6], cn[q][7]);
+          *reinterpret_cast<float4*>(a.hout + rbase + j0) = make_float4(hn[q][0], hn[q][1], hn[q][2], hn[q][3]);
+          *reinterpret_cast<float4*>(a.hout + rbase + j0 + 4) = make_float4(hn[q][4], hn[q][5], hn[q][6], hn[q][7]);
           if (a.hout16)
-            *reinterpret_cast<uint4*>(a.hout16 + rbase + j0) =
-                make_uint4(pack_h2(hn[0], hn[1]), pack_h2(hn[2], hn[3]), pack_h2(hn[4], hn[5]), pack_h2(hn[6], hn[7]));
+            *reinterpret_cast<uint4*>(a.hout16 + rbase + j0) = make_uint4(pack_h2(hn[q][0], hn[q][1]), pack_h2(hn[q][2], hn[q][3]),
+                                                                           pack_h2(hn[q][4], hn[q][5]), pack_h2(hn[q][6], hn[q][7]));
+        }
+      }
+      if (coalesced) {
+        const int nch = C >> 2;
+        const int ech = tid % nch, er0 = tid / nch, erstep = kLv2Workers / nch, nrows = 128 / erstep;
+        const uint32_t srow = stage + static_cast<uint32_t>(row) * C * 4;
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {                  // pass 0: c_t, pass 1: h_t (+ its fp16 copy)
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int ch = (wg + 4 * q) * 2;
+            if (ch * 4 >= C) break;
+            const float* v = pass == 0 ? cn[q] : hn[q];
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((ch ^ (row & 7)) << 4)), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (((ch + 1) ^ (row & 7)) << 4)), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+          }
+          named_bar_sync(1, kLv2Workers);
+          for (int q = 0; q < nrows; ++q) {
+            const int r = er0 + q * erstep;
+            const int t = tile * 128 + r;
+            if (t >= a.n_tokens) continue;
+            float4 sv;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sv.x), "=f"(sv.y), "=f"(sv.z), "=f"(sv.w)
+                         : "r"(stage + static_cast<uint32_t>(r) * C * 4 + ((ech ^ (r & 7)) << 4)));
+            const size_t off = static_cast<size_t>(t) * C + ech * 4;
+            if (pass == 0) {
+              *reinterpret_cast<float4*>(a.cout + off) = sv;
+            } else {
+              *reinterpret_cast<float4*>(a.hout + off) = sv;
+              if (a.hout16) *reinterpret_cast<uint2*>(a.hout16 + off) = make_uint2(pack_h2(sv.x, sv.y), pack_h2(sv.z, sv.w));
+            }
+          }
+          named_bar_sync(2, kLv2Workers);                       // staging reused by the next pass / as the A operand of tile it+2
         }
       }
       tc_fence_before();
@@ -196,6 +262,11 @@ lstm_v2_kernel(const __grid_constant__ LstmV2Args a, const __grid_constant__ CUt
         mbar_arrive_expect_tx(xh_full, a.has_h ? 2 * t_bytes : t_bytes);
         tma_load_2d(sX, &tmap_x, 0, tile * 128, xh_full);
         if (a.has_h) tma_load_2d(sH, &tmap_h, 0, tile * 128, xh_full);
+        if (a.cprev && C % 32 == 0) {                           // c_prev as 32-channel swizzled half tiles (row-per-thread reads)
+          if (it > 0) mbar_wait(c_free, (it - 1) & 1);
+          mbar_arrive_expect_tx(c_full, t_bytes);
+          for (int j = 0; 32 * j < C; ++j) tma_load_2d(sC + j * kAv2Tile, &tmap_c, 32 * j, tile * 128, c_full);
+        }
       }
     }
     __syncwarp();

@@ -86,10 +86,12 @@ mlp_v2_kernel(const __grid_constant__ MlpV2Args a, const __grid_constant__ CUten
     s_lnw[i] = in ? a.ln_w[i] : 1.f;
     s_lnb[i] = in ? a.ln_b[i] : 0.f;
   }
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();
   const uint32_t t_hid = tmem, t_out = tmem + 256;
   const int n_tiles = a.n_tiles;
   const int ks1 = C >> 4;

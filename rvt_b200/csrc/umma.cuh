@@ -213,6 +213,16 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 
 // ----------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// (barrier init, TMEM allocation, descriptor prefetch, staging of constant vectors) while its predecessor in the stream is
+// still draining; `pdl_wait` blocks until the predecessor has COMPLETED and its memory is visible, so every access to data
+// the predecessor produced must come after it.  `pdl_trigger` lets the successor begin launching (it still waits in its own
+// pdl_wait for our completion).  Both are no-ops without the launch attribute.
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------
 // small helpers
 // ----------------------------------------------------------------------------------------
 __device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP, ~1 ulp
