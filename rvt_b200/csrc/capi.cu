@@ -278,6 +278,18 @@ int launch_lstm_v2(const LstmV2Args& a, const CUtensorMap& tx, const CUtensorMap
   return static_cast<int>(launch_pdl(lstm_v2_kernel, dim3(grid), dim3(kLv2Threads), kLv2Smem, st, a, tx, th, tc));
 }
 
+template <bool H2>
+int launch_mlp_v2x(const MlpV2xArgs& a, const CUtensorMap& tm, cudaStream_t st) {
+  static_assert(kMx2Smem <= kMaxSmem, "mlp_v2x shared memory");
+  static DevOnce once;
+  if (cudaError_t e = ensure_smem_attr(once, mlp_v2x_kernel<H2>, static_cast<int>(kMx2Smem)); e != cudaSuccess) return static_cast<int>(e);
+  int grid = persistent_sms();
+  if (v2_cta_cap() > 0) grid = v2_cta_cap();
+  if (grid > a.n_tiles) grid = a.n_tiles;
+  if (grid <= 0) return 0;
+  return static_cast<int>(launch_pdl(mlp_v2x_kernel<H2>, dim3(grid), dim3(kMv2Threads), kMx2Smem, st, a, tm));
+}
+
 int attn_v2_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("RVT_ATTN_V2"); v = e ? atoi(e) : 1; }
@@ -638,6 +650,17 @@ static int mlp_block_impl(const float* x, float* x_out, int force_unfused, void*
     ma.w2p = static_cast<const __half*>(w2_packed); ma.b2 = b2; ma.gamma = gamma2;
     if (!b1 || !b2) return kErrUnsupported;
     ma.gelu_f16x2 = rvt_gelu_f16x2();
+    if (mlp_v2_enabled() >= 2 && dim == 128 && hidden % 64 == 0 && hidden <= 512 && n_mtiles > 0) {
+      // C = 128: streamed weights, hidden in passes of 256 columns (mlp_v2x_kernel); RVT_MLP_V2=2 until validated on hardware
+      alignas(64) CUtensorMap tm;
+      if (make_tmap_f32_rows(x_out, n_tokens, dim, &tm, 32)) {
+        MlpV2xArgs va{};
+        va.x = x_out; va.n_tokens = static_cast<int>(n_tokens); va.C = dim; va.hidden = hidden; va.n_tiles = n_mtiles;
+        va.ln_w = n2_w; va.ln_b = n2_b; va.eps = eps; va.w1p = ma.w1p; va.b1 = b1; va.w2p = ma.w2p; va.b2 = b2; va.gamma = gamma2;
+        va.trace = g_v2_trace;
+        return ma.gelu_f16x2 ? launch_mlp_v2x<true>(va, tm, st) : launch_mlp_v2x<false>(va, tm, st);
+      }
+    }
     if (mlp_v2_enabled() && dim <= 64 && hidden <= 256 && n_mtiles > 0) {
       // persistent kernel, resident weights, TMA-staged token tiles (mlp_v2.cuh)
       alignas(64) CUtensorMap tm;
