@@ -57,7 +57,10 @@ template <int NH, int KC1>
 struct AttnV2Cfg {
   static constexpr int NW = NH * 128;                       // worker threads
   static constexpr int NA = NH >= 2 ? NH / 2 : 1;           // 64-column atoms holding all heads' padded head dims
-  static constexpr int THREADS = NW + 96;                   // + MMA warp, x-producer warp, w-producer warp
+  static constexpr int THREADS = NW + 128;                  // + one auxiliary warpgroup: MMA warp, x-producer warp, w-producer warp, spare
+  // NH = 2 runs two CTAs per SM: 384 threads x 80 registers at launch; the auxiliary warpgroup then hands registers to the
+  // workers (setmaxnreg; the pool is per CTA): workers 96, auxiliary 48 -> 2 x 128 x 96 + 128 x 48 = the same 30720 per CTA
+  static constexpr bool REBALANCE_REGS = NH == 2;
   static constexpr uint32_t R1 = (32768u * KC1 > 2u * NA * kAv2Tile) ? 32768u * KC1 : 2u * NA * kAv2Tile;
   static constexpr uint32_t R2 = KC1 * kAv2Tile;
   static constexpr uint32_t R3 = NA * kAv2Tile;
@@ -201,6 +204,7 @@ attn_v2_kernel(const __grid_constant__ AttnV2Args a, const __grid_constant__ CUt
 
   if (warp < NH * 4) {
     // =============================================== workers ===============================================
+    if (Cfg::REBALANCE_REGS) asm volatile("setmaxnreg.inc.sync.aligned.u32 96;" ::: "memory");
     const int h = warp >> 2;                             // this warpgroup's head
     const int row = (warp & 3) * 32 + lane;              // tile row == TMEM lane
     const int grp = row >> 6, pos = row & 63;
@@ -373,7 +377,7 @@ attn_v2_kernel(const __grid_constant__ AttnV2Args a, const __grid_constant__ CUt
       RVT_TRACE(a, it, 8);
 
       // ---------------- proj epilogue: + bias, * gamma, + residual, scatter (= partition reverse) ----------------
-      if (C % 32 == 0) {
+      if ((C & (C - 1)) == 0 && C >= 32) {
         // Coalesced version.  A thread owns a ROW of the accumulator (TMEM lane), but row-per-thread global accesses touch 32
         // different 128-byte lines per instruction (the first profile's top cost: 3.5 us per tile).  So: (1) acc + bias, * gamma
         // -> fp32 staging tile in shared memory (the A/O and V regions, dead by now; 16-byte chunks XOR-swizzled with row & 7),
@@ -382,9 +386,9 @@ attn_v2_kernel(const __grid_constant__ AttnV2Args a, const __grid_constant__ CUt
         // residual prefetch in the coalesced (row, chunk) mapping, issued BEFORE the accumulator wait: the L2 latency of these
         // loads hides behind the proj MMA (s_tok was published by the row threads at the top of the tile; the qk_ready / s_full
         // hand-offs in between order those writes before these reads)
-        const int nch = C >> 2;                                   // 16-byte chunks per row
-        const int ech = tid % nch, er0 = tid / nch, erstep = NW / nch;
-        constexpr int kRows = 8;                                  // 128 rows * nch chunks / NW threads
+        const int nch = C >> 2;                                   // 16-byte chunks per row (power of two)
+        const int ech = tid % nch, er0 = tid / nch, erstep = NW / nch;          // 128 rows * nch chunks / NW threads = 8 rows each
+        constexpr int kRows = 8;
         float4 xr[kRows];
         int tk[kRows];
 #pragma unroll
@@ -454,7 +458,9 @@ attn_v2_kernel(const __grid_constant__ AttnV2Args a, const __grid_constant__ CUt
       }
       RVT_TRACE(a, it, 10);
     }
-  } else if (warp == NH * 4) {
+  } else {
+   if (Cfg::REBALANCE_REGS) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;" ::: "memory");
+   if (warp == NH * 4) {
     // =============================================== MMA issuer ===============================================
     if (lane == 0) {
       const uint32_t id_qkv = umma_idesc_f16(128, 96, 0);
@@ -558,7 +564,7 @@ attn_v2_kernel(const __grid_constant__ AttnV2Args a, const __grid_constant__ CUt
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp == NH * 4 + 2) {
     // =============================================== weight producer ===============================================
     if (lane == 0) {
       const uint32_t wq_bytes = static_cast<uint32_t>(KC1) * 96 * 128, wp_bytes = static_cast<uint32_t>(C) * 128;
@@ -586,6 +592,7 @@ attn_v2_kernel(const __grid_constant__ AttnV2Args a, const __grid_constant__ CUt
       }
     }
     __syncwarp();
+  }
   }
 
   tc_fence_before();

@@ -767,9 +767,9 @@ static int dws_conv_lstm_impl(const float* x, const float* h_prev, const float* 
     // persistent kernel, resident gate weight, TMA-staged x / h tiles, double-buffered accumulators (lstm_v2.cuh)
     alignas(64) CUtensorMap tx, th, tc;
     if (make_tmap_f32_rows(x, n_tok, dim, &tx) && (!h_prev || make_tmap_f32_rows(h_prev, n_tok, dim, &th)) &&
-        (!c_prev || dim % 32 != 0 || make_tmap_f32_rows(c_prev, n_tok, dim, &tc, 32))) {
+        (!c_prev || (dim & (dim - 1)) != 0 || dim < 32 || make_tmap_f32_rows(c_prev, n_tok, dim, &tc, 32))) {
       if (!h_prev) th = tx;
-      if (!c_prev || dim % 32 != 0) tc = tx;
+      if (!c_prev || (dim & (dim - 1)) != 0 || dim < 32) tc = tx;
       LstmV2Args la{};
       la.cprev = c_prev; la.hout = h_out; la.cout = c_out; la.hout16 = static_cast<__half*>(h_out_f16);
       la.n_tokens = static_cast<int>(n_tok); la.C = dim; la.n_tiles = n_mtiles; la.has_h = h_prev != nullptr;

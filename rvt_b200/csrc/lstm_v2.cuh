@@ -113,7 +113,7 @@ lstm_v2_kernel(const __grid_constant__ LstmV2Args a, const __grid_constant__ CUt
       // first version), so c_prev comes in through TMA (swizzled half tiles) and c_t / h_t go out through a swizzled fp32
       // staging tile -- the A-operand buffer of THIS tile, idle since its MMA finished -- from which (row, 16-byte chunk)
       // threads write whole lines.
-      const bool coalesced = (C % 32 == 0);
+      const bool coalesced = (C & (C - 1)) == 0 && C >= 32;
       const int tok = tile * 128 + row;
       const bool live = tok < a.n_tokens;
       const size_t rbase = static_cast<size_t>(live ? tok : 0) * C;
@@ -262,7 +262,7 @@ lstm_v2_kernel(const __grid_constant__ LstmV2Args a, const __grid_constant__ CUt
         mbar_arrive_expect_tx(xh_full, a.has_h ? 2 * t_bytes : t_bytes);
         tma_load_2d(sX, &tmap_x, 0, tile * 128, xh_full);
         if (a.has_h) tma_load_2d(sH, &tmap_h, 0, tile * 128, xh_full);
-        if (a.cprev && C % 32 == 0) {                           // c_prev as 32-channel swizzled half tiles (row-per-thread reads)
+        if (a.cprev && (C & (C - 1)) == 0 && C >= 32) {          // c_prev as 32-channel swizzled half tiles (row-per-thread reads)
           if (it > 0) mbar_wait(c_free, (it - 1) & 1);
           mbar_arrive_expect_tx(c_full, t_bytes);
           for (int j = 0; 32 * j < C; ++j) tma_load_2d(sC + j * kAv2Tile, &tmap_c, 32 * j, tile * 128, c_full);

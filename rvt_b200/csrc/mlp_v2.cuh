@@ -187,7 +187,7 @@ mlp_v2_kernel(const __grid_constant__ MlpV2Args a, const __grid_constant__ CUten
       if (tile + static_cast<int>(gridDim.x) < n_tiles) layer_norm(it + 1);
       RVT_TRACE(a, it, 3);
       // ---------------- EPI(it): + b2, * gamma2, + residual -> x ----------------
-      if (C % 32 == 0) {
+      if ((C & (C - 1)) == 0 && C >= 32) {
         // coalesced version (see attn_v2.cuh): (acc + b2) * gamma -> swizzled fp32 staging tile in the (now idle) fc2 operand
         // region, then (row, 16-byte chunk) threads read x / write x as whole 128-byte lines
         // residual prefetch in the coalesced (row, chunk) mapping BEFORE the accumulator wait (its latency hides behind fc2)
