@@ -290,6 +290,12 @@ int launch_mlp_v2x(const MlpV2xArgs& a, const CUtensorMap& tm, cudaStream_t st) 
   return static_cast<int>(launch_pdl(mlp_v2x_kernel<H2>, dim3(grid), dim3(kMv2Threads), kMx2Smem, st, a, tm));
 }
 
+int wide_fuse_ln() {     // RVT_WIDE_FUSE_LN=1: wide stages (C >= 256) normalise / cast inside the GEMM's operand loader (one launch less per
+  static int v = -1;     // GEMM, LayerNorm recomputed by every N-tile CTA) instead of a separate ln_rows / cast_xh pass + TMA-fed mainloop
+  if (v < 0) { const char* e = getenv("RVT_WIDE_FUSE_LN"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
 int attn_v2_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("RVT_ATTN_V2"); v = e ? atoi(e) : 1; }
@@ -575,7 +581,7 @@ static int partition_attention_impl(const float* x, float* x_out, int force_unfu
     a.Wp = static_cast<const __half*>(wqkv_packed); a.bias = bqkv; a.map = m;
     a.o16 = static_cast<__half*>(scratch_qkv); a.ldo = 3 * dim; a.act = 0;
     int rc;
-    if (force_unfused || (dim >= kWideDim && dim % 128 == 0)) {
+    if (force_unfused || (dim >= kWideDim && dim % 128 == 0 && !wide_fuse_ln())) {
       if (!scratch_xn) return kErrBadArg;
       rc = force_unfused ? launch_ln_rows_any_f16(x, m, rows, dim, n1_w != nullptr, n1_w, n1_b, eps, scratch_xn, st)
                          : launch_ln_rows<true>(x, m, rows, dim, n1_w != nullptr, n1_w, n1_b, eps, scratch_xn, nullptr, nullptr, st);
@@ -705,7 +711,7 @@ static int mlp_block_impl(const float* x, float* x_out, int force_unfused, void*
     a.act = (rvt_gelu_f16x2() && !force_unfused) ? 3 : 1;      // the training forward keeps the exact GELU its backward differentiates
     a.o16_pre = static_cast<__half*>(pre_out);
     int rc;
-    if (force_unfused || (dim >= kWideDim && dim % 128 == 0)) {
+    if (force_unfused || (dim >= kWideDim && dim % 128 == 0 && !wide_fuse_ln())) {
       if (!scratch_xn) return kErrBadArg;
       rc = force_unfused ? launch_ln_rows_any_f16(x, m, static_cast<int64_t>(n_mtiles) * 128, dim, 1, n2_w, n2_b, eps, scratch_xn, st)
                          : launch_ln_rows<true>(x, m, static_cast<int64_t>(n_mtiles) * 128, dim, 1, n2_w, n2_b, eps, scratch_xn, nullptr,
@@ -777,7 +783,7 @@ static int dws_conv_lstm_impl(const float* x, const float* h_prev, const float* 
       return launch_lstm_v2(la, tx, th, tc, st);
     }
   }
-  if (dws_mode == 0 && dim >= kWideDim && scratch_xh != nullptr) {
+  if (dws_mode == 0 && dim >= kWideDim && scratch_xh != nullptr && !wide_fuse_ln()) {
     // wide stage, plain 1x1 cell: cast [x|h] once, then a TMA-fed mainloop (no per-N-tile A rebuild)
     const int n_rows = n_mtiles * 128;
     const int64_t items = static_cast<int64_t>(n_rows) * (2 * dim / 8);
