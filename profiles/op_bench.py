@@ -59,6 +59,13 @@ def main():
         print(f'{name:5s} S{s + 1}: {us:8.1f} us  {flops / 1e9:7.2f} GFLOP {flops / us / 1e6:7.1f} TF/s   '
               f'{bytes_ / 1e6:7.1f} MB {bytes_ / us / 1e3:7.0f} GB/s')
 
+    def split_ws(s, n, c, cin, d):     # the K-split workspace RNNDetector hands to the wide-stage convs
+        if s == 0 or c < 256:
+            return None
+        from rvt_b200 import _lib
+        k = _lib.lib().rvt_conv_split_k(n, c, cin * d.kernel_size ** 2)
+        return torch.empty(k * n * c, dtype=torch.float32, device=dev) if k > 1 else None
+
     with torch.inference_mode():
         h, w = H0, W0
         cin = 20
@@ -69,14 +76,14 @@ def main():
             ho, wo = h // f, w // f
             n = B * ho * wo
             if s == 0:
-                src, nchw, cw = x8, True, pk['conv_w_s2d']
-                s2d = torch.empty(x8.numel(), dtype=torch.float16, device=dev)
+                # the product path for uint8 events: smem-staged patch loader (stem_mode 2), no scratch tensor
+                src, nchw, cw, s2d = x8, True, pk['conv_w_u8'], None
                 in_bytes = x8.numel()
             else:
                 src, nchw, cw, s2d = torch.randn(B, h, w, cin, device=dev), False, pk['conv_w'], None
                 in_bytes = src.numel() * 4
             timeit('conv', s, lambda: ops.downsample_cf2cl(src, nchw, cw, c, d.kernel_size, f, d.padding, pk['ds_ln_w'],
-                                                           pk['ds_ln_b'], s2d_scratch=s2d),
+                                                           pk['ds_ln_b'], s2d_scratch=s2d, stem_mode=2 if s == 0 else 0, split_ws=split_ws(s, n, c, cin, d)),
                    2 * n * c * cin * d.kernel_size ** 2, in_bytes + n * c * 4)
             xs = torch.randn(B, ho, wo, c, device=dev)
             blk = pk['blocks'][1]

@@ -14,6 +14,7 @@
 #include "attn_v2.cuh"
 #include "mlp_v2.cuh"
 #include "lstm_v2.cuh"
+#include "stem_v2.cuh"
 #include "voxel.cuh"
 #include "neighbours.cuh"
 #include "det.cuh"
@@ -245,7 +246,7 @@ bool make_tmap_f32_rows(const float* base, int64_t rows, int cols, CUtensorMap* 
 
 int mlp_v2_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("RVT_MLP_V2"); v = e ? atoi(e) : 1; }
+  if (v < 0) { const char* e = getenv("RVT_MLP_V2"); v = e ? atoi(e) : 2; }     // 1: C <= 64 only, 2: + the streamed C = 128 variant
   return v;
 }
 
@@ -288,6 +289,36 @@ int launch_mlp_v2x(const MlpV2xArgs& a, const CUtensorMap& tm, cudaStream_t st) 
   if (grid > a.n_tiles) grid = a.n_tiles;
   if (grid <= 0) return 0;
   return static_cast<int>(launch_pdl(mlp_v2x_kernel<H2>, dim3(grid), dim3(kMv2Threads), kMx2Smem, st, a, tm));
+}
+
+// uint8 NCHW events [B, Cin, Hin, Win] as a 3-D tensor (Win, Hin, B*Cin); box = the [Cin x 35 x 80] input patch of one
+// 8 x 16-token stem tile (stem_v2.cuh).  Out-of-image parts of a box are zero-filled.
+bool make_tmap_stem_u8(const void* in, int batch, int cin, int hin, int win, CUtensorMap* out) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn || (reinterpret_cast<uintptr_t>(in) & 15) || win % 16 != 0 || cin > 256) return false;
+  const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(win), static_cast<cuuint64_t>(hin), static_cast<cuuint64_t>(batch) * cin};
+  const cuuint64_t gstride[2] = {static_cast<cuuint64_t>(win), static_cast<cuuint64_t>(win) * hin};
+  const cuuint32_t box[3] = {static_cast<cuuint32_t>(kStemPatchPitch), static_cast<cuuint32_t>(kStemPatchRows), static_cast<cuuint32_t>(cin)};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(in), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int stem_v2_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("RVT_STEM_V2"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
+int launch_stem_v2(const StemV2Args& a, const CUtensorMap& tm, cudaStream_t st) {
+  const size_t smem = stem_v2_smem_bytes(a.Cin, a.C);
+  if (smem > static_cast<size_t>(kMaxSmem)) return kErrUnsupported;
+  static DevOnce once;
+  if (cudaError_t e = ensure_smem_attr(once, stem_v2_kernel, kMaxSmem); e != cudaSuccess) return static_cast<int>(e);
+  int grid = persistent_sms();
+  if (grid > a.n_tiles) grid = a.n_tiles;
+  if (grid <= 0) return 0;
+  return static_cast<int>(launch_pdl(stem_v2_kernel, dim3(grid), dim3(kSv2Threads), smem, st, a, tm));
 }
 
 int wide_fuse_ln() {     // RVT_WIDE_FUSE_LN=1: wide stages (C >= 256) normalise / cast inside the GEMM's operand loader (one launch less per
@@ -451,6 +482,19 @@ static int downsample_impl(const void* in, int in_dtype, int in_nchw, int batch,
     a.K = 7 * cin * 8;
     a.yout = out; a.eln_w = ln_w; a.eln_b = ln_b; a.eeps = eps; a.token_mask = token_mask; a.mask_token = mask_token;
     a.raw_out = raw_out;
+    if (stem_v2_enabled() && !raw_out && ln_w && cout <= 64 && cin <= 256 &&
+        stem_v2_smem_bytes(cin, cout) <= static_cast<size_t>(kMaxSmem)) {
+      // persistent, pipelined version (inference; the training forward keeps the raw conv output and stays on the kernel above)
+      alignas(64) CUtensorMap tm;
+      if (make_tmap_stem_u8(in, batch, cin, hin, win, &tm)) {
+        StemV2Args sa{};
+        sa.wp = static_cast<const __half*>(w_packed); sa.y = out;
+        sa.Cin = cin; sa.Hout = hout; sa.Wout = wout; sa.C = cout; sa.KC = cdiv(a.K, 64);
+        sa.n_tiles = bm.n_groups; sa.ny = bm.ny; sa.nx = bm.nx;
+        sa.ln_w = ln_w; sa.ln_b = ln_b; sa.eps = eps; sa.token_mask = token_mask; sa.mask_token = mask_token;
+        return launch_stem_v2(sa, tm, st);
+      }
+    }
     return launch_gemm<LD_STEM, EP_LN>(a, bm.n_groups, 1, st, nullptr, stem_patch_bytes(cin) + 128);
   }
   if (s2d_scratch && in_nchw) {
@@ -657,7 +701,7 @@ static int mlp_block_impl(const float* x, float* x_out, int force_unfused, void*
     if (!b1 || !b2) return kErrUnsupported;
     ma.gelu_f16x2 = rvt_gelu_f16x2();
     if (mlp_v2_enabled() >= 2 && dim == 128 && hidden % 64 == 0 && hidden <= 512 && n_mtiles > 0) {
-      // C = 128: streamed weights, hidden in passes of 256 columns (mlp_v2x_kernel); RVT_MLP_V2=2 until validated on hardware
+      // C = 128: streamed weights, hidden in passes of 256 columns (mlp_v2x_kernel)
       alignas(64) CUtensorMap tm;
       if (make_tmap_f32_rows(x_out, n_tokens, dim, &tm, 32)) {
         MlpV2xArgs va{};

@@ -1,0 +1,268 @@
+// Stem of stage 1, persistent + pipelined version: ConvDownsampling_Cf2Cl with the 7x7 / stride-4 / pad-3 conv on uint8 NCHW
+// event histograms, LayerNorm over the C output channels and the optional mask token
+// (reference maxvit.py:161-178, maxvit_rnn.py:174-176).  Same arithmetic as gemm_fused<LD_STEM, EP_LN> (fp16 operands that are
+// exact for uint8 counts, fp32 accumulate, two-pass LayerNorm), different schedule: the one-tile-per-CTA version serialises
+// patch load -> 18 operand builds -> epilogue inside a CTA; here one CTA per SM keeps all three busy at once.
+//
+//   tile       8 x 16 output tokens of one sample = 128 accumulator rows; K = (ky, ci, kx8) = 7 * Cin * 8 in chunks of 64
+//   producer   one thread: the [Cin x 35 x 80] uint8 input patch of tile i+1 by ONE 3-D TMA box (out-of-image rows / columns and
+//              the rows of a zero-padded model resolution are zero-filled by the TMA unit) into the other half of a double
+//              buffer; the packed weight chunk of every K step by a bulk copy (the weights stay in L2)
+//   builders   8 warps: patch bytes -> fp16 -> SW128 K-major A chunk (u8 -> fp16 exactly by byte permute, gemm_fused.cuh)
+//              into a 3-deep ring shared with the weight chunks
+//   MMA        one thread: 4 tcgen05.mma (128 x C x 16) per chunk into one of TWO accumulators (TMEM columns [64 b, 64 b + C))
+//   epilogue   4 warps, thread = token = TMEM lane: the whole row in registers -> LayerNorm -> padded fp32 staging tile ->
+//              (token, 16-byte chunk) coalesced stores; runs on tile i while the builders are already on tile i+1
+#pragma once
+#include "attn_v2.cuh"
+
+namespace rvt {
+
+struct StemV2Args {
+  const __half* wp;         // pack_stem_weight_u8: [KC][C x 64] SW128 K-major tiles
+  float* y;                 // [B, Hout, Wout, C]
+  int Cin, Hout, Wout, C, KC, n_tiles, ny, nx;
+  const float* ln_w; const float* ln_b; float eps;      // null: no affine / no LayerNorm is not supported (ln_w may be null)
+  const uint8_t* token_mask; const float* mask_token;
+};
+
+constexpr int kSv2Builders = 256;
+constexpr int kSv2Epi = 128;
+constexpr int kSv2Threads = kSv2Epi + kSv2Builders + 64;      // + producer warp + MMA warp
+constexpr int kSv2Stages = 3;
+constexpr uint32_t kSv2StageBytes = kATileBytes + 64 * 128;   // A chunk + weight chunk (C <= 64)
+__host__ __device__ inline uint32_t stem_v2_patch_bytes(int cin) {
+  return (static_cast<uint32_t>(cin) * kStemPatchRows * kStemPatchPitch + 1023u) & ~1023u;
+}
+__host__ __device__ inline uint32_t stem_v2_smem_bytes(int cin, int c) {
+  return 1024 + 2 * stem_v2_patch_bytes(cin) + kSv2Stages * kSv2StageBytes + 128 * (static_cast<uint32_t>(c) * 4 + 16) + 3 * 64 * 4 +
+         16 * 8 + 16;
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kSv2Threads, 1)
+stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUtensorMap tmap_in) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw_addr);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int C = a.C, Cin = a.Cin, KC = a.KC, n_tiles = a.n_tiles;
+  const uint32_t patch_bytes = stem_v2_patch_bytes(Cin);
+  const uint32_t sP = base;                                    // [2] patches
+  const uint32_t sS = sP + 2 * patch_bytes;                    // [3] stages: A chunk, then the weight chunk
+  const uint32_t sO = sS + kSv2Stages * kSv2StageBytes;        // fp32 staging tile, row pitch C * 4 + 16 bytes
+  const uint32_t o_pitch = static_cast<uint32_t>(C) * 4 + 16;
+  float* s_lnw = reinterpret_cast<float*>(sm + (sO - base) + 128 * o_pitch);
+  float* s_lnb = s_lnw + 64;
+  float* s_mask = s_lnb + 64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_mask + 64);
+  uint64_t* patch_full = bars + 0;     // [2] tx
+  uint64_t* patch_free = bars + 2;     // [2] 256
+  uint64_t* full = bars + 4;           // [3] 256 builders + 1 producer (tx)
+  uint64_t* empty = bars + 7;          // [3] commit
+  uint64_t* acc_full = bars + 10;      // [2] commit
+  uint64_t* acc_free = bars + 12;      // [2] 128
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  if (tid == 0) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&patch_full[b], 1); mbar_init(&patch_free[b], kSv2Builders);
+      mbar_init(&acc_full[b], 1); mbar_init(&acc_free[b], kSv2Epi);
+    }
+    for (int s = 0; s < kSv2Stages; ++s) { mbar_init(&full[s], kSv2Builders + 1); mbar_init(&empty[s], 1); }
+    fence_mbar_init();
+  }
+  if (warp == 13) tmem_alloc(tmem_slot, 128);
+  for (int i = tid; i < 64; i += kSv2Threads) {
+    const bool in = i < C;
+    s_lnw[i] = (in && a.ln_w) ? a.ln_w[i] : 1.f;
+    s_lnb[i] = (in && a.ln_b) ? a.ln_b[i] : 0.f;
+    s_mask[i] = (in && a.mask_token) ? a.mask_token[i] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int per_img = a.ny * a.nx;
+
+  if (warp < 4) {
+    // =============================================== epilogue ===============================================
+    const int row = tid;                                        // accumulator row == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const int nch = C >> 2;                                     // 16-byte chunks per token row
+    const float inv_c = 1.f / static_cast<float>(C);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int ab = it & 1;
+      const int tb = tile / per_img, tt = tile - tb * per_img;
+      const int ty = tt / a.nx, tx = tt - ty * a.nx;
+      const int tok0 = (tb * a.Hout + ty * kStemTileH) * a.Wout + tx * kStemTileW;      // token of row 0; row r: + (r>>4) * Wout + (r&15)
+      const int my_tok = tok0 + (row >> 4) * a.Wout + (row & 15);
+      const bool masked = a.token_mask && a.token_mask[my_tok];
+      mbar_wait(&acc_full[ab], (it >> 1) & 1);
+      tc_fence_after();
+      float v[64];
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 16)
+        if (c0 < C) tmem_ld_x16(tmem + lane_off + ab * 64 + c0, v + c0);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&acc_free[ab]);                               // the accumulator is drained: the MMAs of tile it + 2 may start
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) if (c < C) s += v[c];
+      const float mean = s * inv_c;
+      float ss = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) if (c < C) { const float d = v[c] - mean; ss += d * d; }
+      const float rstd = rsqrtf(ss * inv_c + a.eps);
+      const uint32_t srow = sO + static_cast<uint32_t>(row) * o_pitch;
+#pragma unroll
+      for (int c4 = 0; c4 < 16; ++c4) {
+        if (c4 * 4 >= C) break;
+        float4 o;
+        if (masked) {
+          o = *reinterpret_cast<const float4*>(s_mask + c4 * 4);
+        } else {
+          const float4 g = *reinterpret_cast<const float4*>(s_lnw + c4 * 4), bb = *reinterpret_cast<const float4*>(s_lnb + c4 * 4);
+          o.x = fmaf((v[c4 * 4 + 0] - mean) * rstd, g.x, bb.x);
+          o.y = fmaf((v[c4 * 4 + 1] - mean) * rstd, g.y, bb.y);
+          o.z = fmaf((v[c4 * 4 + 2] - mean) * rstd, g.z, bb.z);
+          o.w = fmaf((v[c4 * 4 + 3] - mean) * rstd, g.w, bb.w);
+        }
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow + c4 * 16), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+      }
+      named_bar_sync(1, kSv2Epi);
+      // (token, chunk) threads: consecutive threads write consecutive 16-byte chunks -> whole lines
+      for (int idx = tid; idx < 128 * nch; idx += kSv2Epi) {
+        const int r = idx / nch, ch = idx - r * nch;
+        float4 sv;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sv.x), "=f"(sv.y), "=f"(sv.z), "=f"(sv.w)
+                     : "r"(sO + static_cast<uint32_t>(r) * o_pitch + ch * 16));
+        const int tok = tok0 + (r >> 4) * a.Wout + (r & 15);
+        *reinterpret_cast<float4*>(a.y + static_cast<size_t>(tok) * C + ch * 4) = sv;
+      }
+      named_bar_sync(2, kSv2Epi);                               // the staging tile is free again
+    }
+  } else if (warp < 12) {
+    // =============================================== builders ===============================================
+    const int bt = tid - kSv2Epi;
+    const int j = bt & 7;                                       // 16-byte chunk of the 128-byte operand row = one (ky, ci) pair
+    const int r0 = bt >> 3;                                     // rows r0 + 32 i
+    const int npairs = 7 * Cin;
+    uint32_t src_off[4], dst_off[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + 32 * i;
+      src_off[i] = (r >> 4) * (4 * kStemPatchPitch) + (r & 15) * 4 + 12;
+      dst_off[i] = sw128_offset(r, j);
+    }
+    const __half2 k1024 = __half2half2(__ushort_as_half(static_cast<unsigned short>(0x6400)));
+    int it = 0;
+    uint32_t g = 0;                                             // running K-chunk counter (ring position)
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int b = it & 1;
+      mbar_wait(&patch_full[b], (it >> 1) & 1);
+      const uint32_t patch = sP + b * patch_bytes;
+      int q = j, ky = j / Cin, ci = j - ky * Cin;               // (ky, ci) pair of this thread's chunk in K chunk 0
+      for (int kc = 0; kc < KC; ++kc, ++g) {
+        const uint32_t s = g % kSv2Stages, ph = (g / kSv2Stages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        const uint32_t tile_a = sS + s * kSv2StageBytes;
+        const bool qv = q < npairs;
+        const uint32_t prow = patch + (ci * kStemPatchRows + ky) * kStemPatchPitch;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+          if (qv) {
+            uint32_t w0, w1;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w0) : "r"(prow + src_off[i]));
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w1) : "r"(prow + src_off[i] + 4));
+            // u8 -> fp16 exactly: bytes (b, 0x64) form the half 1024 + b; subtract 1024
+            uint32_t p0 = __byte_perm(w0, 0x64646464u, 0x4140), p1 = __byte_perm(w0, 0x64646464u, 0x4342);
+            uint32_t p2 = __byte_perm(w1, 0x64646464u, 0x4140), p3 = __byte_perm(w1, 0x64646464u, 0x4342);
+            const __half2 h0 = __hsub2(*reinterpret_cast<__half2*>(&p0), k1024);
+            const __half2 h1 = __hsub2(*reinterpret_cast<__half2*>(&p1), k1024);
+            const __half2 h2 = __hsub2(*reinterpret_cast<__half2*>(&p2), k1024);
+            const __half2 h3 = __hsub2(*reinterpret_cast<__half2*>(&p3), k1024);
+            o0 = *reinterpret_cast<const uint32_t*>(&h0); o1 = *reinterpret_cast<const uint32_t*>(&h1);
+            o2 = *reinterpret_cast<const uint32_t*>(&h2); o3 = *reinterpret_cast<const uint32_t*>(&h3);
+          }
+          st_smem_16B(tile_a + dst_off[i], o0, o1, o2, o3);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&full[s]);
+        q += 8; ci += 8;
+        while (ci >= Cin) { ci -= Cin; ++ky; }
+      }
+      mbar_arrive(&patch_free[b]);
+    }
+  } else if (warp == 12) {
+    // =============================================== producer ===============================================
+    if (lane == 0 && static_cast<int>(blockIdx.x) < n_tiles) {
+      tma_prefetch_desc(&tmap_in);
+      const uint32_t box_bytes = static_cast<uint32_t>(Cin) * kStemPatchRows * kStemPatchPitch;
+      const uint32_t w_bytes = static_cast<uint32_t>(C) * 128;
+      auto load_patch = [&](int it2, int tile2) {
+        const int b = it2 & 1;
+        const int tb = tile2 / per_img, tt = tile2 - tb * per_img;
+        const int ty = tt / a.nx, tx = tt - ty * a.nx;
+        mbar_wait(&patch_free[b], ((it2 >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&patch_full[b], box_bytes);
+        tma_load_3d(sP + b * patch_bytes, &tmap_in, tx * kStemTileW * 4 - 16, ty * kStemTileH * 4 - 3, tb * Cin, &patch_full[b]);
+      };
+      load_patch(0, blockIdx.x);
+      int it = 0;
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        if (tile + static_cast<int>(gridDim.x) < n_tiles) load_patch(it + 1, tile + gridDim.x);
+        for (int kc = 0; kc < KC; ++kc, ++g) {
+          const uint32_t s = g % kSv2Stages, ph = (g / kSv2Stages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], w_bytes);
+          bulk_g2s(sm + (sS - base) + s * kSv2StageBytes + kATileBytes, a.wp + static_cast<size_t>(kc) * C * 64, w_bytes, &full[s]);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================================== MMA issuer ===============================================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(128, C, 0);
+      int it = 0;
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int ab = it & 1;
+        mbar_wait(&acc_free[ab], ((it >> 1) & 1) ^ 1);          // the epilogue of tile it - 2 has drained this accumulator
+        tc_fence_after();
+        const uint32_t t_acc = tmem + ab * 64;
+        for (int kc = 0; kc < KC; ++kc, ++g) {
+          const uint32_t s = g % kSv2Stages, ph = (g / kSv2Stages) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t ta = sS + s * kSv2StageBytes, tw = ta + kATileBytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(t_acc, umma_desc_sw128(ta + k * 32), umma_desc_sw128(tw + k * 32), idesc, (kc | k) != 0);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&acc_full[ab]);
+      }
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 13) tmem_dealloc(tmem, 128);
+}
+
+}  // namespace rvt
