@@ -533,11 +533,17 @@ class RNNDetector(nn.Module):
                             seq_feats[s] = torch.empty((L, bsz, vh // self.strides[s], vw // self.strides[s], self.stage_dims[s]),
                                                        dtype=torch.float32, device=dev)
                         h_dst = seq_feats[s][t]
+                    timeline = getattr(self, 'debug_timeline', None)      # profiling aid (profiles/wavefront_timeline.py), eager only
+                    if timeline is not None:
+                        ev0 = torch.cuda.Event(enable_timing=True)
+                        ev0.record(streams[s])
                     h_new, c_new, h16 = self._stage_step(s, packed[s], cur, nchw, state[s], tm, h_out=h_dst)
-                    if wavefront or s == n - 1:
-                        ev = torch.cuda.Event()
+                    if wavefront or s == n - 1 or timeline is not None:
+                        ev = torch.cuda.Event(enable_timing=timeline is not None)
                         ev.record(streams[s])
                         done[s][t] = ev
+                        if timeline is not None:
+                            timeline.append((s, t, ev0, ev))
                     if wavefront and not capturing:
                         # eager mode: tell the caching allocator about the cross-stream consumers
                         if s + 1 < n:

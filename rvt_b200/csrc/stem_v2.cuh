@@ -29,14 +29,15 @@ struct StemV2Args {
 constexpr int kSv2Builders = 256;
 constexpr int kSv2Epi = 128;
 constexpr int kSv2Threads = kSv2Epi + kSv2Builders + 64;      // + producer warp + MMA warp
-constexpr int kSv2Stages = 3;
-constexpr uint32_t kSv2StageBytes = kATileBytes + 64 * 128;   // A chunk + weight chunk (C <= 64)
+constexpr int kSv2Stages = 3;                                 // A-chunk ring (builders -> MMA: short round trip)
+constexpr int kSv2WStages = 6;                                // weight-chunk ring: deep, an L2 -> smem bulk copy takes ~1000 cycles
+constexpr uint32_t kSv2WBytes = 64 * 128;                     // one weight chunk (C <= 64 rows x 64 halves)
 __host__ __device__ inline uint32_t stem_v2_patch_bytes(int cin) {
   return (static_cast<uint32_t>(cin) * kStemPatchRows * kStemPatchPitch + 1023u) & ~1023u;
 }
 __host__ __device__ inline uint32_t stem_v2_smem_bytes(int cin, int c) {
-  return 1024 + 2 * stem_v2_patch_bytes(cin) + kSv2Stages * kSv2StageBytes + 128 * (static_cast<uint32_t>(c) * 4 + 16) + 3 * 64 * 4 +
-         16 * 8 + 16;
+  return 1024 + 2 * stem_v2_patch_bytes(cin) + kSv2Stages * kATileBytes + kSv2WStages * kSv2WBytes +
+         64 * (static_cast<uint32_t>(c) * 4 + 16) + 3 * 64 * 4 + 32 * 8 + 16;
 }
 
 __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
@@ -58,27 +59,31 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
   const int C = a.C, Cin = a.Cin, KC = a.KC, n_tiles = a.n_tiles;
   const uint32_t patch_bytes = stem_v2_patch_bytes(Cin);
   const uint32_t sP = base;                                    // [2] patches
-  const uint32_t sS = sP + 2 * patch_bytes;                    // [3] stages: A chunk, then the weight chunk
-  const uint32_t sO = sS + kSv2Stages * kSv2StageBytes;        // fp32 staging tile, row pitch C * 4 + 16 bytes
+  const uint32_t sS = sP + 2 * patch_bytes;                    // [3] A chunks
+  const uint32_t sW = sS + kSv2Stages * kATileBytes;           // [6] weight chunks
+  const uint32_t sO = sW + kSv2WStages * kSv2WBytes;           // fp32 staging of HALF a tile (64 rows), row pitch C * 4 + 16 bytes
   const uint32_t o_pitch = static_cast<uint32_t>(C) * 4 + 16;
-  float* s_lnw = reinterpret_cast<float*>(sm + (sO - base) + 128 * o_pitch);
+  float* s_lnw = reinterpret_cast<float*>(sm + (sO - base) + 64 * o_pitch);
   float* s_lnb = s_lnw + 64;
   float* s_mask = s_lnb + 64;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_mask + 64);
   uint64_t* patch_full = bars + 0;     // [2] tx
   uint64_t* patch_free = bars + 2;     // [2] 256
-  uint64_t* full = bars + 4;           // [3] 256 builders + 1 producer (tx)
+  uint64_t* full = bars + 4;           // [3] 256 builders
   uint64_t* empty = bars + 7;          // [3] commit
   uint64_t* acc_full = bars + 10;      // [2] commit
   uint64_t* acc_free = bars + 12;      // [2] 128
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* w_full = bars + 14;        // [6] tx
+  uint64_t* w_empty = bars + 20;       // [6] commit
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
 
   if (tid == 0) {
     for (int b = 0; b < 2; ++b) {
       mbar_init(&patch_full[b], 1); mbar_init(&patch_free[b], kSv2Builders);
       mbar_init(&acc_full[b], 1); mbar_init(&acc_free[b], kSv2Epi);
     }
-    for (int s = 0; s < kSv2Stages; ++s) { mbar_init(&full[s], kSv2Builders + 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kSv2Stages; ++s) { mbar_init(&full[s], kSv2Builders); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kSv2WStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     fence_mbar_init();
   }
   if (warp == 13) tmem_alloc(tmem_slot, 128);
@@ -110,48 +115,68 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
       const bool masked = a.token_mask && a.token_mask[my_tok];
       mbar_wait(&acc_full[ab], (it >> 1) & 1);
       tc_fence_after();
-      float v[64];
-#pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 16)
-        if (c0 < C) tmem_ld_x16(tmem + lane_off + ab * 64 + c0, v + c0);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&acc_free[ab]);                               // the accumulator is drained: the MMAs of tile it + 2 may start
+      // three passes over the TMEM row (sum, centred sum of squares, normalise): 16 live values instead of the whole row
+      const uint32_t trow = tmem + lane_off + ab * 64;
       float s = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < C; c0 += 16) {
+        float v[16];
+        tmem_ld_x16(trow + c0, v);
+        tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 64; ++c) if (c < C) s += v[c];
+        for (int e = 0; e < 16; ++e) s += v[e];
+      }
       const float mean = s * inv_c;
       float ss = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < C; c0 += 16) {
+        float v[16];
+        tmem_ld_x16(trow + c0, v);
+        tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 64; ++c) if (c < C) { const float d = v[c] - mean; ss += d * d; }
+        for (int e = 0; e < 16; ++e) { const float d = v[e] - mean; ss += d * d; }
+      }
       const float rstd = rsqrtf(ss * inv_c + a.eps);
-      const uint32_t srow = sO + static_cast<uint32_t>(row) * o_pitch;
+      const uint32_t srow = sO + static_cast<uint32_t>(row & 63) * o_pitch;
+      // two passes of 64 rows through the half-tile staging buffer: (token, chunk) threads then write whole lines
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        if ((row >> 6) == half) {
+#pragma unroll 1
+          for (int c0 = 0; c0 < C; c0 += 16) {
+            float v[16];
+            tmem_ld_x16(trow + c0, v);
+            tmem_ld_wait();
 #pragma unroll
-      for (int c4 = 0; c4 < 16; ++c4) {
-        if (c4 * 4 >= C) break;
-        float4 o;
-        if (masked) {
-          o = *reinterpret_cast<const float4*>(s_mask + c4 * 4);
-        } else {
-          const float4 g = *reinterpret_cast<const float4*>(s_lnw + c4 * 4), bb = *reinterpret_cast<const float4*>(s_lnb + c4 * 4);
-          o.x = fmaf((v[c4 * 4 + 0] - mean) * rstd, g.x, bb.x);
-          o.y = fmaf((v[c4 * 4 + 1] - mean) * rstd, g.y, bb.y);
-          o.z = fmaf((v[c4 * 4 + 2] - mean) * rstd, g.z, bb.z);
-          o.w = fmaf((v[c4 * 4 + 3] - mean) * rstd, g.w, bb.w);
+            for (int c4 = 0; c4 < 4; ++c4) {
+              float4 o;
+              if (masked) {
+                o = *reinterpret_cast<const float4*>(s_mask + c0 + c4 * 4);
+              } else {
+                const float4 g = *reinterpret_cast<const float4*>(s_lnw + c0 + c4 * 4), bb = *reinterpret_cast<const float4*>(s_lnb + c0 + c4 * 4);
+                o.x = fmaf((v[c4 * 4 + 0] - mean) * rstd, g.x, bb.x);
+                o.y = fmaf((v[c4 * 4 + 1] - mean) * rstd, g.y, bb.y);
+                o.z = fmaf((v[c4 * 4 + 2] - mean) * rstd, g.z, bb.z);
+                o.w = fmaf((v[c4 * 4 + 3] - mean) * rstd, g.w, bb.w);
+              }
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (c0 + c4 * 4) * 4), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(&acc_free[ab]);                           // this row's accumulator is drained (128 arrivals: tile it + 2 may start)
         }
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow + c4 * 16), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+        named_bar_sync(1, kSv2Epi);
+        for (int idx = tid; idx < 64 * nch; idx += kSv2Epi) {
+          const int rl = idx / nch, ch = idx - rl * nch;
+          float4 sv;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sv.x), "=f"(sv.y), "=f"(sv.z), "=f"(sv.w)
+                       : "r"(sO + static_cast<uint32_t>(rl) * o_pitch + ch * 16));
+          const int r = half * 64 + rl;
+          const int tok = tok0 + (r >> 4) * a.Wout + (r & 15);
+          *reinterpret_cast<float4*>(a.y + static_cast<size_t>(tok) * C + ch * 4) = sv;
+        }
+        named_bar_sync(2, kSv2Epi);                             // the staging buffer is free again
       }
-      named_bar_sync(1, kSv2Epi);
-      // (token, chunk) threads: consecutive threads write consecutive 16-byte chunks -> whole lines
-      for (int idx = tid; idx < 128 * nch; idx += kSv2Epi) {
-        const int r = idx / nch, ch = idx - r * nch;
-        float4 sv;
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sv.x), "=f"(sv.y), "=f"(sv.z), "=f"(sv.w)
-                     : "r"(sO + static_cast<uint32_t>(r) * o_pitch + ch * 16));
-        const int tok = tok0 + (r >> 4) * a.Wout + (r & 15);
-        *reinterpret_cast<float4*>(a.y + static_cast<size_t>(tok) * C + ch * 4) = sv;
-      }
-      named_bar_sync(2, kSv2Epi);                               // the staging tile is free again
     }
   } else if (warp < 12) {
     // =============================================== builders ===============================================
@@ -177,7 +202,7 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
       for (int kc = 0; kc < KC; ++kc, ++g) {
         const uint32_t s = g % kSv2Stages, ph = (g / kSv2Stages) & 1;
         mbar_wait(&empty[s], ph ^ 1);
-        const uint32_t tile_a = sS + s * kSv2StageBytes;
+        const uint32_t tile_a = sS + s * kATileBytes;
         const bool qv = q < npairs;
         const uint32_t prow = patch + (ci * kStemPatchRows + ky) * kStemPatchPitch;
 #pragma unroll
@@ -226,10 +251,10 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         if (tile + static_cast<int>(gridDim.x) < n_tiles) load_patch(it + 1, tile + gridDim.x);
         for (int kc = 0; kc < KC; ++kc, ++g) {
-          const uint32_t s = g % kSv2Stages, ph = (g / kSv2Stages) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full[s], w_bytes);
-          bulk_g2s(sm + (sS - base) + s * kSv2StageBytes + kATileBytes, a.wp + static_cast<size_t>(kc) * C * 64, w_bytes, &full[s]);
+          const uint32_t s = g % kSv2WStages, ph = (g / kSv2WStages) & 1;
+          mbar_wait(&w_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&w_full[s], w_bytes);
+          bulk_g2s(sm + (sW - base) + s * kSv2WBytes, a.wp + static_cast<size_t>(kc) * C * 64, w_bytes, &w_full[s]);
         }
       }
     }
@@ -247,12 +272,15 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
         const uint32_t t_acc = tmem + ab * 64;
         for (int kc = 0; kc < KC; ++kc, ++g) {
           const uint32_t s = g % kSv2Stages, ph = (g / kSv2Stages) & 1;
+          const uint32_t ws = g % kSv2WStages, wph = (g / kSv2WStages) & 1;
+          mbar_wait(&w_full[ws], wph);
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint32_t ta = sS + s * kSv2StageBytes, tw = ta + kATileBytes;
+          const uint32_t ta = sS + s * kATileBytes, tw = sW + ws * kSv2WBytes;
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_f16(t_acc, umma_desc_sw128(ta + k * 32), umma_desc_sw128(tw + k * 32), idesc, (kc | k) != 0);
           umma_commit(&empty[s]);
+          umma_commit(&w_empty[ws]);
         }
         umma_commit(&acc_full[ab]);
       }
