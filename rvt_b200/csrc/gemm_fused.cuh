@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_fused_kernel(const __gri
   const uint32_t s_patch = (smem_u32(tmem_slot) + 16 + 127u) & ~127u;     // LD_STEM input patch (128-byte aligned)
 
   if (tid == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], LOADER == LD_TMA ? 1 : kWorkers); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], LOADER == LD_TMA ? 1 : kWorkers / 32); mbar_init(&empty[s], 1); }
     mbar_init(accum, 1);
     fence_mbar_init();
   }
@@ -538,7 +538,8 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_fused_kernel(const __gri
           st_smem_16B(tile + sw128_offset(r, j), o0, o1, o2, o3);
         }
         fence_proxy_async_smem();
-        mbar_arrive(&full[s]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[s]);      // one arrival per warp: 256 same-address arrivals per K chunk serialise in the smem pipe
       }
     } else {
     uint32_t raw_a[4][8], raw_b[4][8];
@@ -558,7 +559,8 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_fused_kernel(const __gri
       const uint32_t tile = sA_addr + s * kATileBytes;
       if (even) commit(kc, raw_a, tile); else commit(kc, raw_b, tile);
       fence_proxy_async_smem();
-      mbar_arrive(&full[s]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
     }
     }
    }  // LOADER != LD_TMA

@@ -68,8 +68,8 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
   float* s_mask = s_lnb + 64;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_mask + 64);
   uint64_t* patch_full = bars + 0;     // [2] tx
-  uint64_t* patch_free = bars + 2;     // [2] 256
-  uint64_t* full = bars + 4;           // [3] 256 builders
+  uint64_t* patch_free = bars + 2;     // [2] 8 (one per builder warp)
+  uint64_t* full = bars + 4;           // [3] 8 (one per builder warp)
   uint64_t* empty = bars + 7;          // [3] commit
   uint64_t* acc_full = bars + 10;      // [2] commit
   uint64_t* acc_free = bars + 12;      // [2] 128
@@ -79,10 +79,10 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
 
   if (tid == 0) {
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&patch_full[b], 1); mbar_init(&patch_free[b], kSv2Builders);
+      mbar_init(&patch_full[b], 1); mbar_init(&patch_free[b], kSv2Builders / 32);
       mbar_init(&acc_full[b], 1); mbar_init(&acc_free[b], kSv2Epi);
     }
-    for (int s = 0; s < kSv2Stages; ++s) { mbar_init(&full[s], kSv2Builders); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kSv2Stages; ++s) { mbar_init(&full[s], kSv2Builders / 32); mbar_init(&empty[s], 1); }
     for (int s = 0; s < kSv2WStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     fence_mbar_init();
   }
@@ -225,11 +225,13 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
           st_smem_16B(tile_a + dst_off[i], o0, o1, o2, o3);
         }
         fence_proxy_async_smem();
-        mbar_arrive(&full[s]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[s]);                   // one arrival per warp (same-address arrivals serialise)
         q += 8; ci += 8;
         while (ci >= Cin) { ci -= Cin; ++ky; }
       }
-      mbar_arrive(&patch_free[b]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&patch_free[b]);
     }
   } else if (warp == 12) {
     // =============================================== producer ===============================================
