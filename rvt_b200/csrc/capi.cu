@@ -304,6 +304,39 @@ bool make_tmap_stem_u8(const void* in, int batch, int cin, int hin, int win, CUt
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// channels-last fp16 image [B, Hin, Win, Cin] (pixel pitch `pitch` elements) as a 4-D tensor (Cin, Win, Hin, B); box = 64 channels of
+// the bw x bh input pixels one conv tap contributes to a bh x bw block of output tokens (element strides = the conv stride), landing as
+// bh*bw rows of a 128-byte-swizzled K-major operand tile.
+bool make_tmap_conv_f16(const void* in, int batch, int hin, int win, int cin, int pitch, int bh, int bw, int stride, CUtensorMap* out) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn || (reinterpret_cast<uintptr_t>(in) & 15) || pitch % 8 != 0 || cin % 64 != 0 || stride < 1 || stride > 8) return false;
+  const cuuint64_t gdim[4] = {static_cast<cuuint64_t>(cin), static_cast<cuuint64_t>(win), static_cast<cuuint64_t>(hin),
+                              static_cast<cuuint64_t>(batch)};
+  const cuuint64_t gstride[3] = {static_cast<cuuint64_t>(pitch) * 2, static_cast<cuuint64_t>(win) * pitch * 2,
+                                 static_cast<cuuint64_t>(hin) * win * pitch * 2};
+  const cuuint32_t box[4] = {64, static_cast<cuuint32_t>((bw - 1) * stride + 1), static_cast<cuuint32_t>((bh - 1) * stride + 1), 1};
+  if (box[1] > 256 || box[2] > 256) return false;
+  const cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
+  return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(in), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// bh x bw output-token blocks for the TMA-fed conv: bh*bw a divisor of 128 (>= 16 rows), bh | hout, bw | wout; widest block first
+bool conv_tma_blocks(int hout, int wout, int* bh, int* bw) {
+  for (int p = 128; p >= 16; p >>= 1)
+    for (int w = p; w >= 1; w >>= 1) {
+      const int h = p / w;
+      if (wout % w == 0 && hout % h == 0) { *bh = h; *bw = w; return true; }
+    }
+  return false;
+}
+
+int conv_tma_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("RVT_CONV_TMA"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
 int stem_v2_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("RVT_STEM_V2"); v = e ? atoi(e) : 0; }
@@ -524,6 +557,21 @@ static int downsample_impl(const void* in, int in_dtype, int in_nchw, int batch,
   }
   a.K = a.Cin * a.KSy * a.KSx;
   a.yout = out; a.eln_w = ln_w; a.eln_b = ln_b; a.eeps = eps; a.token_mask = token_mask; a.mask_token = mask_token;
+  // TMA-fed operand (channels-last fp16 input, Cin % 64 == 0): no loader threads, every tap chunk of a token block is one strided box
+  const RowMap idm = a.map;
+  alignas(64) CUtensorMap ctm;
+  int bh = 0, bw = 0;
+  int n_mtiles = cdiv(n_tok, 128);
+  const bool conv_tma = conv_tma_enabled() && !in_nchw && in_dtype == 2 && cin % 64 == 0 && a.KSy == ksize && stride <= 8 &&
+                        conv_tma_blocks(hout, wout, &bh, &bw) && make_tmap_conv_f16(in, batch, hin, win, cin, cin, bh, bw, stride, &ctm);
+  if (conv_tma) {
+    RowMap bm{};
+    bm.mode = MAP_BLK; bm.H = hout; bm.W = wout; bm.ph = bh; bm.pw = bw; bm.P = bh * bw; bm.rows_per_win = bm.P;
+    bm.ny = hout / bh; bm.nx = wout / bw; bm.n_groups = batch * bm.ny * bm.nx; bm.n_tokens = static_cast<int>(n_tok);
+    a.map = bm;
+    a.tma_conv = 1;
+    n_mtiles = cdiv(static_cast<int64_t>(bm.n_groups) * bm.P, 128);
+  }
   if (cout >= kWideDim && cout % 128 == 0) {
     // few row tiles: split N across CTAs (raw fp32 conv output), then LayerNorm the rows in place
     a.BN = rvt_conv_tile_n(cout);
@@ -535,13 +583,15 @@ static int downsample_impl(const void* in, int in_dtype, int in_nchw, int batch,
     if (!raw_out && !in_nchw && s2d_scratch) splits = rvt_conv_split_k(n_tok, cout, a.K);
     if (splits > 1) { raw = static_cast<float*>(s2d_scratch); a.split_stride = static_cast<long long>(n_tok) * cout; }
     a.yout = raw;
-    int rc = launch_gemm<LD_CONV, EP_RAW>(a, cdiv(n_tok, 128), cout / a.BN, st, nullptr, 0, splits);
+    int rc = conv_tma ? launch_gemm<LD_TMA, EP_RAW>(a, n_mtiles, cout / a.BN, st, &ctm, 0, splits)
+                      : launch_gemm<LD_CONV, EP_RAW>(a, n_mtiles, cout / a.BN, st, nullptr, 0, splits);
     if (rc) return rc;
-    return launch_ln_rows<false>(raw, a.map, n_tok, cout, 1, ln_w, ln_b, eps, out, token_mask, mask_token, st, splits,
+    return launch_ln_rows<false>(raw, idm, n_tok, cout, 1, ln_w, ln_b, eps, out, token_mask, mask_token, st, splits,
                                  a.split_stride);
   }
   a.raw_out = raw_out;
-  return launch_gemm<LD_CONV, EP_LN>(a, cdiv(n_tok, 128), 1, st);
+  if (conv_tma) return launch_gemm<LD_TMA, EP_LN>(a, n_mtiles, 1, st, &ctm);
+  return launch_gemm<LD_CONV, EP_LN>(a, n_mtiles, 1, st);
 }
 
 int rvt_downsample_cf2cl(const void* in, int in_dtype, int in_nchw, int batch, int cin, int hin, int win, int ksize,

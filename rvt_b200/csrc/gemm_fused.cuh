@@ -31,7 +31,7 @@ namespace rvt {
 
 enum { LD_F16 = 0, LD_LN = 1, LD_CONV = 2, LD_XH = 3, LD_TMA = 4, LD_STEM = 5 };
 enum { EP_F16 = 0, EP_RES = 1, EP_LN = 2, EP_LSTM = 3, EP_RAW = 4 };
-enum { MAP_IDENTITY = 0, MAP_WINDOW = 1, MAP_GRID = 2, MAP_BLOCK = 3 };
+enum { MAP_IDENTITY = 0, MAP_WINDOW = 1, MAP_GRID = 2, MAP_BLOCK = 3, MAP_BLK = 4 };
 
 // tile row -> token of a [B, H, W, C] channels-last tensor
 struct RowMap {
@@ -58,6 +58,15 @@ __device__ __forceinline__ int row_to_token(const RowMap& m, int row) {
     const int b = tile / per_img, t = tile - b * per_img;
     const int ty = t / m.nx, tx = t - ty * m.nx;
     return (b * m.H + ty * kStemTileH + (r >> 4)) * m.W + tx * kStemTileW + (r & 15);
+  }
+  if (m.mode == MAP_BLK) {     // ph x pw token blocks (P = ph*pw rows each, a divisor of 128), ny x nx blocks per image: the TMA-fed conv
+    const int blk = row / m.P, w = row - blk * m.P;
+    if (blk >= m.n_groups) return -1;
+    const int per_img = m.ny * m.nx;
+    const int b = blk / per_img, t = blk - b * per_img;
+    const int by = t / m.nx, bx = t - by * m.nx;
+    const int ly = w / m.pw, lx = w - ly * m.pw;
+    return (b * m.H + by * m.ph + ly) * m.W + bx * m.pw + lx;
   }
   const int g = row / m.rows_per_win, p = row - g * m.rows_per_win;
   if (p >= m.P || g >= m.n_groups) return -1;
@@ -88,6 +97,7 @@ struct GemmArgs {
   const float* hprev; const float* dw_w; const float* dw_b; int dws_mode; int dws_ks;
   // LD_CONV (rectangular kernel / stride / pad so the space-to-depth stem maps onto it)
   const void* cin; int in_dtype; int in_nchw; int Cin, Hin, Win, KSy, KSx, sy, sx, pady, padx, Hout, Wout;
+  int tma_conv;        // LD_TMA: A tiles are strided 4-D TMA boxes of a channels-last fp16 image (map.mode == MAP_BLK), K = (ky, kx, ci)
   int in_pitch;        // channels-last input: elements between consecutive pixels (0 = Cin; > Cin reads a channel slice of a wider buffer)
   // EP_F16
   __half* o16; int ldo; int act;
@@ -801,11 +811,34 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_fused_kernel(const __gri
     // =========================== TMA producer (LD_TMA only) ===========================
     if (LOADER == LD_TMA && lane == 0) {
       tma_prefetch_desc(&tmap_a);
+      // tma_conv: the tile is 128 / P blocks of ph x pw output tokens; tap (ky, kx) of a block is ONE strided box of the input image
+      // (element strides = the conv stride; out-of-image pixels = the conv padding are zero-filled by the TMA unit)
+      const int nb = a.tma_conv ? 128 / a.map.P : 0;
+      const int cpt = a.tma_conv ? a.Cin >> 6 : 1;
+      int bx0[8], by0[8], bb[8];
+      if (a.tma_conv) {
+        const int per_img = a.map.ny * a.map.nx;
+#pragma unroll
+        for (int jb = 0; jb < 8; ++jb) {
+          const int blk = mt * nb + jb;
+          const int b = blk / per_img, t = blk - b * per_img;
+          const int by = t / a.map.nx, bx = t - by * a.map.nx;
+          bb[jb] = b; by0[jb] = by * a.map.ph * a.sy - a.pady; bx0[jb] = bx * a.map.pw * a.sx - a.padx;
+        }
+      }
       for (int i = 0; i < kcn; ++i) {
         const int kc = kc0 + i;
         const int s = i % stages;
         mbar_wait(&empty[s], ((i / stages) & 1) ^ 1);
         mbar_arrive_expect_tx(&full[s], kATileBytes + b_bytes);
+        if (a.tma_conv) {
+          const int tap = kc / cpt, cbk = kc - tap * cpt;
+          const int ky = tap / a.KSx, kx = tap - ky * a.KSx;
+#pragma unroll
+          for (int jb = 0; jb < 8; ++jb)
+            if (jb < nb)
+              tma_load_4d(sA_addr + s * kATileBytes + jb * a.map.P * 128, &tmap_a, cbk * 64, bx0[jb] + kx, by0[jb] + ky, bb[jb], &full[s]);
+        } else
         tma_load_2d(sA_addr + s * kATileBytes, &tmap_a, kc * 64, mt * 128, &full[s]);
         bulk_g2s(sB + static_cast<size_t>(s) * b_bytes,
                  a.Wp + (static_cast<size_t>(nt) * KC + kc) * static_cast<size_t>(BN) * 64, b_bytes, &full[s]);

@@ -40,14 +40,6 @@ __host__ __device__ inline uint32_t stem_v2_smem_bytes(int cin, int c) {
          64 * (static_cast<uint32_t>(c) * 4 + 16) + 3 * 64 * 4 + 32 * 8 + 16;
 }
 
-__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-          smem_dst),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
-      : "memory");
-}
-
 __global__ void __launch_bounds__(kSv2Threads, 1)
 stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUtensorMap tmap_in) {
   extern __shared__ uint8_t smem_raw[];

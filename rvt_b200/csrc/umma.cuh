@@ -174,6 +174,22 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr_bytes,
   return d;
 }
 
+// 3-D / 4-D tiled TMA loads (stem input patches; strided conv taps of a channels-last image)
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const void* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+          smem_dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      : "memory");
+}
+
 // 5-D tiled TMA load (window / grid partition boxes of a channels-last fp32 tensor, attn_v2.cuh)
 __device__ __forceinline__ void tma_load_5d(uint32_t smem_dst, const void* tmap, int c0, int c1, int c2, int c3, int c4,
                                             uint64_t* bar) {
