@@ -525,6 +525,7 @@ static int downsample_impl(const void* in, int in_dtype, int in_nchw, int batch,
         sa.Cin = cin; sa.Hout = hout; sa.Wout = wout; sa.C = cout; sa.KC = cdiv(a.K, 64);
         sa.n_tiles = bm.n_groups; sa.ny = bm.ny; sa.nx = bm.nx;
         sa.ln_w = ln_w; sa.ln_b = ln_b; sa.eps = eps; sa.token_mask = token_mask; sa.mask_token = mask_token;
+        sa.trace = g_v2_trace;
         return launch_stem_v2(sa, tm, st);
       }
     }

@@ -24,8 +24,10 @@ struct StemV2Args {
   int Cin, Hout, Wout, C, KC, n_tiles, ny, nx;
   const float* ln_w; const float* ln_b; float eps;      // null: no affine / no LayerNorm is not supported (ln_w may be null)
   const uint8_t* token_mask; const float* mask_token;
+  long long* trace;         // optional [grid][kTraceTiles][kTracePts] globaltimer stamps of the role leaders (profiling aid)
 };
 
+#define SV2_TRACE(leader, it, pt) do { if (a.trace && (leader) && (it) < kTraceTiles) a.trace[(static_cast<long long>(blockIdx.x) * kTraceTiles + (it)) * kTracePts + (pt)] = gtime(); } while (0)
 constexpr int kSv2Builders = 256;
 constexpr int kSv2Epi = 128;
 constexpr int kSv2Threads = kSv2Epi + kSv2Builders + 64;      // + producer warp + MMA warp
@@ -105,7 +107,9 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
       const int tok0 = (tb * a.Hout + ty * kStemTileH) * a.Wout + tx * kStemTileW;      // token of row 0; row r: + (r>>4) * Wout + (r&15)
       const int my_tok = tok0 + (row >> 4) * a.Wout + (row & 15);
       const bool masked = a.token_mask && a.token_mask[my_tok];
+      SV2_TRACE(tid == 0, it, 3);
       mbar_wait(&acc_full[ab], (it >> 1) & 1);
+      SV2_TRACE(tid == 0, it, 4);
       tc_fence_after();
       // three passes over the TMEM row (sum, centred sum of squares, normalise): 16 live values instead of the whole row
       const uint32_t trow = tmem + lane_off + ab * 64;
@@ -129,6 +133,7 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
         for (int e = 0; e < 16; ++e) { const float d = v[e] - mean; ss += d * d; }
       }
       const float rstd = rsqrtf(ss * inv_c + a.eps);
+      SV2_TRACE(tid == 0, it, 5);
       const uint32_t srow = sO + static_cast<uint32_t>(row & 63) * o_pitch;
       // two passes of 64 rows through the half-tile staging buffer: (token, chunk) threads then write whole lines
 #pragma unroll 1
@@ -169,6 +174,7 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
         }
         named_bar_sync(2, kSv2Epi);                             // the staging buffer is free again
       }
+      SV2_TRACE(tid == 0, it, 6);
     }
   } else if (warp < 12) {
     // =============================================== builders ===============================================
@@ -188,7 +194,9 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
     uint32_t g = 0;                                             // running K-chunk counter (ring position)
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int b = it & 1;
+      SV2_TRACE(bt == 0, it, 0);
       mbar_wait(&patch_full[b], (it >> 1) & 1);
+      SV2_TRACE(bt == 0, it, 1);
       const uint32_t patch = sP + b * patch_bytes;
       int q = j, ky = j / Cin, ci = j - ky * Cin;               // (ky, ci) pair of this thread's chunk in K chunk 0
       for (int kc = 0; kc < KC; ++kc, ++g) {
@@ -224,6 +232,7 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&patch_free[b]);
+      SV2_TRACE(bt == 0, it, 2);
     }
   } else if (warp == 12) {
     // =============================================== producer ===============================================
@@ -261,7 +270,9 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
       uint32_t g = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int ab = it & 1;
+        SV2_TRACE(true, it, 7);
         mbar_wait(&acc_free[ab], ((it >> 1) & 1) ^ 1);          // the epilogue of tile it - 2 has drained this accumulator
+        SV2_TRACE(true, it, 8);
         tc_fence_after();
         const uint32_t t_acc = tmem + ab * 64;
         for (int kc = 0; kc < KC; ++kc, ++g) {
@@ -277,6 +288,7 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
           umma_commit(&w_empty[ws]);
         }
         umma_commit(&acc_full[ab]);
+        SV2_TRACE(true, it, 9);
       }
     }
     __syncwarp();
