@@ -80,8 +80,9 @@ def main():
                 src, nchw, cw, s2d = x8, True, pk['conv_w_u8'], None
                 in_bytes = x8.numel()
             else:
-                src, nchw, cw, s2d = torch.randn(B, h, w, cin, device=dev), False, pk['conv_w'], None
-                in_bytes = src.numel() * 4
+                # stages 2-4 read the fp16 copy of the previous stage's h_t (RNNDetector._stage_step)
+                src, nchw, cw, s2d = torch.randn(B, h, w, cin, device=dev).half(), False, pk['conv_w'], None
+                in_bytes = src.numel() * 2
             timeit('conv', s, lambda: ops.downsample_cf2cl(src, nchw, cw, c, d.kernel_size, f, d.padding, pk['ds_ln_w'],
                                                            pk['ds_ln_b'], s2d_scratch=s2d, stem_mode=2 if s == 0 else 0, split_ws=split_ws(s, n, c, cin, d)),
                    2 * n * c * cin * d.kernel_size ** 2, in_bytes + n * c * 4)

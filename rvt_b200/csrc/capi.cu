@@ -333,7 +333,7 @@ bool conv_tma_blocks(int hout, int wout, int* bh, int* bw) {
 
 int conv_tma_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("RVT_CONV_TMA"); v = e ? atoi(e) : 0; }
+  if (v < 0) { const char* e = getenv("RVT_CONV_TMA"); v = e ? atoi(e) : 1; }
   return v;
 }
 

@@ -199,9 +199,12 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
       SV2_TRACE(bt == 0, it, 1);
       const uint32_t patch = sP + b * patch_bytes;
       int q = j, ky = j / Cin, ci = j - ky * Cin;               // (ky, ci) pair of this thread's chunk in K chunk 0
+      long long cyc_wait = 0, cyc_fence = 0;                    // profiling: SM cycles the leader spent waiting for a free slot / publishing
       for (int kc = 0; kc < KC; ++kc, ++g) {
         const uint32_t s = g % kSv2Stages, ph = (g / kSv2Stages) & 1;
+        const long long c0 = a.trace ? clock64() : 0;
         mbar_wait(&empty[s], ph ^ 1);
+        if (a.trace) cyc_wait += clock64() - c0;
         const uint32_t tile_a = sS + s * kATileBytes;
         const bool qv = q < npairs;
         const uint32_t prow = patch + (ci * kStemPatchRows + ky) * kStemPatchPitch;
@@ -224,15 +227,21 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
           }
           st_smem_16B(tile_a + dst_off[i], o0, o1, o2, o3);
         }
+        const long long c1 = a.trace ? clock64() : 0;
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[s]);                   // one arrival per warp (same-address arrivals serialise)
+        if (a.trace) cyc_fence += clock64() - c1;
         q += 8; ci += 8;
         while (ci >= Cin) { ci -= Cin; ++ky; }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&patch_free[b]);
       SV2_TRACE(bt == 0, it, 2);
+      if (a.trace && bt == 0 && it < kTraceTiles) {
+        a.trace[(static_cast<long long>(blockIdx.x) * kTraceTiles + it) * kTracePts + 10] = cyc_wait;
+        a.trace[(static_cast<long long>(blockIdx.x) * kTraceTiles + it) * kTracePts + 11] = cyc_fence;
+      }
     }
   } else if (warp == 12) {
     // =============================================== producer ===============================================
