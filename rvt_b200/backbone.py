@@ -426,7 +426,7 @@ class RNNDetector(nn.Module):
             hp, cp = (self._as_nhwc_f32(t) for t in prev_state)
             assert hp.shape == xs.shape and cp.shape == xs.shape
         sxh = None
-        if c >= 256 and pk['dws_mode'] == 0:
+        if c >= 128 and pk['dws_mode'] == 0:
             sxh = self._scratch_buf(f'xh{s}', ((n_tok + 127) // 128) * 128 * 2 * c, torch.float16, dev)
         # fp16 copy of h_t for the next stage's im2col loader (half the bytes, no conversion)
         h16 = torch.empty(xs.shape, dtype=torch.float16, device=dev) if (want_h16 and s + 1 < self.num_stages) else None

@@ -346,12 +346,18 @@ int stem_v2_enabled() {
 int launch_stem_v2(const StemV2Args& a, const CUtensorMap& tm, cudaStream_t st) {
   const size_t smem = stem_v2_smem_bytes(a.Cin, a.C);
   if (smem > static_cast<size_t>(kMaxSmem)) return kErrUnsupported;
-  static DevOnce once;
-  if (cudaError_t e = ensure_smem_attr(once, stem_v2_kernel, kMaxSmem); e != cudaSuccess) return static_cast<int>(e);
   int grid = persistent_sms();
   if (grid > a.n_tiles) grid = a.n_tiles;
+  if (stem_v2_enabled() >= 2) {      // A operand chunks in tensor memory
+    static DevOnce once_t;
+    if (cudaError_t e = ensure_smem_attr(once_t, stem_v2_kernel<true>, kMaxSmem); e != cudaSuccess) return static_cast<int>(e);
+    if (grid <= 0) return 0;
+    return static_cast<int>(launch_pdl(stem_v2_kernel<true>, dim3(grid), dim3(kSv2Threads), smem, st, a, tm));
+  }
+  static DevOnce once;
+  if (cudaError_t e = ensure_smem_attr(once, stem_v2_kernel<false>, kMaxSmem); e != cudaSuccess) return static_cast<int>(e);
   if (grid <= 0) return 0;
-  return static_cast<int>(launch_pdl(stem_v2_kernel, dim3(grid), dim3(kSv2Threads), smem, st, a, tm));
+  return static_cast<int>(launch_pdl(stem_v2_kernel<false>, dim3(grid), dim3(kSv2Threads), smem, st, a, tm));
 }
 
 int wide_fuse_ln() {     // RVT_WIDE_FUSE_LN=1: wide stages (C >= 256) normalise / cast inside the GEMM's operand loader (one launch less per
@@ -878,7 +884,9 @@ static int dws_conv_lstm_impl(const float* x, const float* h_prev, const float* 
       return launch_lstm_v2(la, tx, th, tc, st);
     }
   }
-  if (dws_mode == 0 && dim >= kWideDim && scratch_xh != nullptr && !wide_fuse_ln()) {
+  static int cast_dim = -1;      // stages at least this wide cast [x | h] once and run the TMA-fed mainloop (RVT_LSTM_CAST_DIM)
+  if (cast_dim < 0) { const char* e = getenv("RVT_LSTM_CAST_DIM"); cast_dim = e ? atoi(e) : 128; }
+  if (dws_mode == 0 && dim >= cast_dim && scratch_xh != nullptr && !wide_fuse_ln()) {
     // wide stage, plain 1x1 cell: cast [x|h] once, then a TMA-fed mainloop (no per-N-tile A rebuild)
     const int n_rows = n_mtiles * 128;
     const int64_t items = static_cast<int64_t>(n_rows) * (2 * dim / 8);

@@ -31,7 +31,9 @@ struct StemV2Args {
 constexpr int kSv2Builders = 256;
 constexpr int kSv2Epi = 128;
 constexpr int kSv2Threads = kSv2Epi + kSv2Builders + 64;      // + producer warp + MMA warp
-constexpr int kSv2Stages = 3;                                 // A-chunk ring (builders -> MMA: short round trip)
+constexpr int kSv2Stages = 3;                                 // A-chunk ring in shared memory (ATMEM = false)
+constexpr int kSv2TStages = 8;                                // A-chunk ring in tensor memory (ATMEM = true): 32 columns per chunk
+constexpr uint32_t kSv2TAcol = 128;                           // TMEM: accumulators [0, 128), A ring [128, 128 + 8 * 32)
 constexpr int kSv2WStages = 6;                                // weight-chunk ring: deep, an L2 -> smem bulk copy takes ~1000 cycles
 constexpr uint32_t kSv2WBytes = 64 * 128;                     // one weight chunk (C <= 64 rows x 64 halves)
 __host__ __device__ inline uint32_t stem_v2_patch_bytes(int cin) {
@@ -39,9 +41,10 @@ __host__ __device__ inline uint32_t stem_v2_patch_bytes(int cin) {
 }
 __host__ __device__ inline uint32_t stem_v2_smem_bytes(int cin, int c) {
   return 1024 + 2 * stem_v2_patch_bytes(cin) + kSv2Stages * kATileBytes + kSv2WStages * kSv2WBytes +
-         64 * (static_cast<uint32_t>(c) * 4 + 16) + 3 * 64 * 4 + 32 * 8 + 16;
+         64 * (static_cast<uint32_t>(c) * 4 + 16) + 3 * 64 * 4 + 48 * 8 + 16;
 }
 
+template <bool ATMEM>
 __global__ void __launch_bounds__(kSv2Threads, 1)
 stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUtensorMap tmap_in) {
   extern __shared__ uint8_t smem_raw[];
@@ -61,26 +64,27 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
   float* s_lnb = s_lnw + 64;
   float* s_mask = s_lnb + 64;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_mask + 64);
+  constexpr int NST = ATMEM ? kSv2TStages : kSv2Stages;
   uint64_t* patch_full = bars + 0;     // [2] tx
   uint64_t* patch_free = bars + 2;     // [2] 8 (one per builder warp)
-  uint64_t* full = bars + 4;           // [3] 8 (one per builder warp)
-  uint64_t* empty = bars + 7;          // [3] commit
-  uint64_t* acc_full = bars + 10;      // [2] commit
-  uint64_t* acc_free = bars + 12;      // [2] 128
-  uint64_t* w_full = bars + 14;        // [6] tx
-  uint64_t* w_empty = bars + 20;       // [6] commit
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+  uint64_t* full = bars + 4;           // [NST] one arrival per builder warp of the chunk (8 smem / 4 TMEM)
+  uint64_t* empty = bars + 12;         // [NST] commit
+  uint64_t* acc_full = bars + 20;      // [2] commit
+  uint64_t* acc_free = bars + 22;      // [2] 128
+  uint64_t* w_full = bars + 24;        // [6] tx
+  uint64_t* w_empty = bars + 30;       // [6] commit
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
 
   if (tid == 0) {
     for (int b = 0; b < 2; ++b) {
       mbar_init(&patch_full[b], 1); mbar_init(&patch_free[b], kSv2Builders / 32);
       mbar_init(&acc_full[b], 1); mbar_init(&acc_free[b], kSv2Epi);
     }
-    for (int s = 0; s < kSv2Stages; ++s) { mbar_init(&full[s], kSv2Builders / 32); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], ATMEM ? 4 : kSv2Builders / 32); mbar_init(&empty[s], 1); }
     for (int s = 0; s < kSv2WStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     fence_mbar_init();
   }
-  if (warp == 13) tmem_alloc(tmem_slot, 128);
+  if (warp == 13) tmem_alloc(tmem_slot, ATMEM ? 512 : 128);
   for (int i = tid; i < 64; i += kSv2Threads) {
     const bool in = i < C;
     s_lnw[i] = (in && a.ln_w) ? a.ln_w[i] : 1.f;
@@ -179,6 +183,62 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
   } else if (warp < 12) {
     // =============================================== builders ===============================================
     const int bt = tid - kSv2Epi;
+    if (ATMEM) {
+      // A operand in TENSOR memory: thread = tile row = TMEM lane builds the 64 halves of its row (32 packed columns) in registers and
+      // writes them with one tcgen05.st -- no shared-memory stores, no proxy fence, and the MMA reads A without touching shared memory.
+      // Warps 4..7 / 8..11 own the four lane quarters; the two warps of a quarter take alternate K chunks.
+      const int qt = (warp - 4) & 3, hpar = (warp - 4) >> 2;
+      const int r = qt * 32 + lane;
+      const uint32_t src_row = (r >> 4) * (4 * kStemPatchPitch) + (r & 15) * 4 + 12;
+      const uint32_t t_a = tmem + kSv2TAcol + (static_cast<uint32_t>(qt * 32) << 16);
+      const int npairs = 7 * Cin;
+      const __half2 k1024 = __half2half2(__ushort_as_half(static_cast<unsigned short>(0x6400)));
+      int it = 0;
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int b = it & 1;
+        SV2_TRACE(bt == 0, it, 0);
+        mbar_wait(&patch_full[b], (it >> 1) & 1);
+        SV2_TRACE(bt == 0, it, 1);
+        const uint32_t patch = sP + b * patch_bytes + src_row;
+        for (int kc = 0; kc < KC; ++kc, ++g) {
+          if (static_cast<int>(g & 1) != hpar) continue;
+          const uint32_t s = g % kSv2TStages, ph = (g / kSv2TStages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          tc_fence_after();
+          int q = kc * 8, ky = q / Cin, ci = q - ky * Cin;
+          uint32_t o[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint32_t w0 = 0, w1 = 0;
+            if (q < npairs) {
+              const uint32_t src = patch + (ci * kStemPatchRows + ky) * kStemPatchPitch;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w0) : "r"(src));
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w1) : "r"(src + 4));
+            }
+            // u8 -> fp16 exactly: bytes (b, 0x64) form the half 1024 + b; subtract 1024 (zero bytes give exact zeros)
+            uint32_t p0 = __byte_perm(w0, 0x64646464u, 0x4140), p1 = __byte_perm(w0, 0x64646464u, 0x4342);
+            uint32_t p2 = __byte_perm(w1, 0x64646464u, 0x4140), p3 = __byte_perm(w1, 0x64646464u, 0x4342);
+            const __half2 h0 = __hsub2(*reinterpret_cast<__half2*>(&p0), k1024);
+            const __half2 h1 = __hsub2(*reinterpret_cast<__half2*>(&p1), k1024);
+            const __half2 h2 = __hsub2(*reinterpret_cast<__half2*>(&p2), k1024);
+            const __half2 h3 = __hsub2(*reinterpret_cast<__half2*>(&p3), k1024);
+            o[4 * j + 0] = *reinterpret_cast<const uint32_t*>(&h0); o[4 * j + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+            o[4 * j + 2] = *reinterpret_cast<const uint32_t*>(&h2); o[4 * j + 3] = *reinterpret_cast<const uint32_t*>(&h3);
+            ++q; ++ci;
+            if (ci >= Cin) { ci = 0; ++ky; }
+          }
+          tmem_st_x32(t_a + s * 32, o);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[s]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&patch_free[b]);
+        SV2_TRACE(bt == 0, it, 2);
+      }
+    } else {
     const int j = bt & 7;                                       // 16-byte chunk of the 128-byte operand row = one (ky, ci) pair
     const int r0 = bt >> 3;                                     // rows r0 + 32 i
     const int npairs = 7 * Cin;
@@ -243,6 +303,7 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
         a.trace[(static_cast<long long>(blockIdx.x) * kTraceTiles + it) * kTracePts + 11] = cyc_fence;
       }
     }
+    }  // !ATMEM
   } else if (warp == 12) {
     // =============================================== producer ===============================================
     if (lane == 0 && static_cast<int>(blockIdx.x) < n_tiles) {
@@ -285,14 +346,17 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
         tc_fence_after();
         const uint32_t t_acc = tmem + ab * 64;
         for (int kc = 0; kc < KC; ++kc, ++g) {
-          const uint32_t s = g % kSv2Stages, ph = (g / kSv2Stages) & 1;
+          const uint32_t s = g % NST, ph = (g / NST) & 1;
           const uint32_t ws = g % kSv2WStages, wph = (g / kSv2WStages) & 1;
           mbar_wait(&w_full[ws], wph);
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t ta = sS + s * kATileBytes, tw = sW + ws * kSv2WBytes;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(t_acc, umma_desc_sw128(ta + k * 32), umma_desc_sw128(tw + k * 32), idesc, (kc | k) != 0);
+          for (int k = 0; k < 4; ++k) {
+            if (ATMEM) umma_f16_ts(t_acc, tmem + kSv2TAcol + s * 32 + k * 8, umma_desc_sw128(tw + k * 32), idesc, (kc | k) != 0);
+            else umma_f16(t_acc, umma_desc_sw128(ta + k * 32), umma_desc_sw128(tw + k * 32), idesc, (kc | k) != 0);
+          }
           umma_commit(&empty[s]);
           umma_commit(&w_empty[ws]);
         }
@@ -305,7 +369,7 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 13) tmem_dealloc(tmem, 128);
+  if (warp == 13) tmem_dealloc(tmem, ATMEM ? 512 : 128);
 }
 
 }  // namespace rvt
