@@ -344,11 +344,13 @@ int stem_v2_enabled() {
 }
 
 int launch_stem_v2(const StemV2Args& a, const CUtensorMap& tm, cudaStream_t st) {
-  const size_t smem = stem_v2_smem_bytes(a.Cin, a.C);
+  size_t smem = stem_v2_smem_bytes(a.Cin, a.C);
   if (smem > static_cast<size_t>(kMaxSmem)) return kErrUnsupported;
   int grid = persistent_sms();
   if (grid > a.n_tiles) grid = a.n_tiles;
-  if (stem_v2_enabled() >= 2) {      // A operand chunks in tensor memory
+  if (stem_v2_enabled() >= 2 && stem_v2t_smem_bytes(a.Cin, a.C, a.KC) <= static_cast<size_t>(kMaxSmem)) {
+    // operand built straight into tensor memory, all weight chunks resident in shared memory
+    smem = stem_v2t_smem_bytes(a.Cin, a.C, a.KC);
     static DevOnce once_t;
     if (cudaError_t e = ensure_smem_attr(once_t, stem_v2_kernel<true>, kMaxSmem); e != cudaSuccess) return static_cast<int>(e);
     if (grid <= 0) return 0;

@@ -32,12 +32,18 @@ constexpr int kSv2Builders = 256;
 constexpr int kSv2Epi = 128;
 constexpr int kSv2Threads = kSv2Epi + kSv2Builders + 64;      // + producer warp + MMA warp
 constexpr int kSv2Stages = 3;                                 // A-chunk ring in shared memory (ATMEM = false)
-constexpr int kSv2TStages = 8;                                // A-chunk ring in tensor memory (ATMEM = true): 32 columns per chunk
-constexpr uint32_t kSv2TAcol = 128;                           // TMEM: accumulators [0, 128), A ring [128, 128 + 8 * 32)
+constexpr int kSv2TStages = 4;                                // ATMEM: operand ring in tensor memory, one slot = one STEP of kSv2KS K chunks
+constexpr int kSv2KS = 3;                                     // K chunks (of 64) per step: 3 x 32 packed columns per slot
+constexpr uint32_t kSv2TAcol = 128;                           // TMEM: accumulators [0, 128), operand ring [128, 128 + 4 * 96) = 512 columns
 constexpr int kSv2WStages = 6;                                // weight-chunk ring: deep, an L2 -> smem bulk copy takes ~1000 cycles
 constexpr uint32_t kSv2WBytes = 64 * 128;                     // one weight chunk (C <= 64 rows x 64 halves)
 __host__ __device__ inline uint32_t stem_v2_patch_bytes(int cin) {
   return (static_cast<uint32_t>(cin) * kStemPatchRows * kStemPatchPitch + 1023u) & ~1023u;
+}
+// ATMEM variant: ONE patch buffer, ALL weight chunks resident, no operand ring in shared memory
+__host__ __device__ inline uint32_t stem_v2t_smem_bytes(int cin, int c, int kc) {
+  return 1024 + stem_v2_patch_bytes(cin) + static_cast<uint32_t>(kc) * kSv2WBytes + 64 * (static_cast<uint32_t>(c) * 4 + 16) + 3 * 64 * 4 +
+         48 * 8 + 16;
 }
 __host__ __device__ inline uint32_t stem_v2_smem_bytes(int cin, int c) {
   return 1024 + 2 * stem_v2_patch_bytes(cin) + kSv2Stages * kATileBytes + kSv2WStages * kSv2WBytes +
@@ -55,10 +61,10 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int C = a.C, Cin = a.Cin, KC = a.KC, n_tiles = a.n_tiles;
   const uint32_t patch_bytes = stem_v2_patch_bytes(Cin);
-  const uint32_t sP = base;                                    // [2] patches
-  const uint32_t sS = sP + 2 * patch_bytes;                    // [3] A chunks
-  const uint32_t sW = sS + kSv2Stages * kATileBytes;           // [6] weight chunks
-  const uint32_t sO = sW + kSv2WStages * kSv2WBytes;           // fp32 staging of HALF a tile (64 rows), row pitch C * 4 + 16 bytes
+  const uint32_t sP = base;                                    // [2] patches ([1] with ATMEM)
+  const uint32_t sS = sP + (ATMEM ? 1 : 2) * patch_bytes;      // [3] A chunks (none with ATMEM)
+  const uint32_t sW = sS + (ATMEM ? 0 : kSv2Stages) * kATileBytes;      // [6] weight chunk ring / ATMEM: all KC chunks, resident
+  const uint32_t sO = sW + (ATMEM ? static_cast<uint32_t>(KC) : kSv2WStages) * kSv2WBytes;     // fp32 staging of HALF a tile (64 rows), row pitch C * 4 + 16 bytes
   const uint32_t o_pitch = static_cast<uint32_t>(C) * 4 + 16;
   float* s_lnw = reinterpret_cast<float*>(sm + (sO - base) + 64 * o_pitch);
   float* s_lnb = s_lnw + 64;
@@ -184,58 +190,63 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
     // =============================================== builders ===============================================
     const int bt = tid - kSv2Epi;
     if (ATMEM) {
-      // A operand in TENSOR memory: thread = tile row = TMEM lane builds the 64 halves of its row (32 packed columns) in registers and
-      // writes them with one tcgen05.st -- no shared-memory stores, no proxy fence, and the MMA reads A without touching shared memory.
-      // Warps 4..7 / 8..11 own the four lane quarters; the two warps of a quarter take alternate K chunks.
+      // Operand in TENSOR memory: thread = tile row = TMEM lane builds the halves of ITS row in registers and writes them with
+      // tcgen05.st (32 packed columns per K chunk) -- no shared-memory stores, no proxy fence, and the MMA reads the operand without
+      // touching shared memory.  One hand-off = a STEP of 3 K chunks (the per-chunk version was bound by the hand-off latencies, not by
+      // any throughput).  Warps 4..7 / 8..11 own the four lane quarters; the two warps of a quarter take alternate steps.
       const int qt = (warp - 4) & 3, hpar = (warp - 4) >> 2;
       const int r = qt * 32 + lane;
       const uint32_t src_row = (r >> 4) * (4 * kStemPatchPitch) + (r & 15) * 4 + 12;
       const uint32_t t_a = tmem + kSv2TAcol + (static_cast<uint32_t>(qt * 32) << 16);
       const int npairs = 7 * Cin;
+      const int n_steps = (KC + kSv2KS - 1) / kSv2KS;
       const __half2 k1024 = __half2half2(__ushort_as_half(static_cast<unsigned short>(0x6400)));
       int it = 0;
       uint32_t g = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int b = it & 1;
         SV2_TRACE(bt == 0, it, 0);
-        mbar_wait(&patch_full[b], (it >> 1) & 1);
+        mbar_wait(&patch_full[0], it & 1);
         SV2_TRACE(bt == 0, it, 1);
-        const uint32_t patch = sP + b * patch_bytes + src_row;
-        for (int kc = 0; kc < KC; ++kc, ++g) {
+        const uint32_t patch = sP + src_row;
+        for (int st = 0; st < n_steps; ++st, ++g) {
           if (static_cast<int>(g & 1) != hpar) continue;
           const uint32_t s = g % kSv2TStages, ph = (g / kSv2TStages) & 1;
           mbar_wait(&empty[s], ph ^ 1);
           tc_fence_after();
-          int q = kc * 8, ky = q / Cin, ci = q - ky * Cin;
-          uint32_t o[32];
+          int q = st * kSv2KS * 8, ky = q / Cin, ci = q - ky * Cin;
+#pragma unroll 1
+          for (int atom = 0; atom < kSv2KS; ++atom) {
+            if (st * kSv2KS + atom >= KC) break;
+            uint32_t o[32];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            uint32_t w0 = 0, w1 = 0;
-            if (q < npairs) {
-              const uint32_t src = patch + (ci * kStemPatchRows + ky) * kStemPatchPitch;
-              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w0) : "r"(src));
-              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w1) : "r"(src + 4));
+            for (int j = 0; j < 8; ++j) {
+              uint32_t w0 = 0, w1 = 0;
+              if (q < npairs) {
+                const uint32_t src = patch + (ci * kStemPatchRows + ky) * kStemPatchPitch;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w0) : "r"(src));
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w1) : "r"(src + 4));
+              }
+              // u8 -> fp16 exactly: bytes (b, 0x64) form the half 1024 + b; subtract 1024 (zero bytes give exact zeros)
+              uint32_t p0 = __byte_perm(w0, 0x64646464u, 0x4140), p1 = __byte_perm(w0, 0x64646464u, 0x4342);
+              uint32_t p2 = __byte_perm(w1, 0x64646464u, 0x4140), p3 = __byte_perm(w1, 0x64646464u, 0x4342);
+              const __half2 h0 = __hsub2(*reinterpret_cast<__half2*>(&p0), k1024);
+              const __half2 h1 = __hsub2(*reinterpret_cast<__half2*>(&p1), k1024);
+              const __half2 h2 = __hsub2(*reinterpret_cast<__half2*>(&p2), k1024);
+              const __half2 h3 = __hsub2(*reinterpret_cast<__half2*>(&p3), k1024);
+              o[4 * j + 0] = *reinterpret_cast<const uint32_t*>(&h0); o[4 * j + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+              o[4 * j + 2] = *reinterpret_cast<const uint32_t*>(&h2); o[4 * j + 3] = *reinterpret_cast<const uint32_t*>(&h3);
+              ++q; ++ci;
+              if (ci >= Cin) { ci = 0; ++ky; }
             }
-            // u8 -> fp16 exactly: bytes (b, 0x64) form the half 1024 + b; subtract 1024 (zero bytes give exact zeros)
-            uint32_t p0 = __byte_perm(w0, 0x64646464u, 0x4140), p1 = __byte_perm(w0, 0x64646464u, 0x4342);
-            uint32_t p2 = __byte_perm(w1, 0x64646464u, 0x4140), p3 = __byte_perm(w1, 0x64646464u, 0x4342);
-            const __half2 h0 = __hsub2(*reinterpret_cast<__half2*>(&p0), k1024);
-            const __half2 h1 = __hsub2(*reinterpret_cast<__half2*>(&p1), k1024);
-            const __half2 h2 = __hsub2(*reinterpret_cast<__half2*>(&p2), k1024);
-            const __half2 h3 = __hsub2(*reinterpret_cast<__half2*>(&p3), k1024);
-            o[4 * j + 0] = *reinterpret_cast<const uint32_t*>(&h0); o[4 * j + 1] = *reinterpret_cast<const uint32_t*>(&h1);
-            o[4 * j + 2] = *reinterpret_cast<const uint32_t*>(&h2); o[4 * j + 3] = *reinterpret_cast<const uint32_t*>(&h3);
-            ++q; ++ci;
-            if (ci >= Cin) { ci = 0; ++ky; }
+            tmem_st_x32(t_a + s * (kSv2KS * 32) + atom * 32, o);
           }
-          tmem_st_x32(t_a + s * 32, o);
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&full[s]);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&patch_free[b]);
+        if (lane == 0) mbar_arrive(&patch_free[0]);
         SV2_TRACE(bt == 0, it, 2);
       }
     } else {
@@ -306,7 +317,23 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
     }  // !ATMEM
   } else if (warp == 12) {
     // =============================================== producer ===============================================
-    if (lane == 0 && static_cast<int>(blockIdx.x) < n_tiles) {
+    if (ATMEM && lane == 0 && static_cast<int>(blockIdx.x) < n_tiles) {
+      tma_prefetch_desc(&tmap_in);
+      const uint32_t box_bytes = static_cast<uint32_t>(Cin) * kStemPatchRows * kStemPatchPitch;
+      const uint32_t w_bytes = static_cast<uint32_t>(C) * 128;
+      mbar_arrive_expect_tx(&w_full[0], w_bytes * KC);           // all weight chunks once, resident for the CTA's lifetime
+      for (int kc = 0; kc < KC; ++kc)
+        bulk_g2s(sm + (sW - base) + kc * kSv2WBytes, a.wp + static_cast<size_t>(kc) * C * 64, w_bytes, &w_full[0]);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int tb = tile / per_img, tt = tile - tb * per_img;
+        const int ty = tt / a.nx, tx = tt - ty * a.nx;
+        mbar_wait(&patch_free[0], (it & 1) ^ 1);                 // the builders are done with the previous tile's patch (they run up to
+        mbar_arrive_expect_tx(&patch_full[0], box_bytes);        // 4 steps ahead of the MMAs, which hides this load)
+        tma_load_3d(sP, &tmap_in, tx * kStemTileW * 4 - 16, ty * kStemTileH * 4 - 3, tb * Cin, &patch_full[0]);
+      }
+    }
+    if (!ATMEM && lane == 0 && static_cast<int>(blockIdx.x) < n_tiles) {
       tma_prefetch_desc(&tmap_in);
       const uint32_t box_bytes = static_cast<uint32_t>(Cin) * kStemPatchRows * kStemPatchPitch;
       const uint32_t w_bytes = static_cast<uint32_t>(C) * 128;
@@ -334,7 +361,37 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
     __syncwarp();
   } else {
     // =============================================== MMA issuer ===============================================
-    if (lane == 0) {
+    if (ATMEM && lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(128, C, 0);
+      const int n_steps = (KC + kSv2KS - 1) / kSv2KS;
+      if (static_cast<int>(blockIdx.x) < n_tiles) mbar_wait(&w_full[0], 0);
+      int it = 0;
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int ab = it & 1;
+        SV2_TRACE(true, it, 7);
+        mbar_wait(&acc_free[ab], ((it >> 1) & 1) ^ 1);          // the epilogue of tile it - 2 has drained this accumulator
+        SV2_TRACE(true, it, 8);
+        tc_fence_after();
+        const uint32_t t_acc = tmem + ab * 64;
+        for (int st = 0; st < n_steps; ++st, ++g) {
+          const uint32_t s = g % kSv2TStages, ph = (g / kSv2TStages) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          for (int atom = 0; atom < kSv2KS; ++atom) {
+            const int kc = st * kSv2KS + atom;
+            if (kc >= KC) break;
+            const uint32_t ta = tmem + kSv2TAcol + s * (kSv2KS * 32) + atom * 32, tw = sW + kc * kSv2WBytes;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16_ts(t_acc, ta + k * 8, umma_desc_sw128(tw + k * 32), idesc, (kc | k) != 0);
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&acc_full[ab]);
+        SV2_TRACE(true, it, 9);
+      }
+    }
+    if (!ATMEM && lane == 0) {
       const uint32_t idesc = umma_idesc_f16(128, C, 0);
       int it = 0;
       uint32_t g = 0;
@@ -353,10 +410,7 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
           tc_fence_after();
           const uint32_t ta = sS + s * kATileBytes, tw = sW + ws * kSv2WBytes;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (ATMEM) umma_f16_ts(t_acc, tmem + kSv2TAcol + s * 32 + k * 8, umma_desc_sw128(tw + k * 32), idesc, (kc | k) != 0);
-            else umma_f16(t_acc, umma_desc_sw128(ta + k * 32), umma_desc_sw128(tw + k * 32), idesc, (kc | k) != 0);
-          }
+          for (int k = 0; k < 4; ++k) umma_f16(t_acc, umma_desc_sw128(ta + k * 32), umma_desc_sw128(tw + k * 32), idesc, (kc | k) != 0);
           umma_commit(&empty[s]);
           umma_commit(&w_empty[ws]);
         }
