@@ -339,7 +339,7 @@ int conv_tma_enabled() {
 
 int stem_v2_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("RVT_STEM_V2"); v = e ? atoi(e) : 2;      // 0: one tile per CTA (gemm_fused<LD_STEM>), 1: persistent, operand ring in smem, 2: operand in TMEM }
+  if (v < 0) { const char* e = getenv("RVT_STEM_V2"); v = e ? atoi(e) : 2; }    // 0: one tile per CTA (gemm_fused<LD_STEM>), 1: persistent, operand ring in smem, 2: operand in TMEM
   return v;
 }
 
