@@ -232,12 +232,12 @@ int launch_attn_v2(const AttnV2Args& a, const CUtensorMap& tm, cudaStream_t st) 
 }
 
 // fp32 row-major [rows, cols] -> box of all `cols` columns x 128 rows, no swizzle (token tiles of the residual stream)
-bool make_tmap_f32_rows(const float* base, int64_t rows, int cols, CUtensorMap* out, int box_c = 0) {   // box_c = 32: SW128 half tiles
+bool make_tmap_f32_rows(const float* base, int64_t rows, int cols, CUtensorMap* out, int box_c = 0, int box_r = 128) {   // box_c = 32: SW128 half tiles
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn || (reinterpret_cast<uintptr_t>(base) & 15) || cols % 4 != 0 || cols > 256) return false;
   const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * 4};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_c ? box_c : cols), 128};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_c ? box_c : cols), static_cast<cuuint32_t>(box_r)};
   const cuuint32_t estr[2] = {1, 1};
   return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -343,23 +343,30 @@ int stem_v2_enabled() {
   return v;
 }
 
-int launch_stem_v2(const StemV2Args& a, const CUtensorMap& tm, cudaStream_t st) {
+int launch_stem_v2(StemV2Args a, const CUtensorMap& tm, cudaStream_t st) {
   size_t smem = stem_v2_smem_bytes(a.Cin, a.C);
   if (smem > static_cast<size_t>(kMaxSmem)) return kErrUnsupported;
   int grid = persistent_sms();
   if (grid > a.n_tiles) grid = a.n_tiles;
+  // the normalised tile leaves through TMA tensor stores when the channel count splits into 32-channel swizzled boxes
+  alignas(64) CUtensorMap tmo;
+  static int tma_store_on = -1;
+  if (tma_store_on < 0) { const char* e = getenv("RVT_STEM_TMA_STORE"); tma_store_on = e ? atoi(e) : 1; }
+  a.tma_store = (tma_store_on && a.C % 32 == 0 && a.Wout % 16 == 0 &&
+                 make_tmap_f32_rows(a.y, static_cast<int64_t>(a.n_tiles) * 128, a.C, &tmo, 32, 16)) ? 1 : 0;
+  if (!a.tma_store) memset(&tmo, 0, sizeof(tmo));
   if (stem_v2_enabled() >= 2 && stem_v2t_smem_bytes(a.Cin, a.C, a.KC) <= static_cast<size_t>(kMaxSmem)) {
     // operand built straight into tensor memory, all weight chunks resident in shared memory
     smem = stem_v2t_smem_bytes(a.Cin, a.C, a.KC);
     static DevOnce once_t;
     if (cudaError_t e = ensure_smem_attr(once_t, stem_v2_kernel<true>, kMaxSmem); e != cudaSuccess) return static_cast<int>(e);
     if (grid <= 0) return 0;
-    return static_cast<int>(launch_pdl(stem_v2_kernel<true>, dim3(grid), dim3(kSv2Threads), smem, st, a, tm));
+    return static_cast<int>(launch_pdl(stem_v2_kernel<true>, dim3(grid), dim3(kSv2Threads), smem, st, a, tm, tmo));
   }
   static DevOnce once;
   if (cudaError_t e = ensure_smem_attr(once, stem_v2_kernel<false>, kMaxSmem); e != cudaSuccess) return static_cast<int>(e);
   if (grid <= 0) return 0;
-  return static_cast<int>(launch_pdl(stem_v2_kernel<false>, dim3(grid), dim3(kSv2Threads), smem, st, a, tm));
+  return static_cast<int>(launch_pdl(stem_v2_kernel<false>, dim3(grid), dim3(kSv2Threads), smem, st, a, tm, tmo));
 }
 
 int wide_fuse_ln() {     // RVT_WIDE_FUSE_LN=1: wide stages (C >= 256) normalise / cast inside the GEMM's operand loader (one launch less per

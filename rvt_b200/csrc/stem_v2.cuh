@@ -25,6 +25,7 @@ struct StemV2Args {
   const float* ln_w; const float* ln_b; float eps;      // null: no affine / no LayerNorm is not supported (ln_w may be null)
   const uint8_t* token_mask; const float* mask_token;
   long long* trace;         // optional [grid][kTraceTiles][kTracePts] globaltimer stamps of the role leaders (profiling aid)
+  int tma_store;            // 1: C % 32 == 0 and tmap_out is valid: the normalised tile leaves through TMA tensor stores
 };
 
 #define SV2_TRACE(leader, it, pt) do { if (a.trace && (leader) && (it) < kTraceTiles) a.trace[(static_cast<long long>(blockIdx.x) * kTraceTiles + (it)) * kTracePts + (pt)] = gtime(); } while (0)
@@ -52,7 +53,7 @@ __host__ __device__ inline uint32_t stem_v2_smem_bytes(int cin, int c) {
 
 template <bool ATMEM>
 __global__ void __launch_bounds__(kSv2Threads, 1)
-stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUtensorMap tmap_in) {
+stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -121,41 +122,46 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
       mbar_wait(&acc_full[ab], (it >> 1) & 1);
       SV2_TRACE(tid == 0, it, 4);
       tc_fence_after();
-      // three passes over the TMEM row (sum, centred sum of squares, normalise): 16 live values instead of the whole row
+      // statistics: the whole row in registers ONCE (one TMEM round trip), exact two-pass mean / variance
       const uint32_t trow = tmem + lane_off + ab * 64;
-      float s = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < C; c0 += 16) {
-        float v[16];
-        tmem_ld_x16(trow + c0, v);
-        tmem_ld_wait();
+      float mean, rstd;
+      {
+        float v[64];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) s += v[e];
-      }
-      const float mean = s * inv_c;
-      float ss = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < C; c0 += 16) {
-        float v[16];
-        tmem_ld_x16(trow + c0, v);
+        for (int c0 = 0; c0 < 64; c0 += 16)
+          if (c0 < C) tmem_ld_x16(trow + c0, v + c0);
         tmem_ld_wait();
+        float s = 0.f;
 #pragma unroll
-        for (int e = 0; e < 16; ++e) { const float d = v[e] - mean; ss += d * d; }
+        for (int c = 0; c < 64; ++c) if (c < C) s += v[c];
+        mean = s * inv_c;
+        float ss = 0.f;
+#pragma unroll
+        for (int c = 0; c < 64; ++c) if (c < C) { const float d = v[c] - mean; ss += d * d; }
+        rstd = rsqrtf(ss * inv_c + a.eps);
       }
-      const float rstd = rsqrtf(ss * inv_c + a.eps);
       SV2_TRACE(tid == 0, it, 5);
-      const uint32_t srow = sO + static_cast<uint32_t>(row & 63) * o_pitch;
-      // two passes of 64 rows through the half-tile staging buffer: (token, chunk) threads then write whole lines
+      // two passes of 64 rows through the half-tile staging buffer.  tma_store: the buffer is 4 token rows x C/32 boxes of
+      // [16 tokens x 32 channels] in the 128-byte swizzle (conflict-free for row-per-thread writes) and leaves through TMA tensor
+      // stores issued by one thread; otherwise padded rows and (token, chunk) threads that write whole lines.
+      const int rl = row & 63;
+      const uint32_t srow = sO + static_cast<uint32_t>(rl) * o_pitch;
+      const uint32_t sbox = sO + static_cast<uint32_t>((rl >> 4) * (C >> 5)) * 2048u + static_cast<uint32_t>(rl & 15) * 128u;
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
+        if (a.tma_store) {
+          if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // the previous stores have read the buffer
+          named_bar_sync(2, kSv2Epi);
+        }
         if ((row >> 6) == half) {
 #pragma unroll 1
-          for (int c0 = 0; c0 < C; c0 += 16) {
-            float v[16];
-            tmem_ld_x16(trow + c0, v);
+          for (int c0 = 0; c0 < C; c0 += 32) {
+            float v[32];
+            tmem_ld_x32(trow + c0, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
+            for (int c4 = 0; c4 < 8; ++c4) {
+              if (c0 + c4 * 4 >= C) break;
               float4 o;
               if (masked) {
                 o = *reinterpret_cast<const float4*>(s_mask + c0 + c4 * 4);
@@ -166,19 +172,33 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
                 o.z = fmaf((v[c4 * 4 + 2] - mean) * rstd, g.z, bb.z);
                 o.w = fmaf((v[c4 * 4 + 3] - mean) * rstd, g.w, bb.w);
               }
-              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (c0 + c4 * 4) * 4), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+              const uint32_t dst = a.tma_store ? sbox + static_cast<uint32_t>(c0 >> 5) * 2048u + ((static_cast<uint32_t>(c4) ^ (rl & 7)) << 4)
+                                               : srow + (c0 + c4 * 4) * 4;
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
             }
           }
           tc_fence_before();
           mbar_arrive(&acc_free[ab]);                           // this row's accumulator is drained (128 arrivals: tile it + 2 may start)
         }
+        if (a.tma_store) {
+          fence_proxy_async_smem();
+          named_bar_sync(1, kSv2Epi);
+          if (tid == 0) {
+            const int nbx = C >> 5;
+            for (int k = 0; k < 4; ++k)
+              for (int h = 0; h < nbx; ++h)
+                tma_store_2d(&tmap_out, h * 32, tok0 + (half * 4 + k) * a.Wout, sO + static_cast<uint32_t>(k * nbx + h) * 2048u);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          continue;
+        }
         named_bar_sync(1, kSv2Epi);
         for (int idx = tid; idx < 64 * nch; idx += kSv2Epi) {
-          const int rl = idx / nch, ch = idx - rl * nch;
+          const int rr = idx / nch, ch = idx - rr * nch;
           float4 sv;
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sv.x), "=f"(sv.y), "=f"(sv.z), "=f"(sv.w)
-                       : "r"(sO + static_cast<uint32_t>(rl) * o_pitch + ch * 16));
-          const int r = half * 64 + rl;
+                       : "r"(sO + static_cast<uint32_t>(rr) * o_pitch + ch * 16));
+          const int r = half * 64 + rr;
           const int tok = tok0 + (r >> 4) * a.Wout + (r & 15);
           *reinterpret_cast<float4*>(a.y + static_cast<size_t>(tok) * C + ch * 4) = sv;
         }
@@ -186,6 +206,7 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
       }
       SV2_TRACE(tid == 0, it, 6);
     }
+    if (a.tma_store && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all tensor stores complete before the CTA retires
   } else if (warp < 12) {
     // =============================================== builders ===============================================
     const int bt = tid - kSv2Epi;
