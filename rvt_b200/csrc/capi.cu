@@ -355,7 +355,7 @@ int launch_stem_v2(StemV2Args a, const CUtensorMap& tm, cudaStream_t st) {
   a.tma_store = (tma_store_on && a.C % 32 == 0 && a.Wout % 16 == 0 &&
                  make_tmap_f32_rows(a.y, static_cast<int64_t>(a.n_tiles) * 128, a.C, &tmo, 32, 16)) ? 1 : 0;
   if (!a.tma_store) memset(&tmo, 0, sizeof(tmo));
-  if (stem_v2_enabled() >= 2 && stem_v2t_smem_bytes(a.Cin, a.C, a.KC) <= static_cast<size_t>(kMaxSmem)) {
+  if (stem_v2_enabled() >= 2 && a.KC * 8 <= 256 && stem_v2t_smem_bytes(a.Cin, a.C, a.KC) <= static_cast<size_t>(kMaxSmem)) {
     // operand built straight into tensor memory, all weight chunks resident in shared memory
     smem = stem_v2t_smem_bytes(a.Cin, a.C, a.KC);
     static DevOnce once_t;

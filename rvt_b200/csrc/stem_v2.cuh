@@ -44,7 +44,7 @@ __host__ __device__ inline uint32_t stem_v2_patch_bytes(int cin) {
 // ATMEM variant: ONE patch buffer, ALL weight chunks resident, no operand ring in shared memory
 __host__ __device__ inline uint32_t stem_v2t_smem_bytes(int cin, int c, int kc) {
   return 1024 + stem_v2_patch_bytes(cin) + static_cast<uint32_t>(kc) * kSv2WBytes + 64 * (static_cast<uint32_t>(c) * 4 + 16) + 3 * 64 * 4 +
-         48 * 8 + 16;
+         48 * 8 + 16 + 256 * 4 /*pair -> patch offset LUT*/;
 }
 __host__ __device__ inline uint32_t stem_v2_smem_bytes(int cin, int c) {
   return 1024 + 2 * stem_v2_patch_bytes(cin) + kSv2Stages * kATileBytes + kSv2WStages * kSv2WBytes +
@@ -81,6 +81,7 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
   uint64_t* w_full = bars + 24;        // [6] tx
   uint64_t* w_empty = bars + 30;       // [6] commit
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
+  uint32_t* s_lut = tmem_slot + 4;      // ATMEM: [KC * 8] byte offset of the patch row of K pair q = (ky, ci), ~0u = zero padding of K
 
   if (tid == 0) {
     for (int b = 0; b < 2; ++b) {
@@ -92,6 +93,12 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
     fence_mbar_init();
   }
   if (warp == 13) tmem_alloc(tmem_slot, ATMEM ? 512 : 128);
+  if (ATMEM) {
+    for (int q = tid; q < KC * 8; q += kSv2Threads) {
+      const int ky = q / Cin, ci = q - ky * Cin;
+      s_lut[q] = q < 7 * Cin ? static_cast<uint32_t>((ci * kStemPatchRows + ky) * kStemPatchPitch) : 0xffffffffu;
+    }
+  }
   for (int i = tid; i < 64; i += kSv2Threads) {
     const bool in = i < C;
     s_lnw[i] = (in && a.ln_w) ? a.ln_w[i] : 1.f;
@@ -219,7 +226,6 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
       const int r = qt * 32 + lane;
       const uint32_t src_row = (r >> 4) * (4 * kStemPatchPitch) + (r & 15) * 4 + 12;
       const uint32_t t_a = tmem + kSv2TAcol + (static_cast<uint32_t>(qt * 32) << 16);
-      const int npairs = 7 * Cin;
       const int n_steps = (KC + kSv2KS - 1) / kSv2KS;
       const __half2 k1024 = __half2half2(__ushort_as_half(static_cast<unsigned short>(0x6400)));
       int it = 0;
@@ -229,23 +235,26 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
         mbar_wait(&patch_full[0], it & 1);
         SV2_TRACE(bt == 0, it, 1);
         const uint32_t patch = sP + src_row;
+        long long cyc_wait = 0;                                 // profiling: SM cycles the leader waited for a free operand slot
         for (int st = 0; st < n_steps; ++st, ++g) {
           if (static_cast<int>(g & 1) != hpar) continue;
           const uint32_t s = g % kSv2TStages, ph = (g / kSv2TStages) & 1;
+          const long long c0 = a.trace ? clock64() : 0;
           mbar_wait(&empty[s], ph ^ 1);
+          if (a.trace) cyc_wait += clock64() - c0;
           tc_fence_after();
-          int q = st * kSv2KS * 8, ky = q / Cin, ci = q - ky * Cin;
+          const uint32_t* lut = s_lut + st * kSv2KS * 8;
 #pragma unroll 1
           for (int atom = 0; atom < kSv2KS; ++atom) {
             if (st * kSv2KS + atom >= KC) break;
             uint32_t o[32];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
+              const uint32_t off = lut[atom * 8 + j];             // warp-uniform: one broadcast load
               uint32_t w0 = 0, w1 = 0;
-              if (q < npairs) {
-                const uint32_t src = patch + (ci * kStemPatchRows + ky) * kStemPatchPitch;
-                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w0) : "r"(src));
-                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w1) : "r"(src + 4));
+              if (off != 0xffffffffu) {
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w0) : "r"(patch + off));
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w1) : "r"(patch + off + 4));
               }
               // u8 -> fp16 exactly: bytes (b, 0x64) form the half 1024 + b; subtract 1024 (zero bytes give exact zeros)
               uint32_t p0 = __byte_perm(w0, 0x64646464u, 0x4140), p1 = __byte_perm(w0, 0x64646464u, 0x4342);
@@ -256,8 +265,6 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
               const __half2 h3 = __hsub2(*reinterpret_cast<__half2*>(&p3), k1024);
               o[4 * j + 0] = *reinterpret_cast<const uint32_t*>(&h0); o[4 * j + 1] = *reinterpret_cast<const uint32_t*>(&h1);
               o[4 * j + 2] = *reinterpret_cast<const uint32_t*>(&h2); o[4 * j + 3] = *reinterpret_cast<const uint32_t*>(&h3);
-              ++q; ++ci;
-              if (ci >= Cin) { ci = 0; ++ky; }
             }
             tmem_st_x32(t_a + s * (kSv2KS * 32) + atom * 32, o);
           }
@@ -269,6 +276,7 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
         __syncwarp();
         if (lane == 0) mbar_arrive(&patch_free[0]);
         SV2_TRACE(bt == 0, it, 2);
+        if (a.trace && bt == 0 && it < kTraceTiles) a.trace[(static_cast<long long>(blockIdx.x) * kTraceTiles + it) * kTracePts + 10] = cyc_wait;
       }
     } else {
     const int j = bt & 7;                                       // 16-byte chunk of the 128-byte operand row = one (ky, ci) pair
@@ -395,9 +403,12 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
         SV2_TRACE(true, it, 8);
         tc_fence_after();
         const uint32_t t_acc = tmem + ab * 64;
+        long long cyc_full = 0;                                 // profiling: SM cycles waiting for the builders
         for (int st = 0; st < n_steps; ++st, ++g) {
           const uint32_t s = g % kSv2TStages, ph = (g / kSv2TStages) & 1;
+          const long long c0 = a.trace ? clock64() : 0;
           mbar_wait(&full[s], ph);
+          if (a.trace) cyc_full += clock64() - c0;
           tc_fence_after();
           for (int atom = 0; atom < kSv2KS; ++atom) {
             const int kc = st * kSv2KS + atom;
@@ -410,6 +421,7 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
         }
         umma_commit(&acc_full[ab]);
         SV2_TRACE(true, it, 9);
+        if (a.trace && it < kTraceTiles) a.trace[(static_cast<long long>(blockIdx.x) * kTraceTiles + it) * kTracePts + 11] = cyc_full;
       }
     }
     if (!ATMEM && lane == 0) {
