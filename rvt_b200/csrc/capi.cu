@@ -293,13 +293,14 @@ int launch_mlp_v2x(const MlpV2xArgs& a, const CUtensorMap& tm, cudaStream_t st) 
 
 // uint8 NCHW events [B, Cin, Hin, Win] as a 3-D tensor (Win, Hin, B*Cin); box = the [Cin x 35 x 80] input patch of one
 // 8 x 16-token stem tile (stem_v2.cuh).  Out-of-image parts of a box are zero-filled.
-bool make_tmap_stem_u8(const void* in, int batch, int cin, int hin, int win, CUtensorMap* out) {
+bool make_tmap_stem_u8(const void* in, int batch, int cin, int hin, int win, CUtensorMap* out, bool planes = false) {   // planes: rows iy0 + 4 k
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn || (reinterpret_cast<uintptr_t>(in) & 15) || win % 16 != 0 || cin > 256) return false;
   const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(win), static_cast<cuuint64_t>(hin), static_cast<cuuint64_t>(batch) * cin};
   const cuuint64_t gstride[2] = {static_cast<cuuint64_t>(win), static_cast<cuuint64_t>(win) * hin};
-  const cuuint32_t box[3] = {static_cast<cuuint32_t>(kStemPatchPitch), static_cast<cuuint32_t>(kStemPatchRows), static_cast<cuuint32_t>(cin)};
-  const cuuint32_t estr[3] = {1, 1, 1};
+  const cuuint32_t box[3] = {static_cast<cuuint32_t>(kStemPatchPitch),
+                             static_cast<cuuint32_t>(planes ? (kSv2PlaneRows - 1) * 4 + 1 : kStemPatchRows), static_cast<cuuint32_t>(cin)};
+  const cuuint32_t estr[3] = {1, planes ? 4u : 1u, 1};
   return fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(in), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -343,6 +344,13 @@ int stem_v2_enabled() {
   return v;
 }
 
+bool stem_v2_atmem(int cin, int c, int kc) {   // the tensor-memory-operand variant fits (weights resident)
+  // more K steps per tile than operand-ring slots: bounds how far one builder warp can run ahead of another (the plane-release
+  // protocol of stem_v2.cuh relies on it); shallower problems take the shared-memory-ring variant
+  return stem_v2_enabled() >= 2 && kc * 8 <= 256 && (kc + kSv2KS - 1) / kSv2KS > kSv2TStages &&
+         stem_v2t_smem_bytes(cin, c, kc) <= static_cast<size_t>(kMaxSmem);
+}
+
 int launch_stem_v2(StemV2Args a, const CUtensorMap& tm, cudaStream_t st) {
   size_t smem = stem_v2_smem_bytes(a.Cin, a.C);
   if (smem > static_cast<size_t>(kMaxSmem)) return kErrUnsupported;
@@ -355,7 +363,7 @@ int launch_stem_v2(StemV2Args a, const CUtensorMap& tm, cudaStream_t st) {
   a.tma_store = (tma_store_on && a.C % 32 == 0 && a.Wout % 16 == 0 &&
                  make_tmap_f32_rows(a.y, static_cast<int64_t>(a.n_tiles) * 128, a.C, &tmo, 32, 16)) ? 1 : 0;
   if (!a.tma_store) memset(&tmo, 0, sizeof(tmo));
-  if (stem_v2_enabled() >= 2 && a.KC * 8 <= 256 && stem_v2t_smem_bytes(a.Cin, a.C, a.KC) <= static_cast<size_t>(kMaxSmem)) {
+  if (stem_v2_atmem(a.Cin, a.C, a.KC)) {
     // operand built straight into tensor memory, all weight chunks resident in shared memory
     smem = stem_v2t_smem_bytes(a.Cin, a.C, a.KC);
     static DevOnce once_t;
@@ -534,7 +542,7 @@ static int downsample_impl(const void* in, int in_dtype, int in_nchw, int batch,
         stem_v2_smem_bytes(cin, cout) <= static_cast<size_t>(kMaxSmem)) {
       // persistent, pipelined version (inference; the training forward keeps the raw conv output and stays on the kernel above)
       alignas(64) CUtensorMap tm;
-      if (make_tmap_stem_u8(in, batch, cin, hin, win, &tm)) {
+      if (make_tmap_stem_u8(in, batch, cin, hin, win, &tm, stem_v2_atmem(cin, cout, cdiv(a.K, 64)))) {
         StemV2Args sa{};
         sa.wp = static_cast<const __half*>(w_packed); sa.y = out;
         sa.Cin = cin; sa.Hout = hout; sa.Wout = wout; sa.C = cout; sa.KC = cdiv(a.K, 64);

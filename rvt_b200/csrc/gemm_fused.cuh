@@ -49,6 +49,10 @@ constexpr int kStemTileH = 8, kStemTileW = 16;          // MAP_BLOCK: a tile is 
 constexpr int kStemPatchRows = kStemTileH * 4 + 3;      // 35 input rows
 constexpr int kStemPatchPitch = 80;                     // bytes per patch row: pixels [4*ox0-16, 4*ox0+64)
 
+// K order of the uint8 stem (pack_stem_weight_u8): (kyi, ci, kx8) with ky = stem_ky(kyi) = 0, 4, 1, 5, 2, 6, 3 -- the kernel rows that read
+// the same input-row phase (iy mod 4) are adjacent, so stem_v2 can stream the input patch as four row-phase planes
+__host__ __device__ __forceinline__ int stem_ky(int kyi) { return (0x3625140 >> (4 * kyi)) & 7; }
+
 __device__ __forceinline__ int row_to_token(const RowMap& m, int row) {
   if (m.mode == MAP_IDENTITY) return row < m.n_tokens ? row : -1;
   if (m.mode == MAP_BLOCK) {
@@ -524,7 +528,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_fused_kernel(const __gri
         const int q = kc * 8 + j;                              // (ky, ci) pair of this thread's 16-byte chunk
         const bool qv = q < npairs;
         const int ky = qv ? q / Cin : 0, ci = qv ? q - ky * Cin : 0;
-        const uint32_t prow_base = s_patch + (ci * kStemPatchRows + ky) * kStemPatchPitch + 12;
+        const uint32_t prow_base = s_patch + (ci * kStemPatchRows + stem_ky(ky)) * kStemPatchPitch + 12;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int r = r0 + 32 * i;

@@ -38,12 +38,16 @@ constexpr int kSv2KS = 3;                                     // K chunks (of 64
 constexpr uint32_t kSv2TAcol = 128;                           // TMEM: accumulators [0, 128), operand ring [128, 128 + 4 * 96) = 512 columns
 constexpr int kSv2WStages = 6;                                // weight-chunk ring: deep, an L2 -> smem bulk copy takes ~1000 cycles
 constexpr uint32_t kSv2WBytes = 64 * 128;                     // one weight chunk (C <= 64 rows x 64 halves)
+constexpr int kSv2PlaneRows = kStemTileH + 1;                 // ATMEM: rows of one row-phase plane of the input patch (iy = iy0 + p + 4 k)
+__host__ __device__ inline uint32_t stem_v2_plane_bytes(int cin) {
+  return (static_cast<uint32_t>(cin) * kSv2PlaneRows * kStemPatchPitch + 127u) & ~127u;
+}
 __host__ __device__ inline uint32_t stem_v2_patch_bytes(int cin) {
   return (static_cast<uint32_t>(cin) * kStemPatchRows * kStemPatchPitch + 1023u) & ~1023u;
 }
-// ATMEM variant: ONE patch buffer, ALL weight chunks resident, no operand ring in shared memory
+// ATMEM variant: the patch as four row-phase planes, ALL weight chunks resident, no operand ring in shared memory
 __host__ __device__ inline uint32_t stem_v2t_smem_bytes(int cin, int c, int kc) {
-  return 1024 + stem_v2_patch_bytes(cin) + static_cast<uint32_t>(kc) * kSv2WBytes + 64 * (static_cast<uint32_t>(c) * 4 + 16) + 3 * 64 * 4 +
+  return 1024 + ((4 * stem_v2_plane_bytes(cin) + 1023u) & ~1023u) + static_cast<uint32_t>(kc) * kSv2WBytes + 64 * (static_cast<uint32_t>(c) * 4 + 16) + 3 * 64 * 4 +
          48 * 8 + 16 + 256 * 4 /*pair -> patch offset LUT*/;
 }
 __host__ __device__ inline uint32_t stem_v2_smem_bytes(int cin, int c) {
@@ -63,7 +67,8 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
   const int C = a.C, Cin = a.Cin, KC = a.KC, n_tiles = a.n_tiles;
   const uint32_t patch_bytes = stem_v2_patch_bytes(Cin);
   const uint32_t sP = base;                                    // [2] patches ([1] with ATMEM)
-  const uint32_t sS = sP + (ATMEM ? 1 : 2) * patch_bytes;      // [3] A chunks (none with ATMEM)
+  const uint32_t plane_bytes = stem_v2_plane_bytes(Cin);
+  const uint32_t sS = sP + (ATMEM ? ((4 * plane_bytes + 1023u) & ~1023u) : 2 * patch_bytes);      // [3] A chunks (none with ATMEM)
   const uint32_t sW = sS + (ATMEM ? 0 : kSv2Stages) * kATileBytes;      // [6] weight chunk ring / ATMEM: all KC chunks, resident
   const uint32_t sO = sW + (ATMEM ? static_cast<uint32_t>(KC) : kSv2WStages) * kSv2WBytes;     // fp32 staging of HALF a tile (64 rows), row pitch C * 4 + 16 bytes
   const uint32_t o_pitch = static_cast<uint32_t>(C) * 4 + 16;
@@ -81,6 +86,8 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
   uint64_t* w_full = bars + 24;        // [6] tx
   uint64_t* w_empty = bars + 30;       // [6] commit
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
+  uint64_t* plane_full = bars + 26;    // ATMEM [4] tx      (slots of the weight ring the ATMEM variant does not use)
+  uint64_t* plane_free = bars + 30;    // ATMEM [4] 8 builder warps
   uint32_t* s_lut = tmem_slot + 4;      // ATMEM: [KC * 8] byte offset of the patch row of K pair q = (ky, ci), ~0u = zero padding of K
 
   if (tid == 0) {
@@ -89,14 +96,20 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
       mbar_init(&acc_full[b], 1); mbar_init(&acc_free[b], kSv2Epi);
     }
     for (int s = 0; s < NST; ++s) { mbar_init(&full[s], ATMEM ? 4 : kSv2Builders / 32); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < kSv2WStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    if (ATMEM) {
+      mbar_init(&w_full[0], 1);
+      for (int pl = 0; pl < 4; ++pl) { mbar_init(&plane_full[pl], 1); mbar_init(&plane_free[pl], kSv2Builders / 32); }
+    } else {
+      for (int s = 0; s < kSv2WStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    }
     fence_mbar_init();
   }
   if (warp == 13) tmem_alloc(tmem_slot, ATMEM ? 512 : 128);
   if (ATMEM) {
     for (int q = tid; q < KC * 8; q += kSv2Threads) {
-      const int ky = q / Cin, ci = q - ky * Cin;
-      s_lut[q] = q < 7 * Cin ? static_cast<uint32_t>((ci * kStemPatchRows + ky) * kStemPatchPitch) : 0xffffffffu;
+      const int kyi = q / Cin, ci = q - kyi * Cin;
+      const int ky = stem_ky(kyi < 7 ? kyi : 0);                // plane ky & 3 holds input rows iy0 + (ky & 3) + 4 k; this row is k = oy + (ky >> 2)
+      s_lut[q] = q < 7 * Cin ? (ky & 3) * plane_bytes + static_cast<uint32_t>((ci * kSv2PlaneRows + (ky >> 2)) * kStemPatchPitch) : 0xffffffffu;
     }
   }
   for (int i = tid; i < 64; i += kSv2Threads) {
@@ -224,7 +237,8 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
       // any throughput).  Warps 4..7 / 8..11 own the four lane quarters; the two warps of a quarter take alternate steps.
       const int qt = (warp - 4) & 3, hpar = (warp - 4) >> 2;
       const int r = qt * 32 + lane;
-      const uint32_t src_row = (r >> 4) * (4 * kStemPatchPitch) + (r & 15) * 4 + 12;
+      const uint32_t src_row = (r >> 4) * kStemPatchPitch + (r & 15) * 4 + 12;      // inside a plane consecutive rows are 4 input rows apart
+      const int npairs = 7 * Cin;
       const uint32_t t_a = tmem + kSv2TAcol + (static_cast<uint32_t>(qt * 32) << 16);
       const int n_steps = (KC + kSv2KS - 1) / kSv2KS;
       const __half2 k1024 = __half2half2(__ushort_as_half(static_cast<unsigned short>(0x6400)));
@@ -232,12 +246,28 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
       uint32_t g = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         SV2_TRACE(bt == 0, it, 0);
-        mbar_wait(&patch_full[0], it & 1);
-        SV2_TRACE(bt == 0, it, 1);
         const uint32_t patch = sP + src_row;
         long long cyc_wait = 0;                                 // profiling: SM cycles the leader waited for a free operand slot
         for (int st = 0; st < n_steps; ++st, ++g) {
-          if (static_cast<int>(g & 1) != hpar) continue;
+          // planes this step reads: pairs [24 st, 24 st + 24) are (kyi, ci) with kyi = q / Cin; the plane index rises with q
+          const int q0 = st * kSv2KS * 8;
+          const int q1 = min(q0 + kSv2KS * 8, npairs) - 1;
+          const int p_lo = stem_ky(min(q0 / Cin, 6)) & 3, p_hi = q1 >= q0 ? (stem_ky(q1 / Cin) & 3) : -1;
+          // a plane is released by every builder warp once the warp is past the last step that reads it (planes 0..2 end with
+          // kyi = 1, 3, 5; plane 3 with the last pair), so its reload for the NEXT tile overlaps the rest of this tile
+          auto release = [&]() {
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+              for (int pl = 0; pl < 4; ++pl) {
+                const int last = (pl < 3 ? (2 * pl + 2) * Cin : npairs) - 1;
+                if (last >= q0 && last < q0 + kSv2KS * 8) mbar_arrive(&plane_free[pl]);
+              }
+            }
+          };
+          if (static_cast<int>(g & 1) != hpar) { release(); continue; }
+          for (int pl = p_lo; pl <= p_hi; ++pl) mbar_wait(&plane_full[pl], it & 1);
+          if (st == 0) SV2_TRACE(bt == 0, it, 1);
           const uint32_t s = g % kSv2TStages, ph = (g / kSv2TStages) & 1;
           const long long c0 = a.trace ? clock64() : 0;
           mbar_wait(&empty[s], ph ^ 1);
@@ -272,9 +302,8 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&full[s]);
+          release();
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&patch_free[0]);
         SV2_TRACE(bt == 0, it, 2);
         if (a.trace && bt == 0 && it < kTraceTiles) a.trace[(static_cast<long long>(blockIdx.x) * kTraceTiles + it) * kTracePts + 10] = cyc_wait;
       }
@@ -307,7 +336,7 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
         if (a.trace) cyc_wait += clock64() - c0;
         const uint32_t tile_a = sS + s * kATileBytes;
         const bool qv = q < npairs;
-        const uint32_t prow = patch + (ci * kStemPatchRows + ky) * kStemPatchPitch;
+        const uint32_t prow = patch + (ci * kStemPatchRows + stem_ky(ky < 7 ? ky : 0)) * kStemPatchPitch;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
@@ -348,7 +377,7 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
     // =============================================== producer ===============================================
     if (ATMEM && lane == 0 && static_cast<int>(blockIdx.x) < n_tiles) {
       tma_prefetch_desc(&tmap_in);
-      const uint32_t box_bytes = static_cast<uint32_t>(Cin) * kStemPatchRows * kStemPatchPitch;
+      const uint32_t plane_box_bytes = static_cast<uint32_t>(Cin) * kSv2PlaneRows * kStemPatchPitch;
       const uint32_t w_bytes = static_cast<uint32_t>(C) * 128;
       mbar_arrive_expect_tx(&w_full[0], w_bytes * KC);           // all weight chunks once, resident for the CTA's lifetime
       for (int kc = 0; kc < KC; ++kc)
@@ -357,9 +386,13 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int tb = tile / per_img, tt = tile - tb * per_img;
         const int ty = tt / a.nx, tx = tt - ty * a.nx;
-        mbar_wait(&patch_free[0], (it & 1) ^ 1);                 // the builders are done with the previous tile's patch (they run up to
-        mbar_arrive_expect_tx(&patch_full[0], box_bytes);        // 4 steps ahead of the MMAs, which hides this load)
-        tma_load_3d(sP, &tmap_in, tx * kStemTileW * 4 - 16, ty * kStemTileH * 4 - 3, tb * Cin, &patch_full[0]);
+        // four row-phase planes (TMA row stride 4): plane pl is free again as soon as the builders are past the kernel rows that
+        // read it, long before the tile ends, so these loads overlap the previous tile
+        for (int pl = 0; pl < 4; ++pl) {
+          mbar_wait(&plane_free[pl], (it & 1) ^ 1);
+          mbar_arrive_expect_tx(&plane_full[pl], plane_box_bytes);
+          tma_load_3d(sP + pl * plane_bytes, &tmap_in, tx * kStemTileW * 4 - 16, ty * kStemTileH * 4 - 3 + pl, tb * Cin, &plane_full[pl]);
+        }
       }
     }
     if (!ATMEM && lane == 0 && static_cast<int>(blockIdx.x) < n_tiles) {

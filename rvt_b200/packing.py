@@ -100,12 +100,17 @@ def pack_qkv_weight(w: torch.Tensor, b, dim_head: int, dhp: int = 32):
     return _swizzle_tiles(wpad.reshape(nh * 3 * dhp, c), 3 * dhp), bpad.reshape(-1).contiguous()
 
 
+STEM_KY_ORDER = (0, 4, 1, 5, 2, 6, 3)
+
+
 def pack_stem_weight_u8(w: torch.Tensor) -> torch.Tensor:
     """7x7 / stride-4 stem weight [Cout, Cin, 7, 7] for the uint8 smem-patch loader (LD_STEM):
-    K order (ky, ci, kx8) where kx8 indexes the 8 input bytes [4*ox-4, 4*ox+4) of a row, i.e. kx8 = kx + 1
+    K order (kyi, ci, kx8), ky = STEM_KY_ORDER[kyi], where kx8 indexes the 8 input bytes [4*ox-4, 4*ox+4) of a row, i.e. kx8 = kx + 1
     and kx8 = 0 carries a zero weight."""
     co, cin, ks, _ = w.shape
     assert ks == 7
     w2 = torch.zeros(co, ks, cin, 8, device=w.device)
     w2[:, :, :, 1:] = w.detach().float().permute(0, 2, 1, 3)
+    # kernel rows in the order 0, 4, 1, 5, 2, 6, 3 (csrc/gemm_fused.cuh stem_ky): rows that read the same input-row phase are adjacent
+    w2 = w2[:, list(STEM_KY_ORDER)]
     return _swizzle_tiles(w2.reshape(co, -1), co)
