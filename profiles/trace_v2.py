@@ -106,7 +106,7 @@ def trace_stem(m, pk, dev):
             dd = (tr[ok, it, i1] - tr[ok, it, i0]) / 1e3
             print(f'    {name:<40s} {dd.mean():6.2f} us  (max {dd.max():6.2f})')
         if os.environ.get('RVT_STEM_V2', '2') == '2':
-            print(f'    SM cycles per tile: builder leader waiting for a free operand slot {tr[ok, it, 10].mean():8.0f}   MMA thread waiting for the builders {tr[ok, it, 11].mean():8.0f}')
+            print(f'    SM cycles per tile: epilogue waiting for the staging buffer (previous TMA stores) {tr[ok, it, 10].mean():8.0f}   TMEM load + normalise + staging + barrier {tr[ok, it, 11].mean():8.0f}')
         else:
             print(f'    builder leader, SM cycles per tile: waiting for a free A slot {tr[ok, it, 10].mean():8.0f}   fence + arrive {tr[ok, it, 11].mean():8.0f}')
 

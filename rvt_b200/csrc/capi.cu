@@ -885,6 +885,9 @@ static int dws_conv_lstm_impl(const float* x, const float* h_prev, const float* 
   a.x = x; a.C = dim; a.hprev = h_prev; a.dw_w = dw_w; a.dw_b = dw_b; a.dws_mode = dws_mode; a.dws_ks = dws_ks;
   a.cprev = c_prev; a.hout = h_out; a.cout = c_out; a.cw = cw; a.hout16 = static_cast<__half*>(h_out_f16);
   a.gates16 = static_cast<__half*>(gates16);
+  static int fast_gates = -1;
+  if (fast_gates < 0) { const char* e = getenv("RVT_FAST_GATES"); fast_gates = e ? atoi(e) : 0; }
+  a.fast_gates = (fast_gates && !gates16) ? 1 : 0;      // never in training (the backward differentiates the exact forms)
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int n_mtiles = cdiv(n_tok, 128);
   if (lstm_v2_enabled() && dws_mode == 0 && dim <= 64 && cw == dim && !gates16 && n_mtiles > 0) {
@@ -897,7 +900,7 @@ static int dws_conv_lstm_impl(const float* x, const float* h_prev, const float* 
       LstmV2Args la{};
       la.cprev = c_prev; la.hout = h_out; la.cout = c_out; la.hout16 = static_cast<__half*>(h_out_f16);
       la.n_tokens = static_cast<int>(n_tok); la.C = dim; la.n_tiles = n_mtiles; la.has_h = h_prev != nullptr;
-      la.w = static_cast<const __half*>(w_packed); la.bias = bias_tiled;
+      la.w = static_cast<const __half*>(w_packed); la.bias = bias_tiled; la.fast_gates = a.fast_gates;
       return launch_lstm_v2(la, tx, th, tc, st);
     }
   }

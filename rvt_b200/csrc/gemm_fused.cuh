@@ -117,6 +117,7 @@ struct GemmArgs {
   const float* cprev; float* hout; float* cout; int cw;
   __half* hout16;      // optional fp16 copy of h_t (operand of the next stage's downsample conv)
   __half* gates16;     // optional fp16 [n_tokens, 4C] activated gates [f|i|o|g] (saved for the LSTM backward)
+  int fast_gates;      // 1: single-MUFU gate non-linearities (tanh.approx.f32); inference only
 };
 
 constexpr int kMaxStages = 6;
@@ -181,6 +182,11 @@ __device__ __forceinline__ float gelu_erf_grad(float v) {
 }
 __device__ __forceinline__ float sigmoid_acc(float v) { return rcp_approx(1.0f + ex2_approx(v * -1.4426950408889634f)); }
 __device__ __forceinline__ float tanh_acc(float v) { return fmaf(2.0f, sigmoid_acc(2.0f * v), -1.0f); }
+// One MUFU per gate instead of two (inference option RVT_FAST_GATES): tanh.approx.f32 (max rel. error 2^-11, PTX ISA) and
+// sigmoid(v) = 0.5 + 0.5 tanh(v / 2).  The Conv-LSTM gates are 10 MUFU per channel-token with the accurate forms -- 17 us of pure
+// MUFU time per stage per timestep at the bench shape.
+__device__ __forceinline__ float tanh_fast(float v) { float r; asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+__device__ __forceinline__ float sigmoid_fast(float v) { return fmaf(0.5f, tanh_fast(0.5f * v), 0.5f); }
 __device__ __forceinline__ void load16(const float* p, float* v) {   // p 16-byte aligned
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -785,10 +791,20 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_fused_kernel(const __gri
           const float* cpv = cpre + gi * 8;
           float hn[8], cn[8];
 #pragma unroll
+          if (a.fast_gates) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              f[e] = sigmoid_fast(f[e]); ig[e] = sigmoid_fast(ig[e]); og[e] = sigmoid_fast(og[e]); g[e] = tanh_fast(g[e]);
+              cn[e] = f[e] * cpv[e] + ig[e] * g[e];
+              hn[e] = og[e] * tanh_fast(cn[e]);
+            }
+          } else {
+#pragma unroll
           for (int e = 0; e < 8; ++e) {
             f[e] = sigmoid_acc(f[e]); ig[e] = sigmoid_acc(ig[e]); og[e] = sigmoid_acc(og[e]); g[e] = tanh_acc(g[e]);
             cn[e] = f[e] * cpv[e] + ig[e] * g[e];
             hn[e] = og[e] * tanh_acc(cn[e]);
+          }
           }
           if (a.gates16) {
             __half* gp = a.gates16 + static_cast<size_t>(etok) * 4 * C + ch0;

@@ -24,6 +24,7 @@ struct LstmV2Args {
   int n_tokens, C, n_tiles, has_h;
   const __half* w;          // pack_lstm_weight(cw = C): [1][KC][4C x 64]
   const float* bias;        // [4C] gate-major [f | i | o | g]
+  int fast_gates;           // 1: single-MUFU gate non-linearities (gemm_fused.cuh tanh_fast / sigmoid_fast)
 };
 
 constexpr int kLv2Workers = 512;
@@ -176,8 +177,13 @@ lstm_v2_kernel(const __grid_constant__ LstmV2Args a, const __grid_constant__ CUt
         for (int e = 0; e < 8; ++e) g[e] += bv[e];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          cn[q][e] = sigmoid_acc(f[e]) * cp[q][e] + sigmoid_acc(ig[e]) * tanh_acc(g[e]);
-          hn[q][e] = sigmoid_acc(og[e]) * tanh_acc(cn[q][e]);
+          if (a.fast_gates) {
+            cn[q][e] = sigmoid_fast(f[e]) * cp[q][e] + sigmoid_fast(ig[e]) * tanh_fast(g[e]);
+            hn[q][e] = sigmoid_fast(og[e]) * tanh_fast(cn[q][e]);
+          } else {
+            cn[q][e] = sigmoid_acc(f[e]) * cp[q][e] + sigmoid_acc(ig[e]) * tanh_acc(g[e]);
+            hn[q][e] = sigmoid_acc(og[e]) * tanh_acc(cn[q][e]);
+          }
         }
         if (!coalesced && live) {
           *reinterpret_cast<float4*>(a.cout + rbase + j0) = make_float4(cn[q][0], cn[q][1], cn[q][2], cn[q][3]);

@@ -165,14 +165,17 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
       // [16 tokens x 32 channels] in the 128-byte swizzle (conflict-free for row-per-thread writes) and leaves through TMA tensor
       // stores issued by one thread; otherwise padded rows and (token, chunk) threads that write whole lines.
       const int rl = row & 63;
+      long long ecyc_free = 0, ecyc_norm = 0;                   // profiling: SM cycles waiting for the staging buffer / load + normalise + barrier
       const uint32_t srow = sO + static_cast<uint32_t>(rl) * o_pitch;
       const uint32_t sbox = sO + static_cast<uint32_t>((rl >> 4) * (C >> 5)) * 2048u + static_cast<uint32_t>(rl & 15) * 128u;
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
+        const long long e0 = a.trace ? clock64() : 0;
         if (a.tma_store) {
           if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // the previous stores have read the buffer
           named_bar_sync(2, kSv2Epi);
         }
+        const long long e1 = a.trace ? clock64() : 0;
         if ((row >> 6) == half) {
 #pragma unroll 1
           for (int c0 = 0; c0 < C; c0 += 32) {
@@ -203,6 +206,7 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
         if (a.tma_store) {
           fence_proxy_async_smem();
           named_bar_sync(1, kSv2Epi);
+          if (a.trace) { ecyc_free += e1 - e0; ecyc_norm += clock64() - e1; }
           if (tid == 0) {
             const int nbx = C >> 5;
             for (int k = 0; k < 4; ++k)
@@ -225,6 +229,10 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
         named_bar_sync(2, kSv2Epi);                             // the staging buffer is free again
       }
       SV2_TRACE(tid == 0, it, 6);
+      if (ATMEM && a.trace && tid == 0 && it < kTraceTiles) {     // (overrides the builder / MMA wait counters of slots 10, 11)
+        a.trace[(static_cast<long long>(blockIdx.x) * kTraceTiles + it) * kTracePts + 10] = ecyc_free;
+        a.trace[(static_cast<long long>(blockIdx.x) * kTraceTiles + it) * kTracePts + 11] = ecyc_norm;
+      }
     }
     if (a.tma_store && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all tensor stores complete before the CTA retires
   } else if (warp < 12) {
@@ -305,7 +313,7 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
           release();
         }
         SV2_TRACE(bt == 0, it, 2);
-        if (a.trace && bt == 0 && it < kTraceTiles) a.trace[(static_cast<long long>(blockIdx.x) * kTraceTiles + it) * kTracePts + 10] = cyc_wait;
+        (void)cyc_wait;
       }
     } else {
     const int j = bt & 7;                                       // 16-byte chunk of the 128-byte operand row = one (ky, ci) pair
@@ -454,7 +462,7 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
         }
         umma_commit(&acc_full[ab]);
         SV2_TRACE(true, it, 9);
-        if (a.trace && it < kTraceTiles) a.trace[(static_cast<long long>(blockIdx.x) * kTraceTiles + it) * kTracePts + 11] = cyc_full;
+        (void)cyc_full;
       }
     }
     if (!ATMEM && lane == 0) {
