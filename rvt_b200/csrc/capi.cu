@@ -338,6 +338,18 @@ int conv_tma_enabled() {
   return v;
 }
 
+// stem output [B*Hout, Wout, C] fp32 as a 3-D tensor; box = 32 channels x 16 tokens x 4 token rows (half a stem tile), 128-byte swizzle
+bool make_tmap_stem_out(float* y, int64_t rows, int wout, int c, CUtensorMap* out) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn || (reinterpret_cast<uintptr_t>(y) & 15) || c % 32 != 0 || wout % kStemTileW != 0) return false;
+  const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(wout), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstride[2] = {static_cast<cuuint64_t>(c) * 4, static_cast<cuuint64_t>(wout) * c * 4};
+  const cuuint32_t box[3] = {32, static_cast<cuuint32_t>(kStemTileW), 4};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, y, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int stem_v2_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("RVT_STEM_V2"); v = e ? atoi(e) : 2; }    // 0: one tile per CTA (gemm_fused<LD_STEM>), 1: persistent, operand ring in smem, 2: operand in TMEM
@@ -360,8 +372,7 @@ int launch_stem_v2(StemV2Args a, const CUtensorMap& tm, cudaStream_t st) {
   alignas(64) CUtensorMap tmo;
   static int tma_store_on = -1;
   if (tma_store_on < 0) { const char* e = getenv("RVT_STEM_TMA_STORE"); tma_store_on = e ? atoi(e) : 1; }
-  a.tma_store = (tma_store_on && a.C % 32 == 0 && a.Wout % 16 == 0 &&
-                 make_tmap_f32_rows(a.y, static_cast<int64_t>(a.n_tiles) * 128, a.C, &tmo, 32, 16)) ? 1 : 0;
+  a.tma_store = (tma_store_on && a.C % 32 == 0 && make_tmap_stem_out(a.y, a.n_tiles / (a.ny * a.nx) * a.Hout, a.Wout, a.C, &tmo)) ? 1 : 0;
   if (!a.tma_store) memset(&tmo, 0, sizeof(tmo));
   if (stem_v2_atmem(a.Cin, a.C, a.KC)) {
     // operand built straight into tensor memory, all weight chunks resident in shared memory
@@ -886,7 +897,7 @@ static int dws_conv_lstm_impl(const float* x, const float* h_prev, const float* 
   a.cprev = c_prev; a.hout = h_out; a.cout = c_out; a.cw = cw; a.hout16 = static_cast<__half*>(h_out_f16);
   a.gates16 = static_cast<__half*>(gates16);
   static int fast_gates = -1;
-  if (fast_gates < 0) { const char* e = getenv("RVT_FAST_GATES"); fast_gates = e ? atoi(e) : 0; }
+  if (fast_gates < 0) { const char* e = getenv("RVT_FAST_GATES"); fast_gates = e ? atoi(e) : 1; }
   a.fast_gates = (fast_gates && !gates16) ? 1 : 0;      // never in training (the backward differentiates the exact forms)
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int n_mtiles = cdiv(n_tok, 128);

@@ -167,12 +167,12 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
       const int rl = row & 63;
       long long ecyc_free = 0, ecyc_norm = 0;                   // profiling: SM cycles waiting for the staging buffer / load + normalise + barrier
       const uint32_t srow = sO + static_cast<uint32_t>(rl) * o_pitch;
-      const uint32_t sbox = sO + static_cast<uint32_t>((rl >> 4) * (C >> 5)) * 2048u + static_cast<uint32_t>(rl & 15) * 128u;
+      const uint32_t sbox = sO + static_cast<uint32_t>(rl) * 128u;      // [channel half][4 token rows x 16 tokens][32 channels], 8 KB per half
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         const long long e0 = a.trace ? clock64() : 0;
         if (a.tma_store) {
-          if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // the previous stores have read the buffer
+          if ((tid & 31) == 0 && (tid >> 5) < (C >> 5)) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // my previous store has read the buffer
           named_bar_sync(2, kSv2Epi);
         }
         const long long e1 = a.trace ? clock64() : 0;
@@ -195,7 +195,7 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
                 o.z = fmaf((v[c4 * 4 + 2] - mean) * rstd, g.z, bb.z);
                 o.w = fmaf((v[c4 * 4 + 3] - mean) * rstd, g.w, bb.w);
               }
-              const uint32_t dst = a.tma_store ? sbox + static_cast<uint32_t>(c0 >> 5) * 2048u + ((static_cast<uint32_t>(c4) ^ (rl & 7)) << 4)
+              const uint32_t dst = a.tma_store ? sbox + static_cast<uint32_t>(c0 >> 5) * 8192u + ((static_cast<uint32_t>(c4) ^ (rl & 7)) << 4)
                                                : srow + (c0 + c4 * 4) * 4;
               asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
             }
@@ -207,11 +207,9 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
           fence_proxy_async_smem();
           named_bar_sync(1, kSv2Epi);
           if (a.trace) { ecyc_free += e1 - e0; ecyc_norm += clock64() - e1; }
-          if (tid == 0) {
-            const int nbx = C >> 5;
-            for (int k = 0; k < 4; ++k)
-              for (int h = 0; h < nbx; ++h)
-                tma_store_2d(&tmap_out, h * 32, tok0 + (half * 4 + k) * a.Wout, sO + static_cast<uint32_t>(k * nbx + h) * 2048u);
+          if ((tid & 31) == 0 && (tid >> 5) < (C >> 5)) {      // lane 0 of warp h: ONE 3-D box [4 token rows x 16 tokens x 32 channels]
+            const int h = tid >> 5;
+            tma_store_3d(&tmap_out, h * 32, tx * kStemTileW, tb * a.Hout + ty * kStemTileH + half * 4, sO + static_cast<uint32_t>(h) * 8192u);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
           continue;
@@ -234,7 +232,7 @@ stem_v2_kernel(const __grid_constant__ StemV2Args a, const __grid_constant__ CUt
         a.trace[(static_cast<long long>(blockIdx.x) * kTraceTiles + it) * kTracePts + 11] = ecyc_norm;
       }
     }
-    if (a.tma_store && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all tensor stores complete before the CTA retires
+    if (a.tma_store && (tid & 31) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all tensor stores complete before the CTA retires
   } else if (warp < 12) {
     // =============================================== builders ===============================================
     const int bt = tid - kSv2Epi;

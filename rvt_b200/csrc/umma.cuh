@@ -197,6 +197,12 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, int c0, int c1, u
                : "memory");
 }
 
+__device__ __forceinline__ void tma_store_3d(const void* tmap, int c0, int c1, int c2, uint32_t smem_src) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(smem_src)
+               : "memory");
+}
+
 // 5-D tiled TMA load (window / grid partition boxes of a channels-last fp32 tensor, attn_v2.cuh)
 __device__ __forceinline__ void tma_load_5d(uint32_t smem_dst, const void* tmap, int c0, int c1, int c2, int c3, int c4,
                                             uint64_t* bar) {
