@@ -98,6 +98,8 @@ bool make_tmap_f16_rows(const void* base, int64_t rows, int64_t cols, int64_t ld
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+int persistent_sms();
+
 template <int LOADER, int EPI>
 int launch_gemm(GemmArgs a, int n_mtiles, int n_ntiles, cudaStream_t st, const CUtensorMap* tmap = nullptr,
                 size_t extra_smem = 0, int n_splits = 1) {
@@ -110,7 +112,14 @@ int launch_gemm(GemmArgs a, int n_mtiles, int n_ntiles, cudaStream_t st, const C
   static int smem_cap_kb = -1, tma_cap_kb = -1;
   if (smem_cap_kb < 0) { const char* e = getenv("RVT_GEMM_SMEM_KB"); smem_cap_kb = e ? atoi(e) : 110; }
   if (tma_cap_kb < 0) { const char* e = getenv("RVT_TMA_SMEM_KB"); tma_cap_kb = e ? atoi(e) : 110; }
-  const size_t cap = static_cast<size_t>(LOADER == LD_TMA ? tma_cap_kb : smem_cap_kb) * 1024;
+  size_t cap = static_cast<size_t>(LOADER == LD_TMA ? tma_cap_kb : smem_cap_kb) * 1024;
+  // Few CTAs (at most one per SM: the long-K GEMMs of the wide stages, e.g. fc2 at C = 512 is 60 CTAs x 32 K chunks): nothing would share
+  // the SM anyway, so take the whole shared memory for a deeper TMA ring -- these CTAs are bound by the L2 -> SM round trip per chunk
+  static int lone_cap_kb = -1;
+  if (lone_cap_kb < 0) { const char* e = getenv("RVT_TMA_LONE_KB"); lone_cap_kb = e ? atoi(e) : 200; }
+  if (LOADER == LD_TMA && static_cast<long long>(n_mtiles) * n_ntiles * (n_splits > 1 ? n_splits : 1) <= persistent_sms() &&
+      static_cast<size_t>(lone_cap_kb) * 1024 > cap)
+    cap = static_cast<size_t>(lone_cap_kb) * 1024;
   if (LOADER == LD_TMA && kc_cta > stages) stages = kc_cta < kMaxStages ? kc_cta : kMaxStages;
   while (stages > 2 && gemm_smem_bytes(stages, a.BN, extra_smem) > cap) --stages;
   while (stages > 1 && gemm_smem_bytes(stages, a.BN, extra_smem) > static_cast<size_t>(kMaxSmem)) --stages;

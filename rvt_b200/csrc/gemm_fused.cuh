@@ -120,7 +120,7 @@ struct GemmArgs {
   int fast_gates;      // 1: single-MUFU gate non-linearities (tanh.approx.f32); inference only
 };
 
-constexpr int kMaxStages = 6;
+constexpr int kMaxStages = 8;
 constexpr uint32_t kATileBytes = 128 * 128;   // 128 rows x 64 fp16
 
 constexpr int kWorkers = 256;                 // 8 producer / epilogue warps
