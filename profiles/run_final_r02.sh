@@ -4,7 +4,7 @@ cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/final_tests.log 2>&1; echo "rc=$?" >> gpurun_out/final_tests.log; tail -3 gpurun_out/final_tests.log
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/final_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/final_smoke.log
-timeout 900 python bench.py > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err; echo "bench rc=$?"; head -c 300 gpurun_out/final_bench.json; echo
+timeout 900 python bench.py > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err; echo "bench rc=$?"; head -c 300 gpurun_out/final_bench.json; echo; grep -v Warning gpurun_out/final_bench.err | tail -5
 timeout 600 python bench.py --impl reference > gpurun_out/final_bench_ref.json 2> gpurun_out/final_bench_ref.err; echo "ref rc=$?"; head -c 300 gpurun_out/final_bench_ref.json; echo
 # launch list of the bench command (cold-cache, serialised: shares, not absolutes)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/final_launches.csv python bench.py --steps 1 --warmup 1 --extras '' --no-cpu-baseline > gpurun_out/final_launches_bench.log 2>&1; echo "launch list rc=$?"
@@ -16,4 +16,8 @@ timeout 300 ncu --set full --clock-control none -k regex:^voxel -c 2 -f -o gpuru
 for w in attn mlp; do timeout 120 python profiles/trace_v2.py $w > gpurun_out/final_trace_$w.log 2>&1; done
 timeout 120 python profiles/trace_v2.py stem > gpurun_out/final_trace_stem.log 2>&1
 timeout 200 python profiles/op_bench.py --json gpurun_out/final_opbench.json > gpurun_out/final_opbench.log 2>&1
-ls -la gpurun_out/*.ncu-rep
+# summarise on the box; the 48-kernel report is too large to travel (gpurun_out/ is capped at 64 MiB), its raw CSV export is not
+python profiles/ncu_table.py gpurun_out/r02_step.ncu-rep gpurun_out/r02_voxel.ncu-rep --csv gpurun_out/ncu_r02_csv > gpurun_out/ncu_r02_table.md 2> gpurun_out/ncu_table.err; echo "ncu table rc=$?"
+ls -la gpurun_out/*.ncu-rep gpurun_out/ncu_r02_csv
+rm -f gpurun_out/r02_step.ncu-rep
+du -sh gpurun_out

@@ -112,5 +112,5 @@ def pack_stem_weight_u8(w: torch.Tensor) -> torch.Tensor:
     w2 = torch.zeros(co, ks, cin, 8, device=w.device)
     w2[:, :, :, 1:] = w.detach().float().permute(0, 2, 1, 3)
     # kernel rows in the order 0, 4, 1, 5, 2, 6, 3 (csrc/gemm_fused.cuh stem_ky): rows that read the same input-row phase are adjacent
-    w2 = w2[:, list(STEM_KY_ORDER)]
+    w2 = torch.stack([w2[:, k] for k in STEM_KY_ORDER], dim=1)      # no index tensor: re-packing must stay capturable in a CUDA graph
     return _swizzle_tiles(w2.reshape(co, -1), co)
