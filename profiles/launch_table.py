@@ -19,6 +19,8 @@ def load(path):
 
 if __name__ == '__main__':
     rows = load(sys.argv[1])
+    # the capture starts at process start: drop PyTorch's own kernels (weight packing, fills) and keep this library's
+    rows = [r for r in rows if not (r[0].startswith('at::') or r[0].startswith('<unnamed>') or 'elementwise' in r[0])]
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 52
     print(f'{len(rows)} launches; first {n}:')
     for name, grid, us in rows[:n]:
