@@ -17,6 +17,8 @@ def main():
     print('| config | operator outputs | worst rel-L2 (bar 1e-3) | worst rel-max |')
     print('|---|---|---|---|')
     for f in sorted(glob.glob(os.path.join(G, 'op_parity_*.json'))):
+        if '.' in os.path.basename(f)[:-5]:
+            continue                     # variant runs (tests/test_gpu_variants.py) are listed separately below
         rows = json.load(open(f))
         l2 = max(r[-2] if isinstance(r[-1], float) and len(r) >= 4 else r[-1] for r in rows) if rows else 0.0
         try:
@@ -34,6 +36,14 @@ def main():
         steps = max(r[0] for r in rows) + 1
         stem = [r[2] for r in rows if r[0] == 0 and r[1].endswith('stages.0.downsample')]
         print(f"| {os.path.basename(f)[7:-5]} | {steps} | {(stem[0] if stem else float('nan')):.2e} | {max(r[2] for r in rows):.2e} |")
+    var = sorted(f for f in glob.glob(os.path.join(G, 'op_parity_*.json')) if '.' in os.path.basename(f)[:-5])
+    if var:
+        print('\nKernel variants behind the runtime switches (`tests/test_gpu_variants.py`; same per-operator test):\n')
+        print('| config . variant | operator outputs | worst rel-L2 | worst rel-max |')
+        print('|---|---|---|---|')
+        for f in var:
+            rows = json.load(open(f))
+            print(f"| {os.path.basename(f)[10:-5]} | {len(rows)} | {max(r[2] for r in rows):.2e} | {max(r[3] for r in rows):.2e} |")
     env = os.path.join(G, 'envelope_sequence.json')
     if os.path.exists(env):
         rows = json.load(open(env))

@@ -102,7 +102,8 @@ def test_each_operator_with_oracle_inputs(name):
             rec(step, pre + 'lstm.c', cg, o_states[s][1].permute(0, 2, 3, 1))
             cur, cur_nchw = o_states[s][0].permute(0, 2, 3, 1).contiguous().to(dev), False
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
-    with open(os.path.join(ROOT, 'gpurun_out', f'op_parity_{name}.json'), 'w') as f:
+    tag = os.environ.get('RVT_PARITY_TAG', '')            # tests/test_gpu_variants.py: keep the variants' numbers apart
+    with open(os.path.join(ROOT, 'gpurun_out', f'op_parity_{name}{tag}.json'), 'w') as f:
         json.dump(rows, f, indent=1)
     bad = [r for r in rows if not (r[2] <= TOL_L2 and r[3] <= TOL_MAX)]
     worst = max(r[2] for r in rows), max(r[3] for r in rows)
