@@ -434,7 +434,7 @@ static int rvt_gelu_f16x2() {
 
 static int rvt_wide_bn() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("RVT_WIDE_BN"); v = e ? atoi(e) : 128; }
+  if (v < 0) { const char* e = getenv("RVT_WIDE_BN"); v = e ? atoi(e) : 256; }      // measured: 64: -8 %, 128: base, 256: +1.9 %, 512: -5 % frames/s
   return v;
 }
 
