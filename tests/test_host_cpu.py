@@ -72,7 +72,7 @@ def test_tiling_helpers(built_lib):
     L = _lib.lib()
     assert L.rvt_abi_version() == 1
     assert [L.rvt_tile_n(n, k) for n, k in ((64, 64), (192, 64), (256, 64), (1536, 512), (144, 48), (512, 2048), (768, 256))] == \
-        [64, 96, 128, 128, 48, 128, 128]
+        [64, 96, 128, 256, 48, 256, 256]           # narrow stages: one N tile up to 128; wide stages (min(n, k) >= 256): tiles of 256
     assert [L.rvt_lstm_cw(c) for c in (32, 48, 64, 96, 192, 512)] == [32, 48, 64, 48, 64, 64]
     assert L.rvt_rows_per_group(60) == 64 and L.rvt_rows_per_group(80) == 128 and L.rvt_rows_per_group(129) < 0
     assert L.rvt_attention_scratch_rows(8, 96, 160, 6, 10) == 2048 * 64
