@@ -65,7 +65,8 @@ int rvt_stacked_histogram(const int64_t* x, const int64_t* y, const int64_t* pol
  * the input is first re-laid out space-to-depth so every conv tap is a 16-byte vector load, and
  * w_packed must come from packing.pack_stem_weight_s2d().  NULL selects the generic gather path.
  * stem_mode: 0/1 = paths above; 2 = uint8 NCHW 7x7/s4 stem with the input patch staged in shared memory
- * (needs rvt_stem_u8_ok(); w_packed from packing.pack_stem_weight_u8(); no scratch).
+ * (needs rvt_stem_u8_ok(); w_packed from packing.pack_stem_weight_u8(): K order (kyi, ci, kx8) with kernel rows
+ * ky = 0, 4, 1, 5, 2, 6, 3 and kx8 = kx + 1 (kx8 = 0 carries zero weights); no scratch).
  * Channels-last inputs (stages 2-4) with Cout >= 256: `s2d_scratch` is instead an optional split-K workspace, f32
  * [rvt_conv_split_k(n_tokens, Cout, K)][n_tokens, Cout]; NULL = one K loop per CTA. */
 int rvt_downsample_cf2cl(const void* in, int in_dtype, int in_nchw, int batch, int cin, int hin, int win,

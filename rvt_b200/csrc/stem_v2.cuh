@@ -1,18 +1,25 @@
-// Stem of stage 1, persistent + pipelined version: ConvDownsampling_Cf2Cl with the 7x7 / stride-4 / pad-3 conv on uint8 NCHW
-// event histograms, LayerNorm over the C output channels and the optional mask token
-// (reference maxvit.py:161-178, maxvit_rnn.py:174-176).  Same arithmetic as gemm_fused<LD_STEM, EP_LN> (fp16 operands that are
-// exact for uint8 counts, fp32 accumulate, two-pass LayerNorm), different schedule: the one-tile-per-CTA version serialises
-// patch load -> 18 operand builds -> epilogue inside a CTA; here one CTA per SM keeps all three busy at once.
+// Stem of stage 1, persistent + pipelined: ConvDownsampling_Cf2Cl with the 7x7 / stride-4 / pad-3 conv on uint8 NCHW event
+// histograms, LayerNorm over the C output channels and the optional mask token (reference maxvit.py:161-178,
+// maxvit_rnn.py:174-176).  Same arithmetic as gemm_fused<LD_STEM, EP_LN> (fp16 operands that are exact for uint8 counts, fp32
+// accumulate, two-pass LayerNorm); the one-tile-per-CTA version serialises patch load -> 18 operand builds -> epilogue inside a
+// CTA, here one CTA per SM keeps the roles busy at once.  A tile = 8 x 16 output tokens of one sample = 128 accumulator rows;
+// K = (kyi, ci, kx8) = 7 * Cin * 8 in chunks of 64, kernel rows in the order ky = stem_ky(kyi) = 0, 4, 1, 5, 2, 6, 3.
 //
-//   tile       8 x 16 output tokens of one sample = 128 accumulator rows; K = (ky, ci, kx8) = 7 * Cin * 8 in chunks of 64
-//   producer   one thread: the [Cin x 35 x 80] uint8 input patch of tile i+1 by ONE 3-D TMA box (out-of-image rows / columns and
-//              the rows of a zero-padded model resolution are zero-filled by the TMA unit) into the other half of a double
-//              buffer; the packed weight chunk of every K step by a bulk copy (the weights stay in L2)
-//   builders   8 warps: patch bytes -> fp16 -> SW128 K-major A chunk (u8 -> fp16 exactly by byte permute, gemm_fused.cuh)
-//              into a 3-deep ring shared with the weight chunks
-//   MMA        one thread: 4 tcgen05.mma (128 x C x 16) per chunk into one of TWO accumulators (TMEM columns [64 b, 64 b + C))
-//   epilogue   4 warps, thread = token = TMEM lane: the whole row in registers -> LayerNorm -> padded fp32 staging tile ->
-//              (token, 16-byte chunk) coalesced stores; runs on tile i while the builders are already on tile i+1
+// stem_v2_kernel<ATMEM = true> (default; DESIGN.md 4.1b has the measurements that led here):
+//   producer   one thread: ALL packed weight chunks once (resident, 144 KB at C = 64); per tile the uint8 input patch as FOUR
+//              row-phase planes (input rows iy0 + p + 4 k: one 3-D TMA box each with row stride 4; out-of-image rows / columns
+//              and the rows of a zero-padded model resolution are the TMA unit's zero fill).  Plane p is dead once the kernel
+//              rows that read it are done (2/7, 4/7, 6/7, 7/7 of the K loop), so its reload for the next tile overlaps this one
+//   builders   8 warps, thread = tile row = TMEM lane: patch bytes -> fp16 (exact byte-permute trick) in registers -> tcgen05.st
+//              into a 4-slot OPERAND RING IN TENSOR MEMORY, one slot = a step of three K chunks (96 packed columns); patch-row
+//              offsets of the (kyi, ci) pairs come from a small shared-memory table
+//   MMA        one thread: TS-form tcgen05.mma (A from tensor memory, B = resident weight chunk), 12 MMAs per hand-off, TWO
+//              accumulators (TMEM columns [64 b, 64 b + C)); ring at columns [128, 512)
+//   epilogue   4 warps, thread = token = TMEM lane: row statistics from one TMEM round trip, normalised rows into
+//              [4 token rows x 16 tokens x 32 channels] boxes in the 128-byte swizzle, out through 3-D TMA tensor stores
+//              (per-thread coalesced stores when C is not a multiple of 32); runs on tile i while the builders are on tile i+1
+// stem_v2_kernel<false> (RVT_STEM_V2=1, and shapes the tensor-memory variant does not take): operand chunks built smem -> smem
+// into a 3-deep ring, weight chunks streamed through a 6-deep ring, two full patches; same epilogue.
 #pragma once
 #include "attn_v2.cuh"
 

@@ -99,6 +99,29 @@ def test_pack_linear_weight_layout():
     assert torch.equal(got, ref.reshape(-1))
 
 
+def test_stem_weight_u8_k_order():
+    """pack_stem_weight_u8: K = (kyi, ci, kx8) with kernel rows in the row-phase order the stem kernels assume
+    (csrc/gemm_fused.cuh stem_ky: 0, 4, 1, 5, 2, 6, 3), kx8 = kx + 1 and a zero weight in slot kx8 = 0."""
+    from rvt_b200 import packing
+    assert packing.STEM_KY_ORDER == tuple((0x3625140 >> (4 * i)) & 7 for i in range(7))      # == stem_ky(i) in the CUDA header
+    torch.manual_seed(0)
+    co, cin = 32, 3
+    w = torch.randn(co, cin, 7, 7)
+    got = packing.pack_stem_weight_u8(w).reshape(-1)
+    k = 7 * cin * 8
+    kc = (k + 63) // 64
+    ref = torch.zeros(1, kc, co * 64, dtype=torch.float16)
+    w16 = w.to(torch.float16)
+    for r in range(co):
+        for kyi, ky in enumerate(packing.STEM_KY_ORDER):
+            for ci in range(cin):
+                for kx in range(7):
+                    kk = (kyi * cin + ci) * 8 + kx + 1
+                    c, within = divmod(kk % 64, 8)
+                    ref[0, kk // 64, (r * 128 + ((c ^ (r & 7)) << 4) + within * 2) // 2] = w16[r, ci, ky, kx]
+    assert torch.equal(got, ref.reshape(-1))
+
+
 def test_lstm_row_order():
     from rvt_b200 import packing
     order = packing.lstm_row_order(8, 4).tolist()
