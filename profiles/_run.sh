@@ -1,4 +1,3 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 400 python -m pytest tests -q -x -m gpu > gpurun_out/final2_tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/final2_tests.log
-timeout 300 python bench.py > gpurun_out/final2_bench.json 2> gpurun_out/final2_bench.err; echo "bench rc=$?"; head -c 200 gpurun_out/final2_bench.json; echo; grep -v Warning gpurun_out/final2_bench.err | tail -3
+timeout 150 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/final2_launches.csv python bench.py --steps 1 --warmup 1 --extras '' --no-cpu-baseline > gpurun_out/final2_launches_bench.log 2>&1; echo "launch list rc=$?"
